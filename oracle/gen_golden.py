@@ -1,0 +1,161 @@
+"""TEST INFRASTRUCTURE ONLY. Generates tests/golden/*.npz from the compiled reference.
+
+Run in the development container (needs /root/reference and ``make -C oracle ref``):
+
+    python oracle/gen_golden.py [--only NAME] [--threads T]
+
+Every fixture is produced by the reference's *own* md_interface / force_calculation /
+compute_energy (oracle/_ref/npsl_ref, unmodified sources); this script only chooses the flags
+and stores what the driver prints, rounded once from long double to float64.
+
+A state "at step K" is obtained by running the reference from scratch for K steps (its loop is
+monolithic, src/newmd.cpp:96), with -W K so that compute_energy has run on the last step
+(src/newmd.cpp:174).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import refdump  # noqa: E402
+from np_shape_lab_b200 import mesh as M  # noqa: E402
+
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+DISC = ["-q", "600", "-c", "0.005", "-t", "1", "-v", "1", "-b", "40", "-s", "40"]
+ROD = ["-q", "600", "-c", "0.01", "-t", "1", "-v", "1", "-b", "40", "-s", "40"]
+JANUS = DISC + ["-N", "2", "-p", "0.5"]
+BUCKLED_README = ["-q", "0", "-c", "0.005", "-t", "0", "-v", "0", "-b", "1", "-s", "1000", "-B", "y"]
+BUCKLING_CTRL = ["-q", "0", "-B", "y", "-b", "1", "-s", "1000"]  # BASELINE.json configs[2] literal: -t 1 -v 1 stay
+
+# name: (mesh source, D, flags, full-state steps, scalar-only trajectory steps)
+CONFIGS = {
+    "disc_D4": ("ref:3_4", 4, DISC, [0, 1, 2], [250, 500, 750, 1000]),
+    "rod_D4": ("ref:3_4", 4, ROD, [0, 1], []),
+    "janus_D4": ("ref:3_4", 4, JANUS, [0, 1], []),
+    "buckled_D4": ("ref:3_4", 4, BUCKLED_README, [0, 1], [500, 1000]),
+    "janus_D8": ("ref:3_8", 8, JANUS, [0, 1], [250, 500, 750, 1000]),
+    "buckling_D8": ("ref:3_8", 8, BUCKLING_CTRL, [0, 1], [500, 1000]),
+    "disc_ico6": ("ico:6", 6, DISC, [0, 1], []),  # synthetic class-I icosphere, 362 vertices
+}
+
+FULL_KEYS = ["pos", "vel", "force", "bforce", "sforce", "tforce", "vforce", "pforce", "itsS", "face_area",
+             "face_volume"]
+
+
+def build(name: str, threads: int | None) -> None:
+    src, D, flags, full_steps, traj_steps = CONFIGS[name]
+    scratch = os.path.join("/tmp", "npsl_golden")
+    os.makedirs(scratch, exist_ok=True)
+    if src.startswith("ref:"):
+        mesh_file = os.path.join(REF, "bin", "infiles", src[4:] + ".dat")
+        mesh = M.load_dat(mesh_file)
+    else:
+        mesh = M.icosphere(int(src[4:]))
+        mesh_file = os.path.join(scratch, "ico_%s.dat" % src[4:])
+        M.write_dat(mesh_file, mesh)
+    wd = refdump.make_workdir(mesh_file, D, root=scratch)
+    out = {}
+    first = None
+    for k in full_steps:
+        d = refdump.dump_at_step(wd, D, flags, k, threads=threads, writedata=max(k, 1) if k >= 3 else 500)
+        if first is None:
+            first = d
+            assert np.array_equal(d["edges"], mesh.edges), "edge order differs from file order"
+            assert np.array_equal(d["faces"], mesh.faces), "face winding differs from loader"
+            out["pos0"] = mesh.pos
+            out["edges"] = d["edges"]
+            out["faces"] = d["faces"]
+            out["l0"] = d["l0"]
+            out["q"] = d["q"]
+            out["params"] = d["params"]
+        for key in FULL_KEYS:
+            out["k%d_%s" % (k, key)] = d[key]
+        out["k%d_scalars" % k] = d["scalars"]
+        out["k%d_mesh_bath" % k] = d["mesh_bath"]
+        out["k%d_ions_bath" % k] = d["ions_bath"]
+        print(name, "step", k, "E=%.12g" % d["energy"], flush=True)
+    for k in traj_steps:
+        d = refdump.dump_at_step(wd, D, flags, k, threads=threads, writedata=k)
+        out["k%d_scalars" % k] = d["scalars"]
+        out["k%d_mesh_bath" % k] = d["mesh_bath"]
+        out["k%d_ions_bath" % k] = d["ions_bath"]
+        if k == traj_steps[-1]:
+            out["k%d_pos" % k] = d["pos"]
+        print(name, "step", k, "A=%.10g U=%.10g E=%.10g" % (d["total_area"], d["penergy"], d["energy"]), flush=True)
+    out["full_steps"] = np.array(full_steps, dtype=np.int64)
+    out["traj_steps"] = np.array(traj_steps, dtype=np.int64)
+    out["scalar_names"] = np.array(refdump.SCALARS)
+    out["param_names"] = np.array(refdump.PARAMS)
+    out["flags"] = np.array(" ".join(["-D", str(D)] + flags))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    shutil.rmtree(wd, ignore_errors=True)
+
+
+def readme_series() -> None:
+    """The reference's shipped golden series (examples/*_Control, 6 significant digits) and the
+    README's final A/U/E (README.md:33,41,47,53) as one small JSON fixture."""
+    ex = {
+        "disc_D4": "HomogeneouslyCharged_Disc_Control",
+        "rod_D4": "HomogeneouslyCharged_Rod_Control",
+        "janus_D4": "InhomogeneouslyCharged_Hemisphere_Control",
+        "buckled_D4": "Uncharged_Buckled_Control",
+    }
+    readme = {
+        "disc_D4": {"A": 15.675, "U": 2620.98, "E": 2699.97},
+        "rod_D4": {"A": 13.259, "U": 1919.14, "E": 1939.96},
+        "janus_D4": {"A": 12.53, "U": 1224.0, "E": 1437.0},
+        "buckled_D4": {"A": 12.3795, "U": 26.86, "E": 127.69},
+    }
+    out = {}
+    for name, d in ex.items():
+        base = os.path.join(REF, "examples", d)
+
+        def table(fn):
+            rows = []
+            for line in open(os.path.join(base, fn)):
+                t = line.split()
+                if t:
+                    rows.append([float(x) for x in t])
+            return rows
+
+        out[name] = {
+            "flags": " ".join(CONFIGS[name][2]),
+            "readme_final": readme[name],
+            "energy_nanomembrane": table("energy_nanomembrane.dat"),
+            "energy_in_parts": table("energy_in_parts_kE_bE_sE_tE_ljE_esE.dat"),
+            "area": table("area.dat"),
+            "volume": table("volume.dat"),
+        }
+    with open(os.path.join(GOLD, "reference_examples.json"), "w") as fh:
+        json.dump(out, fh)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    ap.add_argument("--threads", type=int, default=None)
+    a = ap.parse_args()
+    if not refdump.have_ref():
+        raise SystemExit("build oracle/_ref first: make -C oracle ref")
+    os.makedirs(GOLD, exist_ok=True)
+    readme_series()
+    for name in CONFIGS:
+        if a.only and a.only != name:
+            continue
+        build(name, a.threads)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,366 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into, imported by, or executed from the product path.
+//
+// Driver for the reference's own, unmodified translation units (compiled in place from
+// /root/reference/src by oracle/Makefile into oracle/_ref/). It stands in for src/main.cpp,
+// which cannot be built here (boost::program_options / boost::filesystem are absent), and
+// performs the same set-up sequence before handing over to the reference's md_interface /
+// force_calculation / INTERFACE::compute_energy:
+//
+//   unit scalings            src/main.cpp:196-210
+//   constants                src/main.cpp:212-230
+//   set_up + Debye length    src/main.cpp:231-239
+//   discretize + charges     src/main.cpp:242-248
+//   dressup + reference A,V  src/main.cpp:262-265
+//   LJ parameters            src/main.cpp:268-273
+//   thermostat chains        src/main.cpp:276-290
+//   masses                   src/main.cpp:293-294
+//   MPI row partition        src/main.cpp:448-465
+//   md_interface             src/main.cpp:467
+//
+// Modes
+//   --mode dump  : run md_interface for --steps K (K=0 -> only force_calculation_init and
+//                  compute_energy(0)), then print the full state with 21 significant digits
+//                  (long double) to --out. Used to generate tests/golden/.
+//   --mode run   : run md_interface for --steps K exactly as the CLI would (series files land
+//                  in <cwd>/outfiles), print wall time. Used as CPU baseline for small meshes.
+//   --mode force : time --reps calls of force_calculation restricted to mesh rows
+//                  [--row-lo, --row-hi] (the reference's own MPI row slice, src/main.cpp:448-455),
+//                  print JSON. Used as CPU baseline for the synthetic large meshes.
+//
+// Run from a working directory that holds infiles/3_<D>.dat and an (empty) outfiles/ directory.
+#include "utility.h"
+#include "interface.h"
+#include "vertex.h"
+#include "edge.h"
+#include "face.h"
+#include "control.h"
+#include "functions.h"
+#include "thermostat.h"
+#include "newforces.h"
+#include "newenergies.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+void md_interface(INTERFACE &, vector<PARTICLE> &, vector<THERMOSTAT> &, vector<THERMOSTAT> &, CONTROL &, char, char,
+                  char, const double scalefactor, double box_halflength);
+
+// globals the reference declares extern in src/mpi_utility.h:7-16 and defines in src/main.cpp:64-74
+unsigned int lowerBoundMesh;
+unsigned int upperBoundMesh;
+unsigned int sizFVecMesh;
+int lowerBoundIons;
+int upperBoundIons;
+int sizFVecIons;
+unsigned int extraElementsIons;
+mpi::environment env;
+mpi::communicator world;
+
+namespace {
+
+struct Options {
+    std::string mode = "dump";
+    std::string out = "dump.txt";
+    double R = 10, q = 600, c = 0.005, t = 1, v = 1, b = 40, s = 40;
+    char B = 'n', F = 'n', H = 'n', G = 'N';
+    int N = 1;
+    double p = 0.5;
+    int steps = 0;
+    double dt = 0.001, T = 0.001, Qm = 0.01, Qi = 0.01;
+    unsigned D = 4, C = 5;
+    int writedata = 500;
+    long row_lo = 0, row_hi = -1;
+    int reps = 1;
+};
+
+bool parse(int argc, char **argv, Options &o) {
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto need = [&](const char *name) -> const char * {
+            if (i + 1 >= argc) {
+                std::fprintf(stderr, "missing value for %s\n", name);
+                std::exit(2);
+            }
+            return argv[++i];
+        };
+        if (a == "--mode") o.mode = need("--mode");
+        else if (a == "--out") o.out = need("--out");
+        else if (a == "-R") o.R = atof(need("-R"));
+        else if (a == "-q") o.q = atof(need("-q"));
+        else if (a == "-c") o.c = atof(need("-c"));
+        else if (a == "-t") o.t = atof(need("-t"));
+        else if (a == "-v") o.v = atof(need("-v"));
+        else if (a == "-b") o.b = atof(need("-b"));
+        else if (a == "-s") o.s = atof(need("-s"));
+        else if (a == "-B") o.B = need("-B")[0];
+        else if (a == "-F") o.F = need("-F")[0];
+        else if (a == "-H") o.H = need("-H")[0];
+        else if (a == "-G") o.G = need("-G")[0];
+        else if (a == "-N") o.N = atoi(need("-N"));
+        else if (a == "-p") o.p = atof(need("-p"));
+        else if (a == "-S" || a == "--steps") o.steps = atoi(need("-S"));
+        else if (a == "-d") o.dt = atof(need("-d"));
+        else if (a == "-T") o.T = atof(need("-T"));
+        else if (a == "-Q") o.Qm = atof(need("-Q"));
+        else if (a == "-Y") o.Qi = atof(need("-Y"));
+        else if (a == "-D") o.D = (unsigned) atoi(need("-D"));
+        else if (a == "-C") o.C = (unsigned) atoi(need("-C"));
+        else if (a == "-W") o.writedata = atoi(need("-W"));
+        else if (a == "--row-lo") o.row_lo = atol(need("--row-lo"));
+        else if (a == "--row-hi") o.row_hi = atol(need("--row-hi"));
+        else if (a == "--reps") o.reps = atoi(need("--reps"));
+        else {
+            std::fprintf(stderr, "unknown option %s\n", a.c_str());
+            return false;
+        }
+    }
+    return true;
+}
+
+void pv(FILE *f, const char *name, size_t i, VECTOR3D &a) {
+    std::fprintf(f, "%s %zu %.21Lg %.21Lg %.21Lg\n", name, i, a.x, a.y, a.z);
+}
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    Options o;
+    if (!parse(argc, argv, o)) return 2;
+
+    INTERFACE boundary;
+    CONTROL mdremote;
+    vector<PARTICLE> counterions;  // explicit counterions are a "next" row; always empty here
+
+    boundary.sigma_a = o.t;
+    boundary.sigma_v = o.v;
+    boundary.bkappa = o.b;
+    boundary.sconstant = o.s;
+    mdremote.steps = o.steps;
+    mdremote.timestep = o.dt;
+    mdremote.anneal = 'y';
+    mdremote.annealfreq = 50000;
+    mdremote.annealDuration = 5000;
+    mdremote.TAnnealFac = 1.25;
+    mdremote.moviestart = 1;
+    mdremote.offfreq = 2500;
+    mdremote.moviefreq = 1000;
+    mdremote.povfreq = 100000;
+    mdremote.writedata = o.writedata;
+
+    const double unit_radius_sphere = o.R;
+    double box_halflength = 1.0;
+    double counterion_diameter = 0.6 / unit_radius_sphere;
+
+    double dynePerCm_Scalefactor = pow(10, -14) * (pow(unit_radius_sphere, 2) / unitenergy);
+    boundary.sigma_a = (dynePerCm_Scalefactor * boundary.sigma_a);
+    double atmPerNmThird_Scalefactor =
+        (1.01325 * pow(10, 5)) * pow(10, -27) * (pow(unit_radius_sphere, 6) / (unitenergy * pow(10, -7)));
+    boundary.sigma_v = atmPerNmThird_Scalefactor * boundary.sigma_v;
+    const double scalefactor = epsilon_water * lB_water / unit_radius_sphere;
+
+    unsigned int chain_length = o.C;
+    double Q_mesh = o.Qm, Q_ion = o.Qi, T = o.T;
+    if (chain_length == 1) Q_mesh = 0;
+    if (chain_length == 1) Q_ion = 0;
+    mdremote.QAnnealFac = 1.00 + (mdremote.TAnnealFac / 10.0);
+    char constraintForm = 'L';
+    double lambda_v = 0, lambda_a = 0;
+    boundary.lambda_l = 0;
+    double z_out = 1;
+    boundary.ein = epsilon_water;
+    boundary.eout = epsilon_water;
+    boundary.set_up(unit_radius_sphere);
+    if (o.c == 0)
+        boundary.inv_kappa_out = 100000000;
+    else
+        boundary.inv_kappa_out = (0.257 / sqrt(z_out * boundary.lB_out * unit_radius_sphere * o.c)) / unit_radius_sphere;
+
+    boundary.discretize(3, o.D);
+    boundary.assign_random_q_values(o.q, 1.0, o.N, o.p, o.F, o.H);
+    boundary.dressup(lambda_a, lambda_v);
+    boundary.ref_area = boundary.total_area;
+    boundary.ref_volume = boundary.total_volume;
+
+    boundary.lj_length_mesh_mesh = 0.1 * boundary.avg_edge_length;
+    double meshPointRadius = 0.5 * boundary.avg_edge_length;
+    boundary.lj_length_mesh_ions = ((2.0 * meshPointRadius + counterion_diameter) / 2.0);
+    boundary.elj = 1.0;
+
+    vector<THERMOSTAT> mesh_bath, ions_bath;
+    if (chain_length == 1) {
+        mesh_bath.push_back(THERMOSTAT(0, T, 3 * boundary.V.size(), 0.0, 0, 0));
+        ions_bath.push_back(THERMOSTAT(0, T, 3 * counterions.size(), 0.0, 0, 0));
+    } else {
+        mesh_bath.push_back(THERMOSTAT(Q_mesh, T, 3 * boundary.V.size(), 0, 0, 0));
+        ions_bath.push_back(THERMOSTAT(Q_ion, T, 3 * counterions.size(), 0, 0, 0));
+        while (mesh_bath.size() != chain_length - 1) mesh_bath.push_back(THERMOSTAT(Q_mesh, T, 1, 0, 0, 0));
+        while (ions_bath.size() != chain_length - 1) ions_bath.push_back(THERMOSTAT(Q_ion, T, 1, 0, 0, 0));
+        mesh_bath.push_back(THERMOSTAT(0, T, 3 * boundary.V.size(), 0.0, 0, 0));
+        ions_bath.push_back(THERMOSTAT(0, T, 3 * counterions.size(), 0.0, 0, 0));
+    }
+    for (unsigned int i = 0; i < boundary.V.size(); i++) boundary.V[i].m = 1.0;
+    boundary.dressup(lambda_a, lambda_v);
+
+    // single-rank partition of src/main.cpp:448-465
+    lowerBoundMesh = 0;
+    upperBoundMesh = boundary.V.size() - 1;
+    sizFVecMesh = boundary.V.size();
+    lowerBoundIons = 0;
+    upperBoundIons = -1;
+    sizFVecIons = 0;
+
+    const size_t N = boundary.V.size();
+
+    if (o.mode == "force") {
+        // One rank's row slice of the reference's decomposition; everything else in
+        // force_calculation (mesh terms) is evaluated in full, as on every MPI rank.
+        long lo = o.row_lo, hi = (o.row_hi < 0 ? (long) N - 1 : o.row_hi);
+        if (hi > (long) N - 1) hi = (long) N - 1;
+        lowerBoundMesh = (unsigned) lo;
+        upperBoundMesh = (unsigned) hi;
+        sizFVecMesh = (unsigned) (hi - lo + 1);
+        initialize_velocities_to_zero(boundary.V, counterions);
+        double best = 1e300, total = 0;
+        for (int r = 0; r < o.reps; r++) {
+            double t0 = now_s();
+            force_calculation(boundary, counterions, scalefactor, o.B);
+            double t1 = now_s();
+            total += t1 - t0;
+            if (t1 - t0 < best) best = t1 - t0;
+        }
+        int threads = 1;
+#pragma omp parallel
+        {
+#pragma omp master
+            threads = omp_get_num_threads();
+        }
+        double pairs = (double) (hi - lo + 1) * (double) (N - 1);
+        std::printf("{\"mode\": \"force\", \"vertices\": %zu, \"rows\": %ld, \"pairs_per_call\": %.0f, \"reps\": %d, "
+                    "\"best_s\": %.6f, \"mean_s\": %.6f, \"threads\": %d, \"fx0\": %.17Lg}\n",
+                    N, hi - lo + 1, pairs, o.reps, best, total / o.reps, threads, boundary.V[lo].forvec.x);
+        return 0;
+    }
+
+    double t0 = now_s();
+    md_interface(boundary, counterions, mesh_bath, ions_bath, mdremote, o.G, o.B, constraintForm, scalefactor,
+                 box_halflength);
+    double t1 = now_s();
+
+    if (o.mode == "run") {
+        int threads = 1;
+#pragma omp parallel
+        {
+#pragma omp master
+            threads = omp_get_num_threads();
+        }
+        std::printf("{\"mode\": \"run\", \"vertices\": %zu, \"steps\": %d, \"wall_s\": %.6f, \"threads\": %d, "
+                    "\"area\": %.17g, \"penergy\": %.17g, \"energy\": %.17g}\n",
+                    N, o.steps, t1 - t0, threads, boundary.total_area, boundary.penergy, boundary.energy);
+        return 0;
+    }
+
+    // ---- dump ----
+    FILE *f = std::fopen(o.out.c_str(), "w");
+    if (!f) {
+        std::perror("open --out");
+        return 1;
+    }
+    std::fprintf(f, "sizes %zu %zu %zu\n", N, boundary.E.size(), boundary.F.size());
+    std::fprintf(f, "step %d\n", o.steps);
+    std::fprintf(f, "scalefactor %.17g\nem %.17g\ninv_kappa_out %.17g\nelj %.17g\nlj_length_mesh_mesh %.17g\n",
+                 scalefactor, boundary.em, boundary.inv_kappa_out, boundary.elj, boundary.lj_length_mesh_mesh);
+    std::fprintf(f, "bkappa %.17g\nsconstant %.17g\nsigma_a %.17g\nsigma_v %.17g\n", boundary.bkappa,
+                 boundary.sconstant, boundary.sigma_a, boundary.sigma_v);
+    std::fprintf(f, "ref_area %.17g\nref_volume %.17g\navg_edge_length %.17g\n", boundary.ref_area,
+                 boundary.ref_volume, boundary.avg_edge_length);
+    std::fprintf(f, "dt %.17g\nT %.17g\nbuckling %d\n", mdremote.timestep, T, o.B == 'y' ? 1 : 0);
+    std::fprintf(f, "total_area %.17g\ntotal_volume %.17g\n", boundary.total_area, boundary.total_volume);
+    std::fprintf(f, "netMeshKE %.17g\npenergy %.17g\nenergy %.17g\n", boundary.netMeshKE, boundary.penergy,
+                 boundary.energy);
+
+    // Energy components: compute_energy keeps them in locals (src/interface.cpp:990-1033), so
+    // re-evaluate each with the reference's own member/pair functions and check the sum against
+    // boundary.penergy, which compute_energy did store.
+    long double bE = 0, sE = 0, ljE = 0, esE = 0;
+    for (size_t i = 0; i < boundary.E.size(); i++)
+        bE += boundary.bkappa *
+              (1 - boundary.E[i].itsS / (4 * boundary.E[i].itsF[0]->itsarea * boundary.E[i].itsF[1]->itsarea));
+    if (o.B == 'n') {
+        for (size_t i = 0; i < boundary.E.size(); i++) {
+            double stretched = boundary.E[i].length() - boundary.E[i].l0;
+            sE += 0.5 * boundary.sconstant * stretched * stretched / (boundary.E[i].l0 * boundary.E[i].l0);
+        }
+        sE = sE * boundary.avg_edge_length * boundary.avg_edge_length;
+    } else {
+        for (size_t i = 0; i < boundary.E.size(); i++) {
+            double stretched = boundary.E[i].length() - boundary.avg_edge_length;
+            sE += 0.5 * boundary.sconstant * stretched * stretched;
+        }
+    }
+    double tE = boundary.sigma_a * boundary.total_area;
+    double volE = boundary.sigma_v * ((boundary.total_volume - boundary.ref_volume) *
+                                      (boundary.total_volume - boundary.ref_volume));
+    for (size_t i = 0; i < N; i++) {
+        long double lj_i = 0, es_i = 0;
+        for (size_t j = 0; j < N; j++) {
+            if (i == j) continue;
+            lj_i += energy_lj_pair(boundary.V[i].posvec, boundary.V[j].posvec, boundary.lj_length_mesh_mesh,
+                                   boundary.elj);
+            es_i += energy_es_pair(boundary.V[i], boundary.V[j], boundary.em, boundary.inv_kappa_out, scalefactor);
+        }
+        ljE += 0.5L * lj_i;
+        esE += 0.5L * es_i;
+    }
+    long double psum = bE + sE + tE + volE + ljE + esE;
+    std::fprintf(f, "bE %.21Lg\nsE %.21Lg\ntE %.17g\nvolE %.17g\nljE %.21Lg\nesE %.21Lg\npenergy_check %.21Lg\n", bE,
+                 sE, tE, volE, ljE, esE, psum);
+    bool wrote = (o.steps < 3) || (o.steps % mdremote.writedata == 0);  // src/newmd.cpp:174
+    std::fprintf(f, "energy_fresh %d\n", wrote ? 1 : 0);
+    if (wrote && fabsl(psum - (long double) boundary.penergy) > 1e-11L * (fabsl(psum) + 1)) {
+        std::fprintf(stderr, "component sum %.17Lg != penergy %.17g\n", psum, boundary.penergy);
+        return 3;
+    }
+
+    long double ke = compute_kinetic_energy(boundary.V);
+    std::fprintf(f, "vertex_ke %.21Lg\n", ke);
+    std::fprintf(f, "mesh_bath_ke %.17g\nmesh_bath_pe %.17g\nions_bath_ke %.17g\nions_bath_pe %.17g\n",
+                 bath_kinetic_energy(mesh_bath), bath_potential_energy(mesh_bath), bath_kinetic_energy(ions_bath),
+                 bath_potential_energy(ions_bath));
+    std::fprintf(f, "chain %zu\n", mesh_bath.size());
+    for (size_t j = 0; j < mesh_bath.size(); j++)
+        std::fprintf(f, "mesh_bath %zu %.17g %.17g %d %.17g %.17g\n", j, mesh_bath[j].Q, mesh_bath[j].T,
+                     mesh_bath[j].dof, mesh_bath[j].xi, mesh_bath[j].eta);
+    for (size_t j = 0; j < ions_bath.size(); j++)
+        std::fprintf(f, "ions_bath %zu %.17g %.17g %d %.17g %.17g\n", j, ions_bath[j].Q, ions_bath[j].T,
+                     ions_bath[j].dof, ions_bath[j].xi, ions_bath[j].eta);
+
+    for (size_t i = 0; i < N; i++) {
+        VERTEX &V = boundary.V[i];
+        std::fprintf(f, "q %zu %.17g\n", i, V.q);
+        pv(f, "pos", i, V.posvec);
+        pv(f, "vel", i, V.velvec);
+        pv(f, "for", i, V.forvec);
+        pv(f, "bfo", i, V.bforce);
+        pv(f, "sfo", i, V.sforce);
+        pv(f, "tfo", i, V.TForce);
+        pv(f, "vfo", i, V.VolTForce);
+        VECTOR3D pair = V.forvec - V.bforce - V.sforce - V.TForce - V.VolTForce;
+        pv(f, "pfo", i, pair);
+    }
+    for (size_t i = 0; i < boundary.E.size(); i++)
+        std::fprintf(f, "edge %zu %u %u %.17g %.17g\n", i, boundary.E[i].itsV[0]->index, boundary.E[i].itsV[1]->index,
+                     boundary.E[i].l0, boundary.E[i].itsS);
+    for (size_t i = 0; i < boundary.F.size(); i++)
+        std::fprintf(f, "face %zu %u %u %u %.17g %.17g\n", i, boundary.F[i].itsV[0]->index,
+                     boundary.F[i].itsV[1]->index, boundary.F[i].itsV[2]->index, boundary.F[i].itsarea,
+                     boundary.F[i].subtends_volume);
+    std::fclose(f);
+    std::fprintf(stderr, "dumped step %d to %s (md wall %.3f s)\n", o.steps, o.out.c_str(), t1 - t0);
+    return 0;
+}
