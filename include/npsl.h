@@ -1,0 +1,180 @@
+/*
+ * npsl.h -- C ABI of the B200-native force / energy / integrator path of np-shape-lab.
+ *
+ * This is the drop-in boundary. The reference has no plugin or FFI layer; its boundary is the
+ * in-process C++ call surface of md_interface (src/newmd.cpp). Each entry point below replaces
+ * the body of one of those calls; the reference file:line it stands for is given beside it.
+ * INTEGRATION.md shows the adapter a maintainer of the reference would add on their side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all host arrays are caller-owned, double precision,
+ *     vectors are [n][3] row-major (x,y,z) exactly like a packed array of VECTOR3D-as-double;
+ *   - every call returns 0 on success and a negative npsl_status on failure; the message is
+ *     available from npsl_last_error(); the library never calls exit()/abort();
+ *   - a context is single-owner and not thread-safe (the reference's callers are
+ *     single-threaded, src/newmd.cpp); it is bound to the CUDA device that is current when it
+ *     is created; all device memory is allocated once at creation;
+ *   - there is no CPU fallback: without a CUDA device npsl_create fails with NPSL_ERR_CUDA.
+ */
+#ifndef NPSL_H
+#define NPSL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPSL_ABI_VERSION 1
+#define NPSL_MAX_CHAIN 16   /* links per Nose-Hoover chain, incl. the Q=0 dummy tail */
+#define NPSL_MAX_DEGREE 8   /* maximum vertex valence supported by the gather kernels */
+#define NPSL_NCCL_ID_BYTES 128
+
+typedef enum {
+    NPSL_OK = 0,
+    NPSL_ERR_ARG = -1,      /* bad argument / unsupported mesh */
+    NPSL_ERR_CUDA = -2,     /* CUDA runtime error (incl. no device, extension not usable) */
+    NPSL_ERR_NCCL = -3,     /* NCCL error or libnccl not loadable (sharded contexts only) */
+    NPSL_ERR_STATE = -4,    /* call sequence error (e.g. step before force_init) */
+    NPSL_ERR_NUMERIC = -5   /* non-finite energy detected at a read-back */
+} npsl_status;
+
+typedef struct npsl_ctx npsl_ctx;
+
+/* Static topology, as INTERFACE::discretize leaves it (src/interface.cpp:70-156).
+ * Flattens VERTEX/EDGE/FACE pointer links (src/vertex.h:61-62, src/edge.h:38-39, src/face.h:35-36). */
+typedef struct {
+    int32_t n_vertices, n_edges, n_faces;
+    const int32_t *edge_v; /* [n_edges][2]  EDGE::itsV indices                              */
+    const int32_t *face_v; /* [n_faces][3]  FACE::itsV indices in the stored winding
+                              (already reversed where the file's sign column is -1,
+                              src/interface.cpp:121-129)                                    */
+    const double *l0;      /* [n_edges]     EDGE::l0, initial edge lengths                  */
+} npsl_mesh_desc;
+
+/* One thermostat link, THERMOSTAT{Q,T,dof,xi,eta} (src/thermostat.h:28-35). */
+typedef struct {
+    double Q, T, dof, xi, eta;
+} npsl_bath_link;
+
+/* Reduced-unit parameters, already derived on the host exactly as main() does
+ * (src/main.cpp:196-273). */
+typedef struct {
+    double scalefactor;         /* epsilon_water*lB_water/R            src/main.cpp:210       */
+    double em;                  /* INTERFACE::em                       src/interface.cpp:22   */
+    double inv_kappa_out;       /* Debye length                        src/main.cpp:235-239   */
+    double elj;                 /* LJ strength                         src/main.cpp:273       */
+    double lj_length_mesh_mesh; /* 0.1*avg_edge_length                 src/main.cpp:269-270   */
+    double bkappa;              /* bending modulus (-b)                                        */
+    double sconstant;           /* stretching modulus (-s)                                     */
+    double sigma_a;             /* reduced surface tension             src/main.cpp:202-203   */
+    double sigma_v;             /* reduced volume tension              src/main.cpp:206-207   */
+    double ref_volume;          /* INTERFACE::ref_volume               src/main.cpp:265       */
+    double avg_edge_length;     /* INTERFACE::avg_edge_length          src/interface.cpp:148-155 */
+    double dt;                  /* CONTROL::timestep                                           */
+    int32_t buckling;           /* 0: -B n, 1: -B y (stretching form, src/vertex.cpp:61-88)   */
+    int32_t chain;              /* links per chain incl. dummy (= -C)  src/main.cpp:276-290   */
+    npsl_bath_link mesh_bath[NPSL_MAX_CHAIN];
+    npsl_bath_link ions_bath[NPSL_MAX_CHAIN]; /* evolves even with zero ions, src/newmd.cpp:101 */
+} npsl_params;
+
+/* Energies as INTERFACE::compute_energy reports them (src/interface.cpp:964-1137) plus the
+ * bath terms md_interface adds (src/newmd.cpp:178-192). */
+typedef struct {
+    double kinetic;        /* netMeshKE                                             */
+    double bending;        /* bE   src/interface.cpp:990-995                        */
+    double stretching;     /* sE   src/interface.cpp:1000-1015                      */
+    double tension;        /* tE   src/interface.cpp:1023                           */
+    double lj;             /* ljE  src/interface.cpp:1046-1099                      */
+    double electrostatic;  /* esE                                                   */
+    double volume;         /* volE src/interface.cpp:1030                           */
+    double potential;      /* INTERFACE::penergy                                    */
+    double energy;         /* INTERFACE::energy = KE + penergy                      */
+    double mesh_bath_ke, mesh_bath_pe, ions_bath_ke, ions_bath_pe; /* src/newenergies.h:28-46 */
+    double total_area, total_volume;                               /* INTERFACE::total_*      */
+} npsl_energies;
+
+/* ---- life cycle ------------------------------------------------------------------------ */
+
+/* Single-GPU context on the current CUDA device. Replaces the lazy set-up the reference does
+ * by walking INTERFACE on every call (src/newforces.cpp:140-143). */
+int npsl_create(const npsl_mesh_desc *mesh, const npsl_params *params, npsl_ctx **out);
+
+/* One rank of a row-sharded job (one process per GPU). Rows of the pair interaction and the
+ * owned vertex range follow the reference's MPI decomposition (src/main.cpp:448-455) with the
+ * per-rank range rounded up to the vertex tile. nccl_unique_id: NPSL_NCCL_ID_BYTES bytes
+ * obtained from npsl_nccl_unique_id() on rank 0 and distributed by the caller. */
+int npsl_create_sharded(const npsl_mesh_desc *mesh, const npsl_params *params, int rank, int world,
+                        const void *nccl_unique_id, npsl_ctx **out);
+int npsl_nccl_unique_id(void *out_id);
+
+void npsl_destroy(npsl_ctx *ctx);
+
+/* Message of the most recent failure (ctx may be NULL for creation failures). */
+const char *npsl_last_error(const npsl_ctx *ctx);
+int npsl_abi_version(void);
+
+/* ---- state ----------------------------------------------------------------------------- */
+
+/* VERTEX::posvec / velvec / q -> device. Any pointer may be NULL (left unchanged). */
+int npsl_upload_state(npsl_ctx *ctx, const double *pos, const double *vel, const double *q);
+
+/* device -> VERTEX::posvec / velvec / forvec. Any pointer may be NULL. */
+int npsl_download_state(npsl_ctx *ctx, double *pos, double *vel, double *force);
+
+/* Force components of the most recent npsl_force_init / npsl_force call:
+ * pair (forVecMeshGather), VERTEX::bforce, sforce, TForce, VolTForce (src/newforces.cpp:279-280).
+ * Any pointer may be NULL. */
+int npsl_download_force_components(npsl_ctx *ctx, double *pair, double *bending, double *stretching,
+                                   double *tension, double *volume_tension);
+
+/* FACE::itsarea / subtends_volume / itsdirection and EDGE::itsS of the most recent force call. */
+int npsl_download_mesh_fields(npsl_ctx *ctx, double *face_area, double *face_volume, double *face_dir,
+                              double *edge_S);
+
+int npsl_get_thermostat(npsl_ctx *ctx, npsl_bath_link *mesh_bath, npsl_bath_link *ions_bath);
+/* Also the annealing hook: T and Q of every link are taken from the arrays (src/newmd.cpp:295-298). */
+int npsl_set_thermostat(npsl_ctx *ctx, const npsl_bath_link *mesh_bath, const npsl_bath_link *ions_bath);
+
+/* ---- the path ---------------------------------------------------------------------------- */
+
+/* INTERFACE::dressup (src/interface.cpp:33-67): face direction/area/volume, total area, total
+ * volume at the current positions. */
+int npsl_dressup(npsl_ctx *ctx, double *total_area, double *total_volume);
+
+/* force_calculation_init (src/newforces.cpp:4-135) and force_calculation (:137-289): all forces at
+ * the current positions; velocities untouched. Both also refresh the kinetic energy the
+ * thermostat consumes (compute_kinetic_energy, src/newmd.cpp:52). */
+int npsl_force_init(npsl_ctx *ctx);
+int npsl_force(npsl_ctx *ctx);
+
+/* n iterations of the loop body of md_interface (src/newmd.cpp:96-170): reverse half-chain,
+ * half-kick, drift, dressup, force_calculation, half-kick, KE, forward half-chain. Runs entirely on
+ * the device (one CUDA-graph launch per step); asynchronous until a download or npsl_sync. */
+int npsl_step(npsl_ctx *ctx, int n_steps);
+
+/* INTERFACE::compute_energy (src/interface.cpp:964-1137) + bath energies at the current state. */
+int npsl_energy(npsl_ctx *ctx, npsl_energies *out);
+
+int npsl_sync(npsl_ctx *ctx);
+
+/* ---- introspection (measurement only) --------------------------------------------------- */
+
+/* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
+int64_t npsl_launch_count(const npsl_ctx *ctx);
+/* Average device time of the pair kernel over the launches since the last reset, measured with
+ * CUDA events on the context's stream when timing is enabled. */
+int npsl_pair_timing(npsl_ctx *ctx, int enable);
+int npsl_pair_timing_read(npsl_ctx *ctx, double *mean_ms, int64_t *launches);
+/* Owned row range of this context, half-open. */
+int npsl_owned_rows(const npsl_ctx *ctx, int32_t *lo, int32_t *hi);
+/* Launch geometry of the pair kernel: rows per thread, row tiles x column splits, columns per CTA. */
+int npsl_pair_geometry(const npsl_ctx *ctx, int32_t *rows_per_thread, int32_t *row_tiles, int32_t *col_splits,
+                       int32_t *cols_per_cta);
+/* Pure-DFMA microbenchmark: measured FP64 FMA instructions/s of the current device. */
+int npsl_fp64_peak(double *dfma_per_s, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPSL_H */

@@ -1,0 +1,465 @@
+// Mesh-elastic, integrator and thermostat kernels, FP64, sm_100a.
+//
+// These replace the serial O(N) loops around the pair term in the reference's step
+// (src/newmd.cpp:96-170): the Nose-Hoover half-chains (src/functions.h:176-189), the two
+// velocity half-kicks and the drift (src/vertex.h:105-120), INTERFACE::dressup
+// (src/interface.cpp:33-67), the bending / stretching / surface-tension / volume-tension forces
+// (src/edge.cpp:38-152, src/vertex.cpp:34-106), the force sum (src/newforces.cpp:279-280), the
+// kinetic energy (src/newenergies.h:8-16) and the mesh part of INTERFACE::compute_energy
+// (src/interface.cpp:990-1033).
+//
+// The reference walks pointer-linked VERTEX/EDGE/FACE objects and scatters bending forces into
+// four vertices per edge through a std::map. Here the static topology is flattened once into
+//   * one int4 per edge  (v0, v1, a0, a1): faces F0 = (v0,v1,a0) and F1 = (v1,v0,a1);
+//   * per vertex, k-major tables of width NPSL_MAX_DEGREE: the counter-clockwise one-ring
+//     ring[k][N] (face k of the vertex is (v, ring[k], ring[k+1])), the rest lengths l0 of the ring
+//     edges, and the 2*degree bending-slot indices the vertex gathers;
+// so every kernel is a coalesced sweep plus L2-resident gathers, with no atomics on data and a
+// fixed summation order (run-to-run deterministic, independent of the row sharding).
+//
+// Step = k_kick_drift -> { k_pair || k_mesh } -> k_vertex<STEP>, captured in a CUDA Graph.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace npsl {
+
+constexpr int kMaxDeg = 8;     // == NPSL_MAX_DEGREE
+constexpr int kMaxChain = 16;  // == NPSL_MAX_CHAIN
+constexpr int kMeshThreads = 128;
+
+struct BathLink {
+    double Q, T, dof, xi, eta;
+};
+struct Thermo {
+    BathLink mesh[kMaxChain];
+    BathLink ions[kMaxChain];
+};
+
+// device scalar block
+enum {
+    SC_AREA = 0,  // total_area
+    SC_VOL,       // total_volume
+    SC_BE,        // bending energy
+    SC_SE,        // stretching energy (before the 1/2 sconstant (avg^2) prefactor is applied: final value)
+    SC_KE,        // kinetic energy of the owned vertices
+    SC_ES,        // electrostatic energy of the owned rows
+    SC_LJ,        // LJ energy of the owned rows
+    SC_EXPFAC,    // exp(-dt/2 xi_0) of the current step
+    SC_KICK,      // dt/2 sqrt(expfac)
+    SC_COUNT = 16
+};
+
+struct MeshParams {
+    int nv, ne, nf;
+    int row_lo, row_hi;  // owned vertex range
+    int n_ranks;
+    int chain;
+    int buckling;
+    int n_splits, row_stride;  // layout of the pair partial sums
+    int use_pair;              // 0 when every charge is zero (pair partials are not read)
+    double dt;
+    double pair_coef;  // scalefactor / em
+    double bkappa, sconstant, sigma_a, sigma_v, ref_volume, avg_edge;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small vector helpers
+struct V3 {
+    double x, y, z;
+};
+__device__ __forceinline__ V3 mk(double x, double y, double z) { V3 r = {x, y, z}; return r; }
+__device__ __forceinline__ V3 sub(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+    return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// 32-byte records are moved as two 16-byte halves (there is no 32-byte __ldg/__ldcg overload)
+__device__ __forceinline__ double4 ldg4(const double4 *p) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ double4 ldcg4(const double4 *p) {
+    const double2 a = __ldcg(reinterpret_cast<const double2 *>(p));
+    const double2 b = __ldcg(reinterpret_cast<const double2 *>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ V3 ld3(const double4 *p, int i) {
+    const double4 v = ldg4(p + i);
+    return mk(v.x, v.y, v.z);
+}
+
+// Deterministic block sum of NV values per thread: warp shuffles in a fixed tree, then warp 0
+// sums the per-warp results in warp order. Result valid in thread 0.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *smem /* [NV][32] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+        if (lane == 0) smem[k * 32 + warp] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double s = 0;
+            for (int w = 0; w < nwarp; w++) s += smem[k * 32 + w];
+            v[k] = s;
+        }
+    }
+}
+
+// Last-block-done: every block publishes its partials, takes a ticket; the block that draws the
+// last ticket sums all partials in block order (so the result does not depend on which block
+// that is) and resets the ticket. Returns true in thread 0 of the last block.
+__device__ __forceinline__ bool take_last_ticket(unsigned int *ticket, unsigned int nblocks) {
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    if (t == nblocks - 1) {
+        *ticket = 0;
+        __threadfence();
+        return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Nose-Hoover chain, src/functions.h:176-189 (update_chain_xi), src/thermostat.h:53-58 (update_eta)
+__device__ __forceinline__ void chain_xi(BathLink *b, int j, int chain, double dt, double ke) {
+    if (b[j].Q == 0) return;
+    const double xn = (j + 1 < chain) ? b[j + 1].xi : 0.0;
+    const double drive = (j == 0) ? (2 * ke - b[j].dof * b[j].T) : (b[j - 1].Q * b[j - 1].xi * b[j - 1].xi - b[j].dof * b[j].T);
+    b[j].xi = b[j].xi * exp(-0.5 * dt * xn) + 0.5 * dt * (1.0 / b[j].Q) * drive * exp(-0.25 * dt * xn);
+}
+__device__ __forceinline__ void chain_eta(BathLink *b, int chain, double dt) {
+    for (int j = 0; j < chain; j++)
+        if (b[j].Q != 0) b[j].eta = b[j].eta + 0.5 * dt * b[j].xi;
+}
+// first half of a step, src/newmd.cpp:99-110
+__device__ __forceinline__ double thermo_reverse(Thermo &t, int chain, double dt, double ke) {
+    for (int j = chain - 1; j > -1; j--) chain_xi(t.mesh, j, chain, dt, ke);
+    for (int j = chain - 1; j > -1; j--) chain_xi(t.ions, j, chain, dt, 0.0);
+    chain_eta(t.mesh, chain, dt);
+    chain_eta(t.ions, chain, dt);
+    return exp(-0.5 * dt * t.mesh[0].xi);
+}
+// second half of a step, src/newmd.cpp:161-170
+__device__ __forceinline__ void thermo_forward(Thermo &t, int chain, double dt, double ke) {
+    chain_eta(t.mesh, chain, dt);
+    chain_eta(t.ions, chain, dt);
+    for (int j = 0; j < chain; j++) chain_xi(t.mesh, j, chain, dt, ke);
+    for (int j = 0; j < chain; j++) chain_xi(t.ions, j, chain, dt, 0.0);
+}
+
+__device__ __forceinline__ double sum_ke_parts(const double *ke_parts, int n_ranks) {
+    double ke = 0;
+    for (int r = 0; r < n_ranks; r++) ke += ke_parts[r];  // fixed rank order
+    return ke;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_kick_drift: reverse half-chain (once per block, thread 0), first half-kick, drift.
+// src/newmd.cpp:99-123. th_cur is read by every block; block 0 publishes the half-updated chain
+// to th_mid, which k_vertex<STEP> / k_thermo_post complete into th_cur.
+__global__ void __launch_bounds__(kMeshThreads)
+k_kick_drift(double4 *__restrict__ xyzq, double4 *__restrict__ vel, const double4 *__restrict__ force,
+             const Thermo *__restrict__ th_cur, Thermo *__restrict__ th_mid, const double *__restrict__ ke_parts,
+             double *__restrict__ scal, int *__restrict__ lj_hit, const MeshParams P) {
+    __shared__ double s_ef, s_kick;
+    if (threadIdx.x == 0) {
+        Thermo t = *th_cur;
+        const double ke = sum_ke_parts(ke_parts, P.n_ranks);
+        const double ef = thermo_reverse(t, P.chain, P.dt, ke);
+        const double kick = 0.5 * P.dt * sqrt(ef);
+        s_ef = ef;
+        s_kick = kick;
+        if (blockIdx.x == 0) {
+            *th_mid = t;
+            scal[SC_EXPFAC] = ef;
+            scal[SC_KICK] = kick;
+            *lj_hit = 0;
+        }
+    }
+    __syncthreads();
+    const int i = P.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.row_hi) return;
+    const double ef = s_ef, kick = s_kick, dt = P.dt;
+    double4 v = vel[i];
+    const double4 f = force[i];
+    double4 x = xyzq[i];
+    v.x = v.x * ef + f.x * kick;
+    v.y = v.y * ef + f.y * kick;
+    v.z = v.z * ef + f.z * kick;
+    x.x = x.x + v.x * dt;
+    x.y = x.y + v.y * dt;
+    x.z = x.z + v.z * dt;
+    vel[i] = v;
+    xyzq[i] = x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_mesh: blocks [0, n_face_blocks) sweep faces (INTERFACE::dressup: direction, area, volume and
+// their totals, src/interface.cpp:33-67, src/face.cpp:16-45); the remaining blocks sweep edges
+// (EDGE::bending_forces, src/edge.cpp:38-58, with compute_gradS :60-152 in its closed form
+//   grad_p S = sum_{F in {F0,F1}, p in F} (pn_F - pnn_F) x dir_other(F),
+// and the bending / stretching energies of src/interface.cpp:990-1015).
+//
+// Per edge with oriented record (v0,v1,a0,a1):  dir0 = (p1-p0)x(pa-p1), dir1 = (p0-p1)x(pb-p0),
+// S = dir0.dir1, |dir| = 2A. With  w0 = dir1 - S/|dir0|^2 dir0,  w1 = dir0 - S/|dir1|^2 dir1  and
+// kb = bkappa/(|dir0||dir1|) = bkappa 0.25/(A0 A1), the four bending-force slots are
+//   v0: kb[(p1-pa) x w0 + (pb-p1) x w1]    v1: kb[(pa-p0) x w0 + (p0-pb) x w1]
+//   a0: kb (p0-p1) x w0                    a1: kb (p1-p0) x w1
+// which is  bkappa 0.25/(A0A1) (grad S - S/A0 grad A_F0 - S/A1 grad A_F1)  of the reference with
+// grad_c A_F = (pn-pnn) x dir_F / (4 A_F)  (src/face.cpp:69-90).
+template <bool ENERGY, bool STORE>
+__global__ void __launch_bounds__(kMeshThreads)
+k_mesh(const double4 *__restrict__ xyzq, const int4 *__restrict__ face_v, const int4 *__restrict__ edge_rec,
+       const double *__restrict__ l0, double4 *__restrict__ bslot, double *__restrict__ partials /* [4][nblocks] */,
+       unsigned int *__restrict__ ticket, double *__restrict__ scal, double4 *__restrict__ face_dir_area,
+       double *__restrict__ face_vol, double *__restrict__ edge_S, int n_face_blocks, const MeshParams P) {
+    __shared__ double red[4 * 32];
+    __shared__ bool s_last;
+    const int nblocks = gridDim.x;
+    double acc[4] = {0, 0, 0, 0};  // area, volume, bending energy, stretching energy
+    if ((int) blockIdx.x < n_face_blocks) {
+        const int f = blockIdx.x * blockDim.x + threadIdx.x;
+        if (f < P.nf) {
+            const int4 fv = __ldg(face_v + f);
+            const V3 a = ld3(xyzq, fv.x), b = ld3(xyzq, fv.y), c = ld3(xyzq, fv.z);
+            const V3 dir = cross(sub(b, a), sub(c, b));
+            const double area = 0.5 * sqrt(dot(dir, dir));
+            const double vol = (1. / 6.) * dot(a, cross(b, c));
+            acc[0] = area;
+            acc[1] = vol;
+            if (STORE) {
+                face_dir_area[f] = make_double4(dir.x, dir.y, dir.z, area);
+                face_vol[f] = vol;
+            }
+        }
+    } else {
+        const int e = (blockIdx.x - n_face_blocks) * blockDim.x + threadIdx.x;
+        if (e < P.ne) {
+            const int4 r = __ldg(edge_rec + e);
+            const V3 p0 = ld3(xyzq, r.x), p1 = ld3(xyzq, r.y), pa = ld3(xyzq, r.z), pb = ld3(xyzq, r.w);
+            const V3 e01 = sub(p1, p0);
+            const V3 dir0 = cross(e01, sub(pa, p1));
+            const V3 dir1 = cross(sub(p0, p1), sub(pb, p0));
+            const double S = dot(dir0, dir1);
+            const double n0 = dot(dir0, dir0), n1 = dot(dir1, dir1);
+            const double inv_n0n1 = 1.0 / sqrt(n0 * n1);
+            const double kb = P.bkappa * inv_n0n1;
+            const double c0 = S / n0, c1 = S / n1;
+            const V3 w0 = mk(dir1.x - c0 * dir0.x, dir1.y - c0 * dir0.y, dir1.z - c0 * dir0.z);
+            const V3 w1 = mk(dir0.x - c1 * dir1.x, dir0.y - c1 * dir1.y, dir0.z - c1 * dir1.z);
+            const V3 t00 = cross(sub(p1, pa), w0), t01 = cross(sub(pb, p1), w1);
+            const V3 t10 = cross(sub(pa, p0), w0), t11 = cross(sub(p0, pb), w1);
+            const V3 ta = cross(sub(p0, p1), w0), tb = cross(e01, w1);
+            bslot[e] = make_double4(kb * (t00.x + t01.x), kb * (t00.y + t01.y), kb * (t00.z + t01.z), 0.0);
+            bslot[P.ne + e] = make_double4(kb * (t10.x + t11.x), kb * (t10.y + t11.y), kb * (t10.z + t11.z), 0.0);
+            bslot[2 * P.ne + e] = make_double4(kb * ta.x, kb * ta.y, kb * ta.z, 0.0);
+            bslot[3 * P.ne + e] = make_double4(kb * tb.x, kb * tb.y, kb * tb.z, 0.0);
+            if (STORE) edge_S[e] = S;
+            if (ENERGY) {
+                acc[2] = P.bkappa * (1.0 - S * inv_n0n1);
+                const double l = sqrt(dot(e01, e01));
+                if (!P.buckling) {
+                    const double le = __ldg(l0 + e), st = l - le;
+                    acc[3] = 0.5 * P.sconstant * st * st / (le * le);
+                } else {
+                    const double st = l - P.avg_edge;
+                    acc[3] = 0.5 * P.sconstant * st * st;
+                }
+            }
+        }
+    }
+    block_sum<4>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) partials[k * nblocks + blockIdx.x] = acc[k];
+        s_last = take_last_ticket(ticket, nblocks);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // ordered final sums, one warp-strided pass per quantity, fixed order
+    double tot[4] = {0, 0, 0, 0};
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) tot[k] += __ldcg(partials + k * nblocks + b);
+    }
+    __syncthreads();
+    block_sum<4>(tot, red);
+    if (threadIdx.x == 0) {
+        scal[SC_AREA] = tot[0];
+        scal[SC_VOL] = tot[1];
+        if (ENERGY) {
+            scal[SC_BE] = tot[2];
+            scal[SC_SE] = P.buckling ? tot[3] : tot[3] * P.avg_edge * P.avg_edge;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_vertex: gather-by-vertex of every force term, then (STEP) the second half-kick, the kinetic
+// energy and the forward half-chain, or (FORCE) the per-term forces and the pair energies.
+//   pair       (scalefactor/em) q_i sum_splits partial                src/newforces.cpp:173-176
+//   bending    sum of the vertex's 2*degree slots                     src/edge.cpp:38-58
+//   stretching -s avg^2 sum_e (l-l0)/l (x_v-x_o)/l0^2  (or -B y form)  src/vertex.cpp:56-89
+//   tension    sigma_a * sum_F -grad A_F ; 2 sigma_v (V-V0) sum_F -grad V_F   src/vertex.cpp:34-53,92-106
+//   forvec = sum of the five                                          src/newforces.cpp:279-280
+//   v <- v expfac + f dt/2 sqrt(expfac); ke = 1/2 v.v                 src/newmd.cpp:146-157
+enum { VMODE_STEP = 0, VMODE_FORCE = 1 };
+
+struct VertexTables {
+    const int *degree;      // [nv]
+    const int *ring;        // [kMaxDeg][nv]   -1 padded
+    const double *ring_l0;  // [kMaxDeg][nv]
+    const int *bslot_ref;   // [2*kMaxDeg][nv] -1 padded
+};
+
+struct ForceComponents {  // FORCE mode only
+    double4 *pair, *bend, *stretch, *tension, *voltension;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kMeshThreads)
+k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *__restrict__ force,
+         const double4 *__restrict__ pair_partial, const double4 *__restrict__ lj_out, const int *__restrict__ lj_hit,
+         const double4 *__restrict__ bslot, const VertexTables T, const ForceComponents C,
+         double *__restrict__ partials /* [3][nblocks] */, unsigned int *__restrict__ ticket,
+         double *__restrict__ scal, double *__restrict__ ke_parts, int rank, const Thermo *__restrict__ th_mid,
+         Thermo *__restrict__ th_cur, const MeshParams P) {
+    __shared__ double red[3 * 32];
+    __shared__ bool s_last;
+    const int nblocks = gridDim.x;
+    const int i = P.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[3] = {0, 0, 0};  // ke, es energy, lj energy
+    if (i < P.row_hi) {
+        const int nv = P.nv;
+        const double4 xi4 = ldg4(xyzq + i);
+        const V3 p = mk(xi4.x, xi4.y, xi4.z);
+        // ---- pair term: ordered sum over the column splits
+        V3 fp = mk(0, 0, 0);
+        double ue = 0;
+        if (P.use_pair) {
+            for (int s = 0; s < P.n_splits; s++) {
+                const double4 a = ldcg4(pair_partial + (size_t) s * P.row_stride + (i - P.row_lo));
+                fp.x += a.x; fp.y += a.y; fp.z += a.z; ue += a.w;
+            }
+            const double cq = P.pair_coef * xi4.w;
+            fp.x *= cq; fp.y *= cq; fp.z *= cq;
+            ue *= 0.5 * cq;
+        }
+        double ulj = 0;
+        if (!P.use_pair || __ldcg(lj_hit) != 0) {
+            const double4 a = ldcg4(lj_out + (i - P.row_lo));
+            fp.x += a.x; fp.y += a.y; fp.z += a.z; ulj = a.w;
+        }
+        // ---- bending: gather the slots written by k_mesh
+        V3 fb = mk(0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 2 * kMaxDeg; k++) {
+            const int s = __ldg(T.bslot_ref + k * nv + i);
+            if (s >= 0) {
+                const double4 a = ldcg4(bslot + s);
+                fb.x += a.x; fb.y += a.y; fb.z += a.z;
+            }
+        }
+        // ---- one-ring: stretching, surface tension, volume tension
+        V3 fs = mk(0, 0, 0), gA = mk(0, 0, 0), gV = mk(0, 0, 0);
+        const int deg = __ldg(T.degree + i);
+        const V3 pfirst = ld3(xyzq, __ldg(T.ring + i));
+        V3 pn = pfirst;
+#pragma unroll
+        for (int k = 0; k < kMaxDeg; k++) {
+            if (k >= deg) break;
+            // pn = position of ring[k]; pnn = position of ring[k+1] (cyclic)
+            const V3 pnn = (k + 1 < deg) ? ld3(xyzq, __ldg(T.ring + (k + 1) * nv + i)) : pfirst;
+            // stretching along edge (v, ring[k])
+            const V3 d = sub(p, pn);
+            const double l = sqrt(dot(d, d));
+            double c;
+            if (!P.buckling) {
+                const double le = __ldg(T.ring_l0 + k * nv + i);
+                c = ((l - le) / l) * (1.0 / (le * le));
+            } else {
+                c = (l - P.avg_edge) / l;
+            }
+            fs.x += c * d.x; fs.y += c * d.y; fs.z += c * d.z;
+            // face (p, pn, pnn): FACE::computegradients, src/face.cpp:47-91
+            const V3 cv = cross(pn, pnn);
+            gV.x -= (1. / 6.) * cv.x; gV.y -= (1. / 6.) * cv.y; gV.z -= (1. / 6.) * cv.z;
+            const V3 cp = cross(sub(pn, p), sub(pnn, p));
+            const V3 num = cross(sub(pn, pnn), cp);
+            const double inv_den = 1.0 / (2.0 * sqrt(dot(cp, cp)));
+            gA.x -= num.x * inv_den; gA.y -= num.y * inv_den; gA.z -= num.z * inv_den;
+            pn = pnn;
+        }
+        const double ks = P.buckling ? -P.sconstant : -P.sconstant * P.avg_edge * P.avg_edge;
+        fs.x *= ks; fs.y *= ks; fs.z *= ks;
+        const double kv = 2.0 * P.sigma_v * (__ldcg(scal + SC_VOL) - P.ref_volume);
+        const V3 ft = mk(P.sigma_a * gA.x, P.sigma_a * gA.y, P.sigma_a * gA.z);
+        const V3 fv = mk(kv * gV.x, kv * gV.y, kv * gV.z);
+        const V3 f = mk(fp.x + fb.x + fs.x + ft.x + fv.x, fp.y + fb.y + fs.y + ft.y + fv.y,
+                        fp.z + fb.z + fs.z + ft.z + fv.z);
+        force[i] = make_double4(f.x, f.y, f.z, 0.0);
+        double4 v = vel[i];
+        if (MODE == VMODE_STEP) {
+            const double ef = __ldcg(scal + SC_EXPFAC), kick = __ldcg(scal + SC_KICK);
+            v.x = v.x * ef + f.x * kick;
+            v.y = v.y * ef + f.y * kick;
+            v.z = v.z * ef + f.z * kick;
+            vel[i] = v;
+        } else {
+            C.pair[i] = make_double4(fp.x, fp.y, fp.z, 0.0);
+            C.bend[i] = make_double4(fb.x, fb.y, fb.z, 0.0);
+            C.stretch[i] = make_double4(fs.x, fs.y, fs.z, 0.0);
+            C.tension[i] = make_double4(ft.x, ft.y, ft.z, 0.0);
+            C.voltension[i] = make_double4(fv.x, fv.y, fv.z, 0.0);
+            acc[1] = ue;
+            acc[2] = ulj;
+        }
+        acc[0] = 0.5 * (v.x * v.x + v.y * v.y + v.z * v.z);
+    }
+    block_sum<3>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) partials[k * nblocks + blockIdx.x] = acc[k];
+        s_last = take_last_ticket(ticket, nblocks);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    double tot[3] = {0, 0, 0};
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) tot[k] += __ldcg(partials + k * nblocks + b);
+    }
+    __syncthreads();
+    block_sum<3>(tot, red);
+    if (threadIdx.x == 0) {
+        scal[SC_KE] = tot[0];
+        ke_parts[rank] = tot[0];
+        if (MODE == VMODE_FORCE) {
+            scal[SC_ES] = tot[1];
+            scal[SC_LJ] = tot[2];
+        } else if (P.n_ranks == 1) {
+            Thermo t = *th_mid;
+            thermo_forward(t, P.chain, P.dt, tot[0]);
+            *th_cur = t;
+        }
+    }
+}
+
+// Sharded runs: the forward half-chain needs every rank's kinetic energy, so it runs after the
+// KE exchange as a one-thread kernel (identical arithmetic on every rank).
+__global__ void k_thermo_post(const Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur,
+                              const double *__restrict__ ke_parts, const MeshParams P) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Thermo t = *th_mid;
+    thermo_forward(t, P.chain, P.dt, sum_ke_parts(ke_parts, P.n_ranks));
+    *th_cur = t;
+}
+
+}  // namespace npsl

@@ -1,0 +1,888 @@
+// C ABI of the B200-native force / energy / integrator path (include/npsl.h).
+//
+// Host side of the kernels in pair_kernel.cuh and mesh_kernels.cuh: flattens the static mesh
+// topology once (the reference re-walks pointer-linked VERTEX/EDGE/FACE objects every call,
+// src/newforces.cpp:149-265), owns all device memory, and issues one CUDA-graph launch per MD
+// step. Row-sharded contexts (one process per GPU) follow the reference's MPI row decomposition
+// (src/main.cpp:448-455) with an NCCL all-gather of positions and of the per-rank kinetic
+// energies; NCCL is bound at run time with dlopen so that single-GPU users need no libnccl.
+//
+// There is no CPU path in this file: without a CUDA device every entry point fails.
+#include "../../include/npsl.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "mesh_kernels.cuh"
+#include "pair_kernel.cuh"
+
+using namespace npsl;
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, bound lazily (prototypes restated from the public nccl.h ABI; stable across 2.x)
+namespace {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[NPSL_NCCL_ID_BYTES]; } ncclUniqueId;
+enum { ncclFloat64_ = 8 };
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+std::string g_error;  // creation-time failures (no context yet)
+
+bool load_nccl(std::string &err) {
+    if (g_nccl.ok) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) {
+        err = std::string("cannot load libnccl: ") + dlerror();
+        return false;
+    }
+#define BIND(field, sym)                                                        \
+    *(void **) (&g_nccl.field) = dlsym(g_nccl.handle, sym);                     \
+    if (!g_nccl.field) { err = std::string("libnccl lacks ") + sym; return false; }
+    BIND(GetUniqueId, "ncclGetUniqueId")
+    BIND(CommInitRank, "ncclCommInitRank")
+    BIND(CommDestroy, "ncclCommDestroy")
+    BIND(AllGather, "ncclAllGather")
+    BIND(GetErrorString, "ncclGetErrorString")
+#undef BIND
+    g_nccl.ok = true;
+    return true;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct npsl_ctx {
+    int device = 0;
+    int nv = 0, ne = 0, nf = 0;
+    int rank = 0, world = 1;
+    int row_lo = 0, row_hi = 0;  // owned rows / vertices, half-open
+    int range = 0;               // rows per rank (ceil(nv/world)); buffers hold world*range records
+    npsl_params prm;
+    bool all_q_zero = true;
+    bool forces_valid = false;
+
+    // state, one 32-byte record per vertex (coalesced 16-byte accesses everywhere)
+    double4 *xyzq = nullptr, *vel = nullptr, *force = nullptr;
+    double4 *comp[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // pair, bend, stretch, tension, voltension
+    // topology
+    int4 *face_v = nullptr, *edge_rec = nullptr;
+    double *l0 = nullptr;
+    int *degree = nullptr, *ring = nullptr, *bslot_ref = nullptr;
+    double *ring_l0 = nullptr;
+    // work buffers
+    double4 *bslot = nullptr, *pair_partial = nullptr, *lj_out = nullptr;
+    int *lj_hit = nullptr;
+    double *scal = nullptr, *scal_all = nullptr, *ke_parts = nullptr;
+    Thermo *th_cur = nullptr, *th_mid = nullptr;
+    double *part_mesh = nullptr, *part_vert = nullptr;
+    unsigned int *tickets = nullptr;
+    double4 *face_dir_area = nullptr;
+    double *face_vol = nullptr, *edge_S = nullptr;
+    double *peak_out = nullptr;
+
+    // launch geometry
+    int pair_rows_per_thread = 2, pair_row_tiles = 0, pair_splits = 1, pair_cols_per_cta = 0, pair_row_stride = 0;
+    int n_face_blocks = 0, n_edge_blocks = 0, n_vertex_blocks = 0;
+    PairParams pp;
+    LjParams ljp;
+    MeshParams mp;
+
+    cudaStream_t s_main = nullptr, s_side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaGraphExec_t step_graph = nullptr;
+    ncclComm_t comm = nullptr;
+
+    // measurement
+    int64_t launches = 0;
+    int launches_per_step = 0;
+    bool timing = false;
+    std::vector<cudaEvent_t> t_ev;  // pairs of events around k_pair
+    size_t t_used = 0;
+    double t_sum_ms = 0;
+    int64_t t_count = 0;
+
+    std::vector<double4> stage;  // host staging for AoS<->record conversion
+    std::string err;
+};
+
+namespace {
+
+int fail(npsl_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    g_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(c, NPSL_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define NC(call)                                                                                          \
+    do {                                                                                                  \
+        int e_ = (call);                                                                                  \
+        if (e_ != 0)                                                                                      \
+            return fail(c, NPSL_ERR_NCCL, "%s: %s (%s:%d)", #call, g_nccl.GetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+cudaError_t dalloc(T **p, size_t n) {
+    cudaError_t e = cudaMalloc((void **) p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T));
+    return e;
+}
+
+inline uint64_t dkey(int a, int b) { return ((uint64_t) (uint32_t) a << 32) | (uint32_t) b; }
+
+// Static topology tables consumed by k_mesh / k_vertex (layout described in mesh_kernels.cuh).
+struct Tables {
+    std::vector<int4> face_v, edge_rec;
+    std::vector<int> degree, ring, bslot_ref;
+    std::vector<double> ring_l0;
+};
+
+// Flattens EDGE::itsV/itsF, FACE::itsV and VERTEX::itsE/itsF (src/interface.cpp:100-143) into index
+// tables. Requires a closed, consistently oriented triangle mesh with valence <= NPSL_MAX_DEGREE
+// (the reference asserts two faces per edge, src/interface.cpp:146).
+int build_tables(const npsl_mesh_desc *m, Tables &t, std::string &why) {
+    const int nv = m->n_vertices, ne = m->n_edges, nf = m->n_faces;
+    std::unordered_map<uint64_t, int> third;  // directed edge a->b  ->  vertex opposite in its face
+    third.reserve((size_t) nf * 3 * 2);
+    t.face_v.resize(nf);
+    std::vector<int> cnt(nv, 0);
+    std::vector<int> nxt((size_t) nv * kMaxDeg * 2, -1);  // per vertex: (n, nn) of each incident face
+    for (int f = 0; f < nf; f++) {
+        const int32_t *fv = m->face_v + 3 * f;
+        for (int k = 0; k < 3; k++)
+            if (fv[k] < 0 || fv[k] >= nv) { why = "face vertex index out of range"; return -1; }
+        if (fv[0] == fv[1] || fv[1] == fv[2] || fv[0] == fv[2]) { why = "degenerate face"; return -1; }
+        t.face_v[f] = make_int4(fv[0], fv[1], fv[2], 0);
+        for (int k = 0; k < 3; k++) {
+            const int a = fv[k], b = fv[(k + 1) % 3], c = fv[(k + 2) % 3];
+            if (!third.emplace(dkey(a, b), c).second) { why = "inconsistent face orientation"; return -1; }
+            if (cnt[a] >= kMaxDeg) { why = "vertex valence exceeds NPSL_MAX_DEGREE"; return -1; }
+            nxt[((size_t) a * kMaxDeg + cnt[a]) * 2] = b;
+            nxt[((size_t) a * kMaxDeg + cnt[a]) * 2 + 1] = c;
+            cnt[a]++;
+        }
+    }
+    // edges: oriented record (v0, v1, a0, a1) with F0 = (v0,v1,a0), F1 = (v1,v0,a1)
+    t.edge_rec.resize(ne);
+    std::unordered_map<uint64_t, int> edge_of;
+    edge_of.reserve((size_t) ne * 2);
+    std::vector<int> ecnt(nv, 0);
+    for (int e = 0; e < ne; e++) {
+        const int v0 = m->edge_v[2 * e], v1 = m->edge_v[2 * e + 1];
+        if (v0 < 0 || v0 >= nv || v1 < 0 || v1 >= nv || v0 == v1) { why = "bad edge"; return -1; }
+        auto f0 = third.find(dkey(v0, v1)), f1 = third.find(dkey(v1, v0));
+        if (f0 == third.end() || f1 == third.end()) { why = "edge without two faces (mesh not closed)"; return -1; }
+        t.edge_rec[e] = make_int4(v0, v1, f0->second, f1->second);
+        if (!edge_of.emplace(dkey(std::min(v0, v1), std::max(v0, v1)), e).second) { why = "duplicate edge"; return -1; }
+        ecnt[v0]++;
+        ecnt[v1]++;
+    }
+    if ((size_t) ne * 2 != third.size()) { why = "edge / face counts inconsistent"; return -1; }
+    // one-rings, counter-clockwise, starting at the first incident face in file order
+    t.degree.assign(nv, 0);
+    t.ring.assign((size_t) kMaxDeg * nv, -1);
+    t.ring_l0.assign((size_t) kMaxDeg * nv, 1.0);
+    for (int v = 0; v < nv; v++) {
+        const int d = cnt[v];
+        if (d < 3 || ecnt[v] != d) { why = "vertex is not an interior manifold vertex"; return -1; }
+        t.degree[v] = d;
+        const int *nx = &nxt[(size_t) v * kMaxDeg * 2];
+        int cur = nx[0];
+        for (int k = 0; k < d; k++) {
+            t.ring[(size_t) k * nv + v] = cur;
+            auto it = edge_of.find(dkey(std::min(v, cur), std::max(v, cur)));
+            if (it == edge_of.end()) { why = "face side without an edge record"; return -1; }
+            t.ring_l0[(size_t) k * nv + v] = m->l0[it->second];
+            int found = -1;
+            for (int j = 0; j < d; j++)
+                if (nx[2 * j] == cur) found = nx[2 * j + 1];
+            if (found < 0) { why = "open one-ring"; return -1; }
+            cur = found;
+        }
+        if (cur != nx[0]) { why = "one-ring does not close"; return -1; }
+    }
+    // bending slots gathered by each vertex, ascending edge index (the order in which the
+    // reference's edge loop adds into VERTEX::bforce, src/newforces.cpp:256-257)
+    t.bslot_ref.assign((size_t) 2 * kMaxDeg * nv, -1);
+    std::vector<int> bc(nv, 0);
+    for (int e = 0; e < ne; e++) {
+        const int4 r = t.edge_rec[e];
+        const int vs[4] = {r.x, r.y, r.z, r.w};
+        for (int s = 0; s < 4; s++) {
+            const int v = vs[s];
+            if (bc[v] >= 2 * kMaxDeg) { why = "bending slot overflow"; return -1; }
+            t.bslot_ref[(size_t) bc[v] * nv + v] = s * ne + e;
+            bc[v]++;
+        }
+    }
+    for (int v = 0; v < nv; v++)
+        if (bc[v] != 2 * t.degree[v]) { why = "bending slot count mismatch"; return -1; }
+    return 0;
+}
+
+void fill_thermo(Thermo &t, const npsl_bath_link *mesh, const npsl_bath_link *ions) {
+    for (int j = 0; j < kMaxChain; j++) {
+        t.mesh[j] = {mesh[j].Q, mesh[j].T, mesh[j].dof, mesh[j].xi, mesh[j].eta};
+        t.ions[j] = {ions[j].Q, ions[j].T, ions[j].dof, ions[j].xi, ions[j].eta};
+    }
+}
+
+int high_word(double x) {
+    int64_t b;
+    memcpy(&b, &x, 8);
+    return (int) (b >> 32);
+}
+
+// Column split / row tile geometry of k_pair. The grid is sized to several CTAs per SM so that the
+// hardware scheduler balances the tail; every (split,row) partial has its own slot, so the choice
+// never changes which terms are summed in which order within a split.
+void plan_pair(npsl_ctx *c, int n_sm) {
+    const int rows = c->row_hi - c->row_lo;
+    c->pair_rows_per_thread = 2;
+    const int tile_rows = kPairThreads * c->pair_rows_per_thread;
+    c->pair_row_tiles = std::max(1, (rows + tile_rows - 1) / tile_rows);
+    const int col_tiles = (c->nv + kPairTileJ - 1) / kPairTileJ;
+    // aim for >= 16 CTAs per SM in flight over the launch, but keep at least 2 column tiles per CTA
+    int want = (16 * n_sm + c->pair_row_tiles - 1) / c->pair_row_tiles;
+    int splits = std::max(1, std::min(want, std::max(1, col_tiles / 2)));
+    int tiles_per_cta = (col_tiles + splits - 1) / splits;
+    splits = (col_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    c->pair_splits = splits;
+    c->pair_cols_per_cta = tiles_per_cta * kPairTileJ;
+    c->pair_row_stride = (rows + 31) / 32 * 32;
+}
+
+template <int ROWS>
+void launch_pair(npsl_ctx *c, bool energy, cudaStream_t s) {
+    dim3 grid(c->pair_row_tiles, c->pair_splits);
+    if (energy)
+        k_pair<ROWS, true><<<grid, kPairThreads, 0, s>>>(c->xyzq, c->pair_partial, c->lj_hit, c->pp);
+    else
+        k_pair<ROWS, false><<<grid, kPairThreads, 0, s>>>(c->xyzq, c->pair_partial, c->lj_hit, c->pp);
+}
+
+// Issues the kernels of one force evaluation (and, with step=true, of one whole MD step) on the
+// context's streams. Used both for direct execution and under stream capture.
+int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
+    const VertexTables vt = {c->degree, c->ring, c->ring_l0, c->bslot_ref};
+    const ForceComponents fc = {c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4]};
+    int n = 0;
+    if (step) {
+        k_kick_drift<<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->force, c->th_cur,
+                                                                        c->th_mid, c->ke_parts, c->scal, c->lj_hit,
+                                                                        c->mp);
+        n++;
+        if (c->world > 1)
+            NC(g_nccl.AllGather(c->xyzq + (size_t) c->rank * c->range, c->xyzq, (size_t) c->range * 4, ncclFloat64_,
+                                c->comm, c->s_main));
+    } else {
+        CU(cudaMemsetAsync(c->lj_hit, 0, sizeof(int), c->s_main));
+    }
+    // mesh terms on the side stream, concurrent with the pair term
+    CU(cudaEventRecord(c->ev_fork, c->s_main));
+    CU(cudaStreamWaitEvent(c->s_side, c->ev_fork, 0));
+    {
+        const int grid = c->n_face_blocks + c->n_edge_blocks;
+        unsigned int *tk = c->tickets;
+#define MESH(E, S)                                                                                              \
+    k_mesh<E, S><<<grid, kMeshThreads, 0, c->s_side>>>(c->xyzq, c->face_v, c->edge_rec, c->l0, c->bslot,         \
+                                                       c->part_mesh, tk, c->scal, c->face_dir_area, c->face_vol, \
+                                                       c->edge_S, c->n_face_blocks, c->mp)
+        if (energy && store) MESH(true, true);
+        else if (energy) MESH(true, false);
+        else if (store) MESH(false, true);
+        else MESH(false, false);
+#undef MESH
+        n++;
+    }
+    CU(cudaEventRecord(c->ev_join, c->s_side));
+    if (!c->all_q_zero) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (time_pair && c->t_used + 2 <= c->t_ev.size()) {
+            e0 = c->t_ev[c->t_used];
+            e1 = c->t_ev[c->t_used + 1];
+            c->t_used += 2;
+            CU(cudaEventRecord(e0, c->s_main));
+        }
+        switch (c->pair_rows_per_thread) {
+            case 1: launch_pair<1>(c, energy, c->s_main); break;
+            case 2: launch_pair<2>(c, energy, c->s_main); break;
+            default: launch_pair<4>(c, energy, c->s_main); break;
+        }
+        n++;
+        if (e1) CU(cudaEventRecord(e1, c->s_main));
+    }
+    k_lj<<<(c->row_hi - c->row_lo + 127) / 128, 128, 0, c->s_main>>>(c->xyzq, c->lj_out, c->lj_hit,
+                                                                      c->all_q_zero ? 1 : 0, c->ljp);
+    n++;
+    CU(cudaStreamWaitEvent(c->s_main, c->ev_join, 0));
+    if (step) {
+        k_vertex<VMODE_STEP><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(
+            c->xyzq, c->vel, c->force, c->pair_partial, c->lj_out, c->lj_hit, c->bslot, vt, fc, c->part_vert,
+            c->tickets + 1, c->scal, c->ke_parts, c->rank, c->th_mid, c->th_cur, c->mp);
+        n++;
+        if (c->world > 1) {
+            NC(g_nccl.AllGather(c->scal + SC_KE, c->ke_parts, 1, ncclFloat64_, c->comm, c->s_main));
+            k_thermo_post<<<1, 32, 0, c->s_main>>>(c->th_mid, c->th_cur, c->ke_parts, c->mp);
+            n++;
+        }
+    } else {
+        k_vertex<VMODE_FORCE><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(
+            c->xyzq, c->vel, c->force, c->pair_partial, c->lj_out, c->lj_hit, c->bslot, vt, fc, c->part_vert,
+            c->tickets + 1, c->scal, c->ke_parts, c->rank, c->th_mid, c->th_cur, c->mp);
+        n++;
+        if (c->world > 1)
+            NC(g_nccl.AllGather(c->scal + SC_KE, c->ke_parts, 1, ncclFloat64_, c->comm, c->s_main));
+    }
+    CU(cudaGetLastError());
+    return n;
+}
+
+int ensure_graph(npsl_ctx *c) {
+    if (c->step_graph) return 0;
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamBeginCapture(c->s_main, cudaStreamCaptureModeThreadLocal));
+    int n = issue(c, true, false, false, false);
+    cudaError_t e = cudaStreamEndCapture(c->s_main, &g);
+    if (n < 0) {
+        if (g) cudaGraphDestroy(g);
+        return n;
+    }
+    if (e != cudaSuccess) return fail(c, NPSL_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e));
+    c->launches_per_step = n;
+    e = cudaGraphInstantiate(&c->step_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(c, NPSL_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int collect_timing(npsl_ctx *c) {
+    if (!c->t_used) return 0;
+    CU(cudaStreamSynchronize(c->s_main));
+    for (size_t k = 0; k + 1 < c->t_used; k += 2) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->t_ev[k], c->t_ev[k + 1]));
+        c->t_sum_ms += ms;
+        c->t_count++;
+    }
+    c->t_used = 0;
+    return 0;
+}
+
+// in-place all-gather of a per-vertex record array laid out as world*range records
+int gather_records(npsl_ctx *c, double4 *buf) {
+    if (c->world == 1) return 0;
+    NC(g_nccl.AllGather(buf + (size_t) c->rank * c->range, buf, (size_t) c->range * 4, ncclFloat64_, c->comm,
+                        c->s_main));
+    return 0;
+}
+
+int download_records(npsl_ctx *c, double4 *dev, double *out, bool gather) {
+    if (!out) return 0;
+    if (gather) {
+        int r = gather_records(c, dev);
+        if (r) return r;
+    }
+    c->stage.resize(c->nv);
+    CU(cudaMemcpyAsync(c->stage.data(), dev, sizeof(double4) * c->nv, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    for (int i = 0; i < c->nv; i++) {
+        out[3 * i] = c->stage[i].x;
+        out[3 * i + 1] = c->stage[i].y;
+        out[3 * i + 2] = c->stage[i].z;
+    }
+    return 0;
+}
+
+int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, int world, const void *nccl_id,
+                npsl_ctx **out) {
+    npsl_ctx *c = nullptr;
+    if (!out) return fail(c, NPSL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!mesh || !prm || !mesh->edge_v || !mesh->face_v || !mesh->l0) return fail(c, NPSL_ERR_ARG, "NULL argument");
+    if (mesh->n_vertices < 4 || mesh->n_edges < 6 || mesh->n_faces < 4) return fail(c, NPSL_ERR_ARG, "mesh too small");
+    if (world < 1 || rank < 0 || rank >= world) return fail(c, NPSL_ERR_ARG, "bad rank/world");
+    if (prm->chain < 1 || prm->chain > NPSL_MAX_CHAIN) return fail(c, NPSL_ERR_ARG, "chain length out of range");
+    if (!(prm->inv_kappa_out > 0) || !(prm->em > 0)) return fail(c, NPSL_ERR_ARG, "inv_kappa_out and em must be positive");
+    if (world > 1 && !nccl_id) return fail(c, NPSL_ERR_ARG, "sharded context needs an NCCL unique id");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(c, NPSL_ERR_CUDA, "no CUDA device (%s); this library has no CPU path",
+                    ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+    Tables tb;
+    std::string why;
+    if (build_tables(mesh, tb, why)) return fail(c, NPSL_ERR_ARG, "unsupported mesh: %s", why.c_str());
+
+    c = new npsl_ctx();
+    npsl_ctx *guard = c;
+    auto bail = [&](int code) { std::string e = c->err; npsl_destroy(guard); g_error = e; return code; };
+#define CUB(call)                                                                                 \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            fail(c, NPSL_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));                      \
+            return bail(NPSL_ERR_CUDA);                                                           \
+        }                                                                                         \
+    } while (0)
+    CUB(cudaGetDevice(&c->device));
+    cudaDeviceProp prop;
+    CUB(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major < 10) {
+        fail(c, NPSL_ERR_CUDA, "device %s is sm_%d%d; this build targets sm_100a only", prop.name, prop.major, prop.minor);
+        return bail(NPSL_ERR_CUDA);
+    }
+    c->nv = mesh->n_vertices; c->ne = mesh->n_edges; c->nf = mesh->n_faces;
+    c->rank = rank; c->world = world;
+    c->range = (c->nv + world - 1) / world;  // src/main.cpp:448
+    c->row_lo = std::min(rank * c->range, c->nv);
+    c->row_hi = std::min((rank + 1) * c->range, c->nv);
+    if (c->row_hi <= c->row_lo) {
+        fail(c, NPSL_ERR_ARG, "rank %d of %d owns no rows of %d vertices", rank, world, c->nv);
+        return bail(NPSL_ERR_ARG);
+    }
+    c->prm = *prm;
+    const size_t nrec = (size_t) c->range * world;
+    CUB(dalloc(&c->xyzq, nrec)); CUB(dalloc(&c->vel, nrec)); CUB(dalloc(&c->force, nrec));
+    for (int k = 0; k < 5; k++) CUB(dalloc(&c->comp[k], nrec));
+    CUB(dalloc(&c->face_v, c->nf)); CUB(dalloc(&c->edge_rec, c->ne)); CUB(dalloc(&c->l0, c->ne));
+    CUB(dalloc(&c->degree, c->nv)); CUB(dalloc(&c->ring, (size_t) kMaxDeg * c->nv));
+    CUB(dalloc(&c->ring_l0, (size_t) kMaxDeg * c->nv)); CUB(dalloc(&c->bslot_ref, (size_t) 2 * kMaxDeg * c->nv));
+    CUB(dalloc(&c->bslot, (size_t) 4 * c->ne));
+    CUB(dalloc(&c->lj_out, c->range)); CUB(dalloc(&c->lj_hit, 1));
+    CUB(dalloc(&c->scal, SC_COUNT)); CUB(dalloc(&c->scal_all, (size_t) SC_COUNT * world));
+    CUB(dalloc(&c->ke_parts, world));
+    CUB(dalloc(&c->th_cur, 1)); CUB(dalloc(&c->th_mid, 1));
+    CUB(dalloc(&c->tickets, 4));
+    CUB(dalloc(&c->face_dir_area, c->nf)); CUB(dalloc(&c->face_vol, c->nf)); CUB(dalloc(&c->edge_S, c->ne));
+    CUB(dalloc(&c->peak_out, 1));
+    CUB(cudaMemcpy(c->face_v, tb.face_v.data(), sizeof(int4) * c->nf, cudaMemcpyHostToDevice));
+    CUB(cudaMemcpy(c->edge_rec, tb.edge_rec.data(), sizeof(int4) * c->ne, cudaMemcpyHostToDevice));
+    CUB(cudaMemcpy(c->l0, mesh->l0, sizeof(double) * c->ne, cudaMemcpyHostToDevice));
+    CUB(cudaMemcpy(c->degree, tb.degree.data(), sizeof(int) * c->nv, cudaMemcpyHostToDevice));
+    CUB(cudaMemcpy(c->ring, tb.ring.data(), sizeof(int) * tb.ring.size(), cudaMemcpyHostToDevice));
+    CUB(cudaMemcpy(c->ring_l0, tb.ring_l0.data(), sizeof(double) * tb.ring_l0.size(), cudaMemcpyHostToDevice));
+    CUB(cudaMemcpy(c->bslot_ref, tb.bslot_ref.data(), sizeof(int) * tb.bslot_ref.size(), cudaMemcpyHostToDevice));
+
+    plan_pair(c, prop.multiProcessorCount);
+    CUB(dalloc(&c->pair_partial, (size_t) c->pair_splits * c->pair_row_stride));
+    c->n_face_blocks = (c->nf + kMeshThreads - 1) / kMeshThreads;
+    c->n_edge_blocks = (c->ne + kMeshThreads - 1) / kMeshThreads;
+    c->n_vertex_blocks = (c->row_hi - c->row_lo + kMeshThreads - 1) / kMeshThreads;
+    CUB(dalloc(&c->part_mesh, (size_t) 4 * (c->n_face_blocks + c->n_edge_blocks)));
+    CUB(dalloc(&c->part_vert, (size_t) 3 * c->n_vertex_blocks));
+
+    const double lam = prm->inv_kappa_out;
+    c->pp.c2 = -1.4426950408889634074 / lam;
+    c->pp.inv_lambda = 1.0 / lam;
+    c->pp.n = c->nv; c->pp.row_lo = c->row_lo; c->pp.row_hi = c->row_hi;
+    c->pp.cols_per_cta = c->pair_cols_per_cta; c->pp.n_splits = c->pair_splits; c->pp.row_stride = c->pair_row_stride;
+    const double d2 = prm->lj_length_mesh_mesh * prm->lj_length_mesh_mesh;
+    const double cut2 = 1.25992104989487316476 * d2;  // dcut2, src/utility.h:37
+    c->pp.lj_cut_hi = high_word(cut2) + 1;             // conservative: exact test happens in k_lj
+    c->ljp.d2 = d2; c->ljp.cut2 = cut2; c->ljp.elj = prm->elj;
+    c->ljp.n = c->nv; c->ljp.row_lo = c->row_lo; c->ljp.row_hi = c->row_hi;
+    MeshParams &mp = c->mp;
+    mp.nv = c->nv; mp.ne = c->ne; mp.nf = c->nf; mp.row_lo = c->row_lo; mp.row_hi = c->row_hi;
+    mp.n_ranks = world; mp.chain = prm->chain; mp.buckling = prm->buckling ? 1 : 0;
+    mp.n_splits = c->pair_splits; mp.row_stride = c->pair_row_stride; mp.use_pair = 0;
+    mp.dt = prm->dt; mp.pair_coef = prm->scalefactor / prm->em;
+    mp.bkappa = prm->bkappa; mp.sconstant = prm->sconstant; mp.sigma_a = prm->sigma_a; mp.sigma_v = prm->sigma_v;
+    mp.ref_volume = prm->ref_volume; mp.avg_edge = prm->avg_edge_length;
+    Thermo th;
+    memset(&th, 0, sizeof th);
+    fill_thermo(th, prm->mesh_bath, prm->ions_bath);
+    CUB(cudaMemcpy(c->th_cur, &th, sizeof th, cudaMemcpyHostToDevice));
+    CUB(cudaMemcpy(c->th_mid, &th, sizeof th, cudaMemcpyHostToDevice));
+
+    CUB(cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&c->s_side, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+#undef CUB
+    if (world > 1) {
+        std::string e;
+        if (!load_nccl(e)) { fail(c, NPSL_ERR_NCCL, "%s", e.c_str()); return bail(NPSL_ERR_NCCL); }
+        ncclUniqueId id;
+        memcpy(&id, nccl_id, sizeof id);
+        int r = g_nccl.CommInitRank(&c->comm, world, id, rank);
+        if (r != 0) { fail(c, NPSL_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); return bail(NPSL_ERR_NCCL); }
+    }
+    *out = c;
+    return NPSL_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int npsl_abi_version(void) { return NPSL_ABI_VERSION; }
+
+const char *npsl_last_error(const npsl_ctx *ctx) { return ctx ? ctx->err.c_str() : g_error.c_str(); }
+
+int npsl_create(const npsl_mesh_desc *mesh, const npsl_params *params, npsl_ctx **out) {
+    return create_impl(mesh, params, 0, 1, nullptr, out);
+}
+
+int npsl_create_sharded(const npsl_mesh_desc *mesh, const npsl_params *params, int rank, int world,
+                        const void *nccl_unique_id, npsl_ctx **out) {
+    return create_impl(mesh, params, rank, world, nccl_unique_id, out);
+}
+
+int npsl_nccl_unique_id(void *out_id) {
+    npsl_ctx *c = nullptr;
+    if (!out_id) return fail(c, NPSL_ERR_ARG, "out_id is NULL");
+    std::string e;
+    if (!load_nccl(e)) return fail(c, NPSL_ERR_NCCL, "%s", e.c_str());
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(out_id, &id, sizeof id);
+    return NPSL_OK;
+}
+
+void npsl_destroy(npsl_ctx *c) {
+    if (!c) return;
+    if (c->s_main) cudaStreamSynchronize(c->s_main);
+    if (c->s_side) cudaStreamSynchronize(c->s_side);
+    if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+    if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
+    for (cudaEvent_t e : c->t_ev) cudaEventDestroy(e);
+    void *ptrs[] = {c->xyzq, c->vel, c->force, c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->face_v,
+                    c->edge_rec, c->l0, c->degree, c->ring, c->bslot_ref, c->ring_l0, c->bslot, c->pair_partial,
+                    c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_parts, c->th_cur, c->th_mid, c->part_mesh,
+                    c->part_vert, c->tickets, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->s_main) cudaStreamDestroy(c->s_main);
+    if (c->s_side) cudaStreamDestroy(c->s_side);
+    delete c;
+}
+
+// ---- state ----------------------------------------------------------------------------------------
+
+int npsl_upload_state(npsl_ctx *c, const double *pos, const double *vel, const double *q) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    const int n = c->nv;
+    if (pos || q) {
+        c->stage.resize(n);
+        CU(cudaMemcpyAsync(c->stage.data(), c->xyzq, sizeof(double4) * n, cudaMemcpyDeviceToHost, c->s_main));
+        CU(cudaStreamSynchronize(c->s_main));
+        for (int i = 0; i < n; i++) {
+            if (pos) { c->stage[i].x = pos[3 * i]; c->stage[i].y = pos[3 * i + 1]; c->stage[i].z = pos[3 * i + 2]; }
+            if (q) c->stage[i].w = q[i];
+        }
+        if (q) {
+            c->all_q_zero = true;
+            for (int i = 0; i < n; i++)
+                if (q[i] != 0.0) { c->all_q_zero = false; break; }
+            const int use = c->all_q_zero ? 0 : 1;
+            if (use != c->mp.use_pair) {
+                c->mp.use_pair = use;
+                if (c->step_graph) { cudaGraphExecDestroy(c->step_graph); c->step_graph = nullptr; }
+            }
+        }
+        CU(cudaMemcpyAsync(c->xyzq, c->stage.data(), sizeof(double4) * n, cudaMemcpyHostToDevice, c->s_main));
+        CU(cudaStreamSynchronize(c->s_main));
+        if (pos) c->forces_valid = false;
+    }
+    if (vel) {
+        c->stage.resize(n);
+        for (int i = 0; i < n; i++) c->stage[i] = make_double4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], 0.0);
+        CU(cudaMemcpyAsync(c->vel, c->stage.data(), sizeof(double4) * n, cudaMemcpyHostToDevice, c->s_main));
+        CU(cudaStreamSynchronize(c->s_main));
+    }
+    return NPSL_OK;
+}
+
+int npsl_download_state(npsl_ctx *c, double *pos, double *vel, double *force) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    int r;
+    if ((r = download_records(c, c->xyzq, pos, false))) return r;
+    if ((r = download_records(c, c->vel, vel, true))) return r;
+    if ((r = download_records(c, c->force, force, true))) return r;
+    return collect_timing(c);
+}
+
+int npsl_download_force_components(npsl_ctx *c, double *pair, double *bending, double *stretching, double *tension,
+                                   double *volume_tension) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    if (!c->forces_valid) return fail(c, NPSL_ERR_STATE, "no force evaluation at the current positions");
+    double *outs[5] = {pair, bending, stretching, tension, volume_tension};
+    for (int k = 0; k < 5; k++) {
+        int r = download_records(c, c->comp[k], outs[k], true);
+        if (r) return r;
+    }
+    return NPSL_OK;
+}
+
+int npsl_download_mesh_fields(npsl_ctx *c, double *face_area, double *face_volume, double *face_dir, double *edge_S) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    if (face_area || face_dir) {
+        std::vector<double4> tmp(c->nf);
+        CU(cudaMemcpyAsync(tmp.data(), c->face_dir_area, sizeof(double4) * c->nf, cudaMemcpyDeviceToHost, c->s_main));
+        CU(cudaStreamSynchronize(c->s_main));
+        for (int f = 0; f < c->nf; f++) {
+            if (face_area) face_area[f] = tmp[f].w;
+            if (face_dir) { face_dir[3 * f] = tmp[f].x; face_dir[3 * f + 1] = tmp[f].y; face_dir[3 * f + 2] = tmp[f].z; }
+        }
+    }
+    if (face_volume) CU(cudaMemcpyAsync(face_volume, c->face_vol, sizeof(double) * c->nf, cudaMemcpyDeviceToHost, c->s_main));
+    if (edge_S) CU(cudaMemcpyAsync(edge_S, c->edge_S, sizeof(double) * c->ne, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    return NPSL_OK;
+}
+
+int npsl_get_thermostat(npsl_ctx *c, npsl_bath_link *mesh_bath, npsl_bath_link *ions_bath) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    Thermo th;
+    CU(cudaMemcpyAsync(&th, c->th_cur, sizeof th, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    for (int j = 0; j < c->prm.chain; j++) {
+        if (mesh_bath) mesh_bath[j] = {th.mesh[j].Q, th.mesh[j].T, th.mesh[j].dof, th.mesh[j].xi, th.mesh[j].eta};
+        if (ions_bath) ions_bath[j] = {th.ions[j].Q, th.ions[j].T, th.ions[j].dof, th.ions[j].xi, th.ions[j].eta};
+    }
+    return NPSL_OK;
+}
+
+int npsl_set_thermostat(npsl_ctx *c, const npsl_bath_link *mesh_bath, const npsl_bath_link *ions_bath) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    Thermo th;
+    CU(cudaMemcpyAsync(&th, c->th_cur, sizeof th, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    for (int j = 0; j < c->prm.chain; j++) {
+        if (mesh_bath) th.mesh[j] = {mesh_bath[j].Q, mesh_bath[j].T, mesh_bath[j].dof, mesh_bath[j].xi, mesh_bath[j].eta};
+        if (ions_bath) th.ions[j] = {ions_bath[j].Q, ions_bath[j].T, ions_bath[j].dof, ions_bath[j].xi, ions_bath[j].eta};
+    }
+    CU(cudaMemcpyAsync(c->th_cur, &th, sizeof th, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    return NPSL_OK;
+}
+
+// ---- the path -------------------------------------------------------------------------------------
+
+int npsl_dressup(npsl_ctx *c, double *total_area, double *total_volume) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    k_mesh<false, true><<<c->n_face_blocks + c->n_edge_blocks, kMeshThreads, 0, c->s_main>>>(
+        c->xyzq, c->face_v, c->edge_rec, c->l0, c->bslot, c->part_mesh, c->tickets, c->scal, c->face_dir_area,
+        c->face_vol, c->edge_S, c->n_face_blocks, c->mp);
+    c->launches++;
+    double s[2];
+    CU(cudaMemcpyAsync(s, c->scal + SC_AREA, sizeof s, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    if (total_area) *total_area = s[0];
+    if (total_volume) *total_volume = s[1];
+    return NPSL_OK;
+}
+
+static int force_pass(npsl_ctx *c) {
+    int n = issue(c, false, true, true, false);
+    if (n < 0) return n;
+    c->launches += n;
+    c->forces_valid = true;
+    return NPSL_OK;
+}
+
+int npsl_force_init(npsl_ctx *c) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    return force_pass(c);
+}
+
+int npsl_force(npsl_ctx *c) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    return force_pass(c);
+}
+
+int npsl_step(npsl_ctx *c, int n_steps) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    if (n_steps < 0) return fail(c, NPSL_ERR_ARG, "n_steps < 0");
+    if (!c->forces_valid) return fail(c, NPSL_ERR_STATE, "npsl_step before npsl_force_init");
+    if (c->timing) {
+        for (int k = 0; k < n_steps; k++) {
+            if (c->t_used + 2 > c->t_ev.size()) {
+                int r = collect_timing(c);
+                if (r) return r;
+            }
+            int n = issue(c, true, false, false, true);
+            if (n < 0) return n;
+            c->launches += n;
+        }
+        return NPSL_OK;
+    }
+    int r = ensure_graph(c);
+    if (r) return r;
+    for (int k = 0; k < n_steps; k++) CU(cudaGraphLaunch(c->step_graph, c->s_main));
+    c->launches += (int64_t) c->launches_per_step * n_steps;
+    return NPSL_OK;
+}
+
+int npsl_energy(npsl_ctx *c, npsl_energies *out) {
+    if (!c || !out) return fail(c, NPSL_ERR_ARG, "NULL argument");
+    if (!c->forces_valid) return fail(c, NPSL_ERR_STATE, "npsl_energy before npsl_force_init");
+    // INTERFACE::compute_energy re-walks the pair loop at the current positions and reuses the
+    // cached EDGE::itsS / face areas (src/interface.cpp:990-1065); positions have not moved since
+    // the last force evaluation, so one energy-enabled force pass yields identical values.
+    int r = force_pass(c);
+    if (r) return r;
+    std::vector<double> all((size_t) SC_COUNT * c->world);
+    if (c->world > 1) {
+        NC(g_nccl.AllGather(c->scal, c->scal_all, SC_COUNT, ncclFloat64_, c->comm, c->s_main));
+        CU(cudaMemcpyAsync(all.data(), c->scal_all, sizeof(double) * all.size(), cudaMemcpyDeviceToHost, c->s_main));
+    } else {
+        CU(cudaMemcpyAsync(all.data(), c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->s_main));
+    }
+    Thermo th;
+    CU(cudaMemcpyAsync(&th, c->th_cur, sizeof th, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    double ke = 0, es = 0, lj = 0;
+    for (int k = 0; k < c->world; k++) {  // fixed rank order
+        ke += all[(size_t) k * SC_COUNT + SC_KE];
+        es += all[(size_t) k * SC_COUNT + SC_ES];
+        lj += all[(size_t) k * SC_COUNT + SC_LJ];
+    }
+    const double *s = all.data() + (size_t) c->rank * SC_COUNT;
+    const npsl_params &p = c->prm;
+    out->kinetic = ke;
+    out->bending = s[SC_BE];
+    out->stretching = s[SC_SE];
+    out->total_area = s[SC_AREA];
+    out->total_volume = s[SC_VOL];
+    out->tension = p.sigma_a * s[SC_AREA];
+    const double dv = s[SC_VOL] - p.ref_volume;
+    out->volume = p.sigma_v * (dv * dv);
+    out->lj = lj;
+    out->electrostatic = es;
+    out->potential = out->bending + out->stretching + out->tension + out->volume + (out->lj + out->electrostatic);
+    out->energy = out->kinetic + out->potential;
+    double mk = 0, mpe = 0, ik = 0, ipe = 0;  // src/newenergies.h:28-46, src/thermostat.h:61-70 (kB = 1)
+    for (int j = 0; j < p.chain; j++) {
+        mk += 0.5 * th.mesh[j].Q * th.mesh[j].xi * th.mesh[j].xi;
+        mpe += th.mesh[j].dof * th.mesh[j].T * th.mesh[j].eta;
+        ik += 0.5 * th.ions[j].Q * th.ions[j].xi * th.ions[j].xi;
+        ipe += th.ions[j].dof * th.ions[j].T * th.ions[j].eta;
+    }
+    out->mesh_bath_ke = mk; out->mesh_bath_pe = mpe; out->ions_bath_ke = ik; out->ions_bath_pe = ipe;
+    if (!std::isfinite(out->energy)) return fail(c, NPSL_ERR_NUMERIC, "non-finite energy");
+    return NPSL_OK;
+}
+
+int npsl_sync(npsl_ctx *c) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    CU(cudaStreamSynchronize(c->s_main));
+    CU(cudaGetLastError());
+    return collect_timing(c);
+}
+
+// ---- introspection -----------------------------------------------------------------------------------
+
+int64_t npsl_launch_count(const npsl_ctx *c) { return c ? c->launches : 0; }
+
+int npsl_pair_timing(npsl_ctx *c, int enable) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    int r = collect_timing(c);
+    if (r) return r;
+    c->timing = enable != 0;
+    if (c->timing && c->t_ev.empty()) {
+        c->t_ev.resize(512);
+        for (auto &e : c->t_ev) CU(cudaEventCreate(&e));
+    }
+    c->t_sum_ms = 0;
+    c->t_count = 0;
+    return NPSL_OK;
+}
+
+int npsl_pair_timing_read(npsl_ctx *c, double *mean_ms, int64_t *launches) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    int r = collect_timing(c);
+    if (r) return r;
+    if (mean_ms) *mean_ms = c->t_count ? c->t_sum_ms / (double) c->t_count : 0.0;
+    if (launches) *launches = c->t_count;
+    return NPSL_OK;
+}
+
+int npsl_owned_rows(const npsl_ctx *c, int32_t *lo, int32_t *hi) {
+    if (!c) return NPSL_ERR_ARG;
+    if (lo) *lo = c->row_lo;
+    if (hi) *hi = c->row_hi;
+    return NPSL_OK;
+}
+
+int npsl_pair_geometry(const npsl_ctx *c, int32_t *rows_per_thread, int32_t *row_tiles, int32_t *col_splits,
+                       int32_t *cols_per_cta) {
+    if (!c) return NPSL_ERR_ARG;
+    if (rows_per_thread) *rows_per_thread = c->pair_rows_per_thread;
+    if (row_tiles) *row_tiles = c->pair_row_tiles;
+    if (col_splits) *col_splits = c->pair_splits;
+    if (cols_per_cta) *cols_per_cta = c->pair_cols_per_cta;
+    return NPSL_OK;
+}
+
+int npsl_fp64_peak(double *dfma_per_s, double *sm_clock_mhz) {
+    npsl_ctx *c = nullptr;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    double *out = nullptr;
+    CU(cudaMalloc((void **) &out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    k_dfma_peak<<<blocks, threads>>>(out, 1 << 10, 1.0000001, 0.9999999);  // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 3; rep++) {
+        CU(cudaEventRecord(e0));
+        k_dfma_peak<<<blocks, threads>>>(out, iters, 1.0000001, 0.9999999);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double rate = (double) blocks * threads * 16.0 * iters / (ms * 1e-3);
+        best = std::max(best, rate);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    CU(cudaGetLastError());
+    if (dfma_per_s) *dfma_per_s = best;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+    if (sm_clock_mhz) *sm_clock_mhz = khz / 1000.0;
+    return NPSL_OK;
+}
+
+}  // extern "C"
