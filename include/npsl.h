@@ -158,6 +158,20 @@ int npsl_energy(npsl_ctx *ctx, npsl_energies *out);
 
 int npsl_sync(npsl_ctx *ctx);
 
+/* ---- host-buffer entry points (what a caller holding the reference's AoS mesh uses) -------- */
+
+/* force_calculation with host buffers (src/newforces.cpp:137-289 as md_interface calls it,
+ * src/newmd.cpp:143): positions [n][3] host -> device, every force term, total force [n][3]
+ * (VERTEX::forvec) device -> host. pos == NULL keeps the device positions, force == NULL skips the
+ * read-back. Host<->device copies go through pinned staging owned by the context. */
+int npsl_force_calculation(npsl_ctx *ctx, const double *pos, double *force);
+
+/* md_interface with host buffers (src/newmd.cpp:9-323 without its file writers): upload
+ * pos/vel/q (NULL = keep), force_calculation_init, n_steps loop iterations, compute_energy at the
+ * final state, download positions / velocities (NULL = skip). */
+int npsl_md_run(npsl_ctx *ctx, const double *pos, const double *vel, const double *q, int n_steps,
+                npsl_energies *energies_out, double *pos_out, double *vel_out);
+
 /* ---- introspection (measurement only) --------------------------------------------------- */
 
 /* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
@@ -166,6 +180,14 @@ int64_t npsl_launch_count(const npsl_ctx *ctx);
  * CUDA events on the context's stream when timing is enabled. */
 int npsl_pair_timing(npsl_ctx *ctx, int enable);
 int npsl_pair_timing_read(npsl_ctx *ctx, double *mean_ms, int64_t *launches);
+/* Device time in ms of n_steps steps (one CUDA-graph launch each), measured with CUDA events on the
+ * context's own stream. flush_l2 != 0: a buffer larger than L2 is overwritten before every step,
+ * outside that step's event bracket; the result is the sum of the per-step brackets. */
+int npsl_step_timing(npsl_ctx *ctx, int n_steps, int flush_l2, double *total_ms);
+/* Override the pair kernel's launch plan (rows per thread in {1,2,4}, column splits >= 1); 0 keeps
+ * the automatic choice for that field. Results do not depend on rows_per_thread; they depend on
+ * col_splits only through the (fixed, ordered) grouping of the column sum. */
+int npsl_set_pair_plan(npsl_ctx *ctx, int rows_per_thread, int col_splits);
 /* Owned row range of this context, half-open. */
 int npsl_owned_rows(const npsl_ctx *ctx, int32_t *lo, int32_t *hi);
 /* Launch geometry of the pair kernel: rows per thread, row tiles x column splits, columns per CTA. */

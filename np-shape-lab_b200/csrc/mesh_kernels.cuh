@@ -462,4 +462,26 @@ __global__ void k_thermo_post(const Thermo *__restrict__ th_mid, Thermo *__restr
     *th_cur = t;
 }
 
+// ------------------------------------------------------------------------------------------------
+// AoS <-> record conversion on the device (the boundary hands over packed [n][3] doubles, the
+// layout of an array of VECTOR3D-as-double; the kernels work on 32-byte records).
+__global__ void k_scatter3(double4 *__restrict__ rec, const double *__restrict__ packed, int n, int keep_w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double w = keep_w ? rec[i].w : 0.0;
+    rec[i] = make_double4(packed[3 * i], packed[3 * i + 1], packed[3 * i + 2], w);
+}
+__global__ void k_scatter_w(double4 *__restrict__ rec, const double *__restrict__ w, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rec[i].w = w[i];
+}
+__global__ void k_gather3(const double4 *__restrict__ rec, double *__restrict__ packed, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 v = rec[i];
+    packed[3 * i] = v.x;
+    packed[3 * i + 1] = v.y;
+    packed[3 * i + 2] = v.z;
+}
+
 }  // namespace npsl

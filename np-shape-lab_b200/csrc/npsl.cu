@@ -121,7 +121,15 @@ struct npsl_ctx {
     double t_sum_ms = 0;
     int64_t t_count = 0;
 
-    std::vector<double4> stage;  // host staging for AoS<->record conversion
+    // host<->device staging for the packed [n][3] arrays of the boundary: pinned host + device
+    double *h_pin[2] = {nullptr, nullptr};
+    double *d_pack[2] = {nullptr, nullptr};
+    // measurement: L2 flush buffer and per-step event brackets of npsl_step_timing
+    void *flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    std::vector<cudaEvent_t> s_ev;
+    int plan_rows = 0, plan_splits = 0;  // overrides of npsl_set_pair_plan (0 = automatic)
+    int n_sm = 148;
     std::string err;
 };
 
@@ -269,18 +277,28 @@ int high_word(double x) {
 // never changes which terms are summed in which order within a split.
 void plan_pair(npsl_ctx *c, int n_sm) {
     const int rows = c->row_hi - c->row_lo;
-    c->pair_rows_per_thread = 2;
+    c->pair_rows_per_thread = c->plan_rows ? c->plan_rows : 2;
     const int tile_rows = kPairThreads * c->pair_rows_per_thread;
     c->pair_row_tiles = std::max(1, (rows + tile_rows - 1) / tile_rows);
     const int col_tiles = (c->nv + kPairTileJ - 1) / kPairTileJ;
     // aim for >= 16 CTAs per SM in flight over the launch, but keep at least 2 column tiles per CTA
     int want = (16 * n_sm + c->pair_row_tiles - 1) / c->pair_row_tiles;
     int splits = std::max(1, std::min(want, std::max(1, col_tiles / 2)));
+    if (c->plan_splits) splits = std::max(1, std::min(c->plan_splits, col_tiles));
     int tiles_per_cta = (col_tiles + splits - 1) / splits;
     splits = (col_tiles + tiles_per_cta - 1) / tiles_per_cta;
     c->pair_splits = splits;
     c->pair_cols_per_cta = tiles_per_cta * kPairTileJ;
     c->pair_row_stride = (rows + 31) / 32 * 32;
+}
+
+// copies the launch plan into the kernel parameter blocks
+void apply_pair_plan(npsl_ctx *c) {
+    c->pp.cols_per_cta = c->pair_cols_per_cta;
+    c->pp.n_splits = c->pair_splits;
+    c->pp.row_stride = c->pair_row_stride;
+    c->mp.n_splits = c->pair_splits;
+    c->mp.row_stride = c->pair_row_stride;
 }
 
 template <int ROWS>
@@ -408,21 +426,39 @@ int gather_records(npsl_ctx *c, double4 *buf) {
     return 0;
 }
 
-int download_records(npsl_ctx *c, double4 *dev, double *out, bool gather) {
+// records on the device -> packed [nv][3] host array, through the pinned staging buffer `slot`
+int download_records(npsl_ctx *c, double4 *dev, double *out, bool gather, int slot = 0) {
     if (!out) return 0;
     if (gather) {
         int r = gather_records(c, dev);
         if (r) return r;
     }
-    c->stage.resize(c->nv);
-    CU(cudaMemcpyAsync(c->stage.data(), dev, sizeof(double4) * c->nv, cudaMemcpyDeviceToHost, c->s_main));
+    const int nb = (c->nv + 255) / 256;
+    k_gather3<<<nb, 256, 0, c->s_main>>>(dev, c->d_pack[slot], c->nv);
+    c->launches++;
+    CU(cudaMemcpyAsync(c->h_pin[slot], c->d_pack[slot], sizeof(double) * 3 * c->nv, cudaMemcpyDeviceToHost, c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
-    for (int i = 0; i < c->nv; i++) {
-        out[3 * i] = c->stage[i].x;
-        out[3 * i + 1] = c->stage[i].y;
-        out[3 * i + 2] = c->stage[i].z;
-    }
+    memcpy(out, c->h_pin[slot], sizeof(double) * 3 * c->nv);
     return 0;
+}
+
+// packed [nv][3] host array -> xyz of the device records (w kept or zeroed)
+int upload_records(npsl_ctx *c, double4 *dev, const double *in, bool keep_w, int slot = 0) {
+    if (!in) return 0;
+    CU(cudaStreamSynchronize(c->s_main));  // the staging buffer may still be in flight
+    memcpy(c->h_pin[slot], in, sizeof(double) * 3 * c->nv);
+    CU(cudaMemcpyAsync(c->d_pack[slot], c->h_pin[slot], sizeof(double) * 3 * c->nv, cudaMemcpyHostToDevice, c->s_main));
+    const int nb = (c->nv + 255) / 256;
+    k_scatter3<<<nb, 256, 0, c->s_main>>>(dev, c->d_pack[slot], c->nv, keep_w ? 1 : 0);
+    c->launches++;
+    return 0;
+}
+
+void drop_graph(npsl_ctx *c) {
+    if (c->step_graph) {
+        cudaGraphExecDestroy(c->step_graph);
+        c->step_graph = nullptr;
+    }
 }
 
 int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, int world, const void *nccl_id,
@@ -495,7 +531,12 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     CUB(cudaMemcpy(c->ring_l0, tb.ring_l0.data(), sizeof(double) * tb.ring_l0.size(), cudaMemcpyHostToDevice));
     CUB(cudaMemcpy(c->bslot_ref, tb.bslot_ref.data(), sizeof(int) * tb.bslot_ref.size(), cudaMemcpyHostToDevice));
 
-    plan_pair(c, prop.multiProcessorCount);
+    for (int k = 0; k < 2; k++) {
+        CUB(cudaMallocHost((void **) &c->h_pin[k], sizeof(double) * 3 * c->nv));
+        CUB(dalloc(&c->d_pack[k], (size_t) 3 * c->nv));
+    }
+    c->n_sm = prop.multiProcessorCount;
+    plan_pair(c, c->n_sm);
     CUB(dalloc(&c->pair_partial, (size_t) c->pair_splits * c->pair_row_stride));
     c->n_face_blocks = (c->nf + kMeshThreads - 1) / kMeshThreads;
     c->n_edge_blocks = (c->ne + kMeshThreads - 1) / kMeshThreads;
@@ -507,7 +548,6 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     c->pp.c2 = -1.4426950408889634074 / lam;
     c->pp.inv_lambda = 1.0 / lam;
     c->pp.n = c->nv; c->pp.row_lo = c->row_lo; c->pp.row_hi = c->row_hi;
-    c->pp.cols_per_cta = c->pair_cols_per_cta; c->pp.n_splits = c->pair_splits; c->pp.row_stride = c->pair_row_stride;
     const double d2 = prm->lj_length_mesh_mesh * prm->lj_length_mesh_mesh;
     const double cut2 = 1.25992104989487316476 * d2;  // dcut2, src/utility.h:37
     c->pp.lj_cut_hi = high_word(cut2) + 1;             // conservative: exact test happens in k_lj
@@ -516,7 +556,8 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     MeshParams &mp = c->mp;
     mp.nv = c->nv; mp.ne = c->ne; mp.nf = c->nf; mp.row_lo = c->row_lo; mp.row_hi = c->row_hi;
     mp.n_ranks = world; mp.chain = prm->chain; mp.buckling = prm->buckling ? 1 : 0;
-    mp.n_splits = c->pair_splits; mp.row_stride = c->pair_row_stride; mp.use_pair = 0;
+    mp.use_pair = 0;
+    apply_pair_plan(c);
     mp.dt = prm->dt; mp.pair_coef = prm->scalefactor / prm->em;
     mp.bkappa = prm->bkappa; mp.sconstant = prm->sconstant; mp.sigma_a = prm->sigma_a; mp.sigma_v = prm->sigma_v;
     mp.ref_volume = prm->ref_volume; mp.avg_edge = prm->avg_edge_length;
@@ -579,6 +620,12 @@ void npsl_destroy(npsl_ctx *c) {
     if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
     for (cudaEvent_t e : c->t_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->s_ev) cudaEventDestroy(e);
+    for (int k = 0; k < 2; k++) {
+        if (c->h_pin[k]) cudaFreeHost(c->h_pin[k]);
+        if (c->d_pack[k]) cudaFree(c->d_pack[k]);
+    }
+    if (c->flush_buf) cudaFree(c->flush_buf);
     void *ptrs[] = {c->xyzq, c->vel, c->force, c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->face_v,
                     c->edge_rec, c->l0, c->degree, c->ring, c->bslot_ref, c->ring_l0, c->bslot, c->pair_partial,
                     c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_parts, c->th_cur, c->th_mid, c->part_mesh,
@@ -597,43 +644,37 @@ void npsl_destroy(npsl_ctx *c) {
 int npsl_upload_state(npsl_ctx *c, const double *pos, const double *vel, const double *q) {
     if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
     const int n = c->nv;
-    if (pos || q) {
-        c->stage.resize(n);
-        CU(cudaMemcpyAsync(c->stage.data(), c->xyzq, sizeof(double4) * n, cudaMemcpyDeviceToHost, c->s_main));
+    int r;
+    if ((r = upload_records(c, c->xyzq, pos, true, 0))) return r;
+    if (pos) c->forces_valid = false;
+    if ((r = upload_records(c, c->vel, vel, false, 1))) return r;
+    if (q) {
         CU(cudaStreamSynchronize(c->s_main));
-        for (int i = 0; i < n; i++) {
-            if (pos) { c->stage[i].x = pos[3 * i]; c->stage[i].y = pos[3 * i + 1]; c->stage[i].z = pos[3 * i + 2]; }
-            if (q) c->stage[i].w = q[i];
+        memcpy(c->h_pin[0], q, sizeof(double) * n);
+        CU(cudaMemcpyAsync(c->d_pack[0], c->h_pin[0], sizeof(double) * n, cudaMemcpyHostToDevice, c->s_main));
+        k_scatter_w<<<(n + 255) / 256, 256, 0, c->s_main>>>(c->xyzq, c->d_pack[0], n);
+        c->launches++;
+        c->all_q_zero = true;
+        for (int i = 0; i < n; i++)
+            if (q[i] != 0.0) { c->all_q_zero = false; break; }
+        const int use = c->all_q_zero ? 0 : 1;
+        if (use != c->mp.use_pair) {
+            c->mp.use_pair = use;
+            drop_graph(c);
         }
-        if (q) {
-            c->all_q_zero = true;
-            for (int i = 0; i < n; i++)
-                if (q[i] != 0.0) { c->all_q_zero = false; break; }
-            const int use = c->all_q_zero ? 0 : 1;
-            if (use != c->mp.use_pair) {
-                c->mp.use_pair = use;
-                if (c->step_graph) { cudaGraphExecDestroy(c->step_graph); c->step_graph = nullptr; }
-            }
-        }
-        CU(cudaMemcpyAsync(c->xyzq, c->stage.data(), sizeof(double4) * n, cudaMemcpyHostToDevice, c->s_main));
-        CU(cudaStreamSynchronize(c->s_main));
-        if (pos) c->forces_valid = false;
+        c->forces_valid = false;
     }
-    if (vel) {
-        c->stage.resize(n);
-        for (int i = 0; i < n; i++) c->stage[i] = make_double4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], 0.0);
-        CU(cudaMemcpyAsync(c->vel, c->stage.data(), sizeof(double4) * n, cudaMemcpyHostToDevice, c->s_main));
-        CU(cudaStreamSynchronize(c->s_main));
-    }
+    CU(cudaStreamSynchronize(c->s_main));
+    CU(cudaGetLastError());
     return NPSL_OK;
 }
 
 int npsl_download_state(npsl_ctx *c, double *pos, double *vel, double *force) {
     if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
     int r;
-    if ((r = download_records(c, c->xyzq, pos, false))) return r;
-    if ((r = download_records(c, c->vel, vel, true))) return r;
-    if ((r = download_records(c, c->force, force, true))) return r;
+    if ((r = download_records(c, c->xyzq, pos, false, 0))) return r;
+    if ((r = download_records(c, c->vel, vel, true, 1))) return r;
+    if ((r = download_records(c, c->force, force, true, 0))) return r;
     return collect_timing(c);
 }
 
@@ -799,6 +840,30 @@ int npsl_energy(npsl_ctx *c, npsl_energies *out) {
     return NPSL_OK;
 }
 
+int npsl_force_calculation(npsl_ctx *c, const double *pos, double *force) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    int r;
+    if ((r = upload_records(c, c->xyzq, pos, true, 0))) return r;
+    int n = issue(c, false, false, false, false);
+    if (n < 0) return n;
+    c->launches += n;
+    c->forces_valid = true;
+    if ((r = download_records(c, c->force, force, true, 1))) return r;
+    return NPSL_OK;
+}
+
+int npsl_md_run(npsl_ctx *c, const double *pos, const double *vel, const double *q, int n_steps,
+                npsl_energies *energies_out, double *pos_out, double *vel_out) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    int r;
+    if ((r = npsl_upload_state(c, pos, vel, q))) return r;
+    if ((r = npsl_force_init(c))) return r;
+    if ((r = npsl_step(c, n_steps))) return r;
+    if (energies_out && (r = npsl_energy(c, energies_out))) return r;
+    if ((r = npsl_download_state(c, pos_out, vel_out, nullptr))) return r;
+    return NPSL_OK;
+}
+
 int npsl_sync(npsl_ctx *c) {
     if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
     CU(cudaStreamSynchronize(c->s_main));
@@ -830,6 +895,73 @@ int npsl_pair_timing_read(npsl_ctx *c, double *mean_ms, int64_t *launches) {
     if (r) return r;
     if (mean_ms) *mean_ms = c->t_count ? c->t_sum_ms / (double) c->t_count : 0.0;
     if (launches) *launches = c->t_count;
+    return NPSL_OK;
+}
+
+int npsl_step_timing(npsl_ctx *c, int n_steps, int flush_l2, double *total_ms) {
+    if (!c || !total_ms) return fail(c, NPSL_ERR_ARG, "NULL argument");
+    if (n_steps < 1) return fail(c, NPSL_ERR_ARG, "n_steps < 1");
+    if (!c->forces_valid) return fail(c, NPSL_ERR_STATE, "npsl_step_timing before npsl_force_init");
+    int r = ensure_graph(c);
+    if (r) return r;
+    if (c->s_ev.size() < 2) {
+        c->s_ev.resize(2);
+        for (auto &e : c->s_ev) CU(cudaEventCreate(&e));
+    }
+    if (flush_l2 && !c->flush_buf) {
+        c->flush_bytes = (size_t) 256 << 20;  // 2x the 126 MB L2
+        CU(cudaMalloc(&c->flush_buf, c->flush_bytes));
+    }
+    double sum = 0;
+    if (!flush_l2) {
+        CU(cudaEventRecord(c->s_ev[0], c->s_main));
+        for (int k = 0; k < n_steps; k++) CU(cudaGraphLaunch(c->step_graph, c->s_main));
+        CU(cudaEventRecord(c->s_ev[1], c->s_main));
+        CU(cudaEventSynchronize(c->s_ev[1]));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->s_ev[0], c->s_ev[1]));
+        sum = ms;
+    } else {
+        // per-step brackets; the flush sits between them
+        const size_t need = (size_t) 2 * n_steps;
+        while (c->s_ev.size() < need) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            c->s_ev.push_back(e);
+        }
+        for (int k = 0; k < n_steps; k++) {
+            CU(cudaMemsetAsync(c->flush_buf, k & 0xff, c->flush_bytes, c->s_main));
+            CU(cudaEventRecord(c->s_ev[2 * k], c->s_main));
+            CU(cudaGraphLaunch(c->step_graph, c->s_main));
+            CU(cudaEventRecord(c->s_ev[2 * k + 1], c->s_main));
+        }
+        CU(cudaStreamSynchronize(c->s_main));
+        for (int k = 0; k < n_steps; k++) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, c->s_ev[2 * k], c->s_ev[2 * k + 1]));
+            sum += ms;
+        }
+    }
+    c->launches += (int64_t) c->launches_per_step * n_steps;
+    CU(cudaGetLastError());
+    *total_ms = sum;
+    return NPSL_OK;
+}
+
+int npsl_set_pair_plan(npsl_ctx *c, int rows_per_thread, int col_splits) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    if (!(rows_per_thread == 0 || rows_per_thread == 1 || rows_per_thread == 2 || rows_per_thread == 4) || col_splits < 0)
+        return fail(c, NPSL_ERR_ARG, "rows_per_thread must be 0,1,2,4 and col_splits >= 0");
+    CU(cudaStreamSynchronize(c->s_main));
+    c->plan_rows = rows_per_thread;
+    c->plan_splits = col_splits;
+    plan_pair(c, c->n_sm);
+    if (c->pair_partial) cudaFree(c->pair_partial);
+    c->pair_partial = nullptr;
+    CU(dalloc(&c->pair_partial, (size_t) c->pair_splits * c->pair_row_stride));
+    apply_pair_plan(c);
+    drop_graph(c);
+    c->forces_valid = false;
     return NPSL_OK;
 }
 

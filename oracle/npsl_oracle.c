@@ -447,6 +447,13 @@ void npo_md_init(void *hh) {
     h->vertex_ke = kinetic_energy(h);
 }
 
+/* compute_kinetic_energy at the current velocities (src/newmd.cpp:52) without the velocity reset of
+ * the prologue: lets a test continue the loop body from an arbitrary (pos, vel). */
+void npo_refresh_ke(void *hh) {
+    npo_t *h = (npo_t *) hh;
+    h->vertex_ke = kinetic_energy(h);
+}
+
 /* One iteration of the loop of md_interface, src/newmd.cpp:96-170 (no constraints, no ions) */
 void npo_md_step(void *hh) {
     npo_t *h = (npo_t *) hh;

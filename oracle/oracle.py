@@ -39,6 +39,7 @@ def lib():
         L.npo_force.argtypes = [vp, C.c_int, C.c_int]
         L.npo_energy.argtypes = [vp, C.c_int, C.c_int, dp]
         L.npo_md_init.argtypes = [vp]
+        L.npo_refresh_ke.argtypes = [vp]
         L.npo_md_step.argtypes = [vp]
         L.npo_md_steps.argtypes = [vp, C.c_int]
         L.npo_bath_energies.argtypes = [vp, dp]
@@ -113,6 +114,9 @@ class Oracle:
 
     def md_init(self):
         self.L.npo_md_init(self.h)
+
+    def refresh_ke(self):
+        self.L.npo_refresh_ke(self.h)
 
     def md_steps(self, n: int):
         self.L.npo_md_steps(self.h, int(n))

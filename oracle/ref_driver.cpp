@@ -73,6 +73,7 @@ struct Options {
     int writedata = 500;
     long row_lo = 0, row_hi = -1;
     int reps = 1;
+    int warm = 0;
 };
 
 bool parse(int argc, char **argv, Options &o) {
@@ -111,6 +112,7 @@ bool parse(int argc, char **argv, Options &o) {
         else if (a == "--row-lo") o.row_lo = atol(need("--row-lo"));
         else if (a == "--row-hi") o.row_hi = atol(need("--row-hi"));
         else if (a == "--reps") o.reps = atoi(need("--reps"));
+        else if (a == "--warm") o.warm = atoi(need("--warm"));
         else {
             std::fprintf(stderr, "unknown option %s\n", a.c_str());
             return false;
@@ -227,6 +229,7 @@ int main(int argc, char **argv) {
         sizFVecMesh = (unsigned) (hi - lo + 1);
         initialize_velocities_to_zero(boundary.V, counterions);
         double best = 1e300, total = 0;
+        for (int r = 0; r < o.warm; r++) force_calculation(boundary, counterions, scalefactor, o.B);  // untimed
         for (int r = 0; r < o.reps; r++) {
             double t0 = now_s();
             force_calculation(boundary, counterions, scalefactor, o.B);

@@ -1,0 +1,305 @@
+"""Parity of the CUDA path (through the C ABI, libnpsl.so) with the reference.
+
+Golden fixtures = the reference's own code (compiled unmodified, oracle/gen_golden.py); the oracle
+= its CPU restatement, used for inputs the fixtures do not hold (perturbed meshes, larger
+icospheres). Tolerances are the ones north_star states: per-vertex forces and every energy
+component to 1e-10 relative at steps 0/1, A/U/E trajectories to 1e-6 relative over 1000 steps."""
+import numpy as np
+import pytest
+
+from conftest import golden, make_oracle, relerr
+from np_shape_lab_b200 import capi
+from np_shape_lab_b200 import mesh as M
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+COMP = [("pair", "pforce"), ("bending", "bforce"), ("stretching", "sforce"), ("tension", "tforce"),
+        ("volume_tension", "vforce")]
+E_MAP = {"kinetic": "netMeshKE", "bending": "bE", "stretching": "sE", "tension": "tE", "lj": "ljE",
+         "electrostatic": "esE", "volume": "volE", "potential": "penergy", "energy": "energy",
+         "mesh_bath_ke": "mesh_bath_ke", "mesh_bath_pe": "mesh_bath_pe", "ions_bath_ke": "ions_bath_ke",
+         "ions_bath_pe": "ions_bath_pe", "total_area": "total_area", "total_volume": "total_volume"}
+
+
+def make_ctx(g, pos=None, vel=None, **kw):
+    P = capi.make_params(g.params, g["k0_mesh_bath"], g["k0_ions_bath"])
+    ctx = capi.Context(g["edges"], g["faces"], g["l0"], P, n_vertices=g.nv(), **kw)
+    ctx.upload_state(g["pos0"] if pos is None else pos, np.zeros_like(g["pos0"]) if vel is None else vel, g["q"])
+    return ctx
+
+
+def check_against_fixture(ctx, g, k):
+    fref = g["k%d_force" % k]
+    fscale = float(np.max(np.abs(fref)))
+    st = ctx.download_state()
+    assert relerr(st["force"], fref) < TOL, (g.name, k, "force")
+    assert relerr(st["pos"], g["k%d_pos" % k]) < 1e-13
+    assert relerr(st["vel"], g["k%d_vel" % k], floor=1e-9) < TOL
+    e = ctx.energy()  # also refreshes the per-term force components and mesh fields
+    comp = ctx.download_force_components()
+    for ck, gk in COMP:
+        # absolute floor for terms that are exactly zero in the fixture (e.g. pair force when q = 0)
+        assert relerr(comp[ck], g["k%d_%s" % (k, gk)], floor=1e-6 * fscale) < TOL, (g.name, k, ck)
+    mf = ctx.download_mesh_fields()
+    assert relerr(mf["edge_S"], g["k%d_itsS" % k]) < TOL
+    assert relerr(mf["face_area"], g["k%d_face_area" % k]) < TOL
+    assert relerr(mf["face_volume"], g["k%d_face_volume" % k]) < TOL
+    s = g.scalars(k)
+    escale = abs(s["energy"])
+    for ek, gk in E_MAP.items():
+        ref = s[gk]
+        if ek in ("mesh_bath_ke", "mesh_bath_pe", "ions_bath_ke", "ions_bath_pe", "kinetic"):
+            # thermostat / kinetic terms are ~1e-5 of E at step 1: relative to their own size
+            assert abs(e[ek] - ref) <= TOL * max(abs(ref), 1e-9), (g.name, k, ek, e[ek], ref)
+        else:
+            assert abs(e[ek] - ref) <= TOL * max(abs(ref), 1e-6 * escale), (g.name, k, ek, e[ek], ref)
+    mb, ib = ctx.get_thermostat()
+    assert relerr(mb, g["k%d_mesh_bath" % k]) < TOL
+    assert relerr(ib, g["k%d_ions_bath" % k]) < TOL
+
+
+def test_forces_and_energies_match_reference_at_first_steps(gold):
+    """Steps 0, 1 (and 2 for the disc): total force, each force term, EDGE::itsS, face areas and
+    volumes, KE/bE/sE/tE/ljE/esE/volE, thermostat chains (including the empty ion chain)."""
+    with make_ctx(gold) as ctx:
+        ctx.force_init()
+        done = 0
+        for k in gold.full_steps:
+            ctx.step(k - done)
+            done = k
+            check_against_fixture(ctx, gold, k)
+
+
+@pytest.mark.parametrize("name", ["disc_D4", "janus_D8", "buckled_D4", "buckling_D8"])
+def test_trajectory_matches_reference_over_1000_steps(name):
+    """A/U/E within 1e-6 relative at steps 250..1000 of the reference's own run."""
+    g = golden(name)
+    with make_ctx(g) as ctx:
+        ctx.force_init()
+        done = 0
+        for k in g.traj_steps:
+            ctx.step(k - done)
+            done = k
+            e, s = ctx.energy(), g.scalars(k)
+            assert abs(e["total_area"] - s["total_area"]) <= 1e-6 * s["total_area"], (name, k)
+            assert abs(e["potential"] - s["penergy"]) <= 1e-6 * abs(s["penergy"]), (name, k)
+            assert abs(e["energy"] - s["energy"]) <= 1e-6 * abs(s["energy"]), (name, k)
+            cons_ref = s["energy"] + s["mesh_bath_ke"] + s["mesh_bath_pe"] + s["ions_bath_ke"] + s["ions_bath_pe"]
+            cons = e["energy"] + e["mesh_bath_ke"] + e["mesh_bath_pe"] + e["ions_bath_ke"] + e["ions_bath_pe"]
+            assert abs(cons - cons_ref) <= 1e-6 * abs(cons_ref), (name, k)
+        pos = ctx.download_state()["pos"]
+        assert relerr(pos, g["k%d_pos" % g.traj_steps[-1]]) < 1e-6
+
+
+def perturbed(g, seed, amp):
+    rng = np.random.default_rng(seed)
+    pos = g["pos0"] * (1.0 + 0.05 * rng.standard_normal()) + amp * rng.standard_normal(g["pos0"].shape)
+    vel = 0.05 * rng.standard_normal(g["pos0"].shape)
+    return pos, vel
+
+
+@pytest.mark.parametrize("name,seed", [("disc_D4", 1), ("janus_D8", 2), ("buckling_D8", 3), ("rod_D4", 4)])
+def test_perturbed_state_matches_oracle(name, seed):
+    """Away from the symmetric initial sphere (all four mesh terms and the volume term live,
+    non-zero velocities): forces, components, energies and 20 steps vs the oracle."""
+    g = golden(name)
+    pos, vel = perturbed(g, seed, 0.01)
+    o = make_oracle(g)
+    o.set_state(pos, vel, g["q"])
+    o.dressup()
+    o.force()
+    o.refresh_ke()
+    with make_ctx(g, pos, vel) as ctx:
+        ctx.force_init()
+        e, eo = ctx.energy(), o.energy()
+        comp = ctx.download_force_components()
+        fscale = float(np.max(np.abs(o.vec("force"))))
+        assert relerr(ctx.download_state()["force"], o.vec("force")) < TOL
+        for ck, gk in COMP:
+            assert relerr(comp[ck], o.vec(gk), floor=1e-6 * fscale) < TOL, ck
+        for ek, ok in [("kinetic", "KE"), ("bending", "bE"), ("stretching", "sE"), ("tension", "tE"),
+                       ("electrostatic", "esE"), ("volume", "volE"), ("potential", "penergy"), ("energy", "energy")]:
+            assert abs(e[ek] - eo[ok]) <= TOL * max(abs(eo[ok]), 1e-6 * abs(eo["energy"])), (ek, e[ek], eo[ok])
+        # md_init zeroes nothing here: continue both from the same (pos, vel) with the loop body only
+        o2 = make_oracle(g)
+        o2.set_state(pos, vel, g["q"])
+        o2.dressup()
+        o2.force()
+        o2.refresh_ke()  # the KE the first half-chain consumes
+        o2.md_steps(20)
+        ctx.step(20)
+        st = ctx.download_state()
+        assert relerr(st["pos"], o2.vec("pos")) < 1e-9
+        assert relerr(st["vel"], o2.vec("vel")) < 1e-8
+        assert relerr(st["force"], o2.vec("force")) < 1e-8
+
+
+def test_lj_branch_is_exact_when_vertices_nearly_collide():
+    """WCA term (src/newforces.cpp:165-171): pull one vertex to within the cutoff of a neighbour."""
+    g = golden("disc_D4")
+    pos = np.array(g["pos0"])
+    a, b = [int(x) for x in g["edges"][10]]
+    d = g.params["lj_length_mesh_mesh"]
+    u = (pos[b] - pos[a]) / np.linalg.norm(pos[b] - pos[a])
+    pos[b] = pos[a] + 1.05 * d * u
+    o = make_oracle(g)
+    o.set_state(pos, np.zeros_like(pos), g["q"])
+    o.dressup()
+    o.force()
+    eo = o.energy()
+    assert eo["ljE"] > 0
+    with make_ctx(g, pos) as ctx:
+        ctx.force_init()
+        e = ctx.energy()
+        assert abs(e["lj"] - eo["ljE"]) <= TOL * eo["ljE"]
+        assert abs(e["electrostatic"] - eo["esE"]) <= TOL * eo["esE"]
+        assert relerr(ctx.download_force_components()["pair"], o.vec("pforce")) < TOL
+
+
+def test_run_to_run_determinism_and_plan_invariance():
+    """Fixed summation order: two contexts give bit-identical trajectories; changing rows per
+    thread does not change a single bit; changing the column split changes only rounding."""
+    g = golden("janus_D8")
+    outs = []
+    for plan in [(0, 0), (0, 0), (1, 0), (4, 0)]:
+        with make_ctx(g) as ctx:
+            if plan != (0, 0):
+                ctx.set_pair_plan(*plan)
+            splits = ctx.pair_geometry()["col_splits"]
+            ctx.force_init()
+            ctx.step(25)
+            outs.append((splits, ctx.download_state()))
+    base = outs[0][1]
+    for splits, st in outs[1:]:
+        for k in ("pos", "vel", "force"):
+            if splits == outs[0][0]:
+                assert np.array_equal(st[k], base[k]), k
+    with make_ctx(g) as ctx:
+        ctx.set_pair_plan(2, 1)
+        ctx.force_init()
+        f1 = ctx.download_state()["force"]
+    with make_ctx(g) as ctx:
+        ctx.set_pair_plan(2, 3)
+        ctx.force_init()
+        f3 = ctx.download_state()["force"]
+    assert relerr(f3, f1) < 1e-13
+
+
+def test_pair_forces_sum_to_zero_and_bending_is_translation_invariant():
+    """Newton's third law for the ordered-pair sum, zero net bending/stretching force."""
+    g = golden("disc_ico6")
+    pos, vel = perturbed(g, 7, 0.02)
+    with make_ctx(g, pos, vel) as ctx:
+        ctx.force_init()
+        comp = ctx.download_force_components()
+        scale = np.abs(comp["pair"]).sum()
+        assert np.abs(comp["pair"].sum(axis=0)).max() < 1e-13 * scale
+        for k in ("bending", "stretching", "tension", "volume_tension"):
+            assert np.abs(comp[k].sum(axis=0)).max() < 1e-12 * max(np.abs(comp[k]).sum(), 1e-300), k
+
+
+def test_finite_difference_of_energy_is_minus_force():
+    """F = -dU/dx for a handful of coordinates (central differences on the device energies)."""
+    g = golden("disc_D4")
+    pos, _ = perturbed(g, 11, 0.01)
+    vel = np.zeros_like(pos)
+    with make_ctx(g, pos, vel) as ctx:
+        ctx.force_init()
+        f = ctx.download_state()["force"]
+        h = 1e-6
+        for (i, c) in [(0, 0), (17, 1), (200, 2), (371, 0)]:
+            up, dn = pos.copy(), pos.copy()
+            up[i, c] += h
+            dn[i, c] -= h
+            ctx.upload_state(pos=up)
+            ctx.force_init()
+            eu = ctx.energy()["potential"]
+            ctx.upload_state(pos=dn)
+            ctx.force_init()
+            ed = ctx.energy()["potential"]
+            fd = -(eu - ed) / (2 * h)
+            assert abs(fd - f[i, c]) <= 2e-6 * max(abs(f[i, c]), 1.0), (i, c, fd, f[i, c])
+
+
+def test_host_buffer_entry_points():
+    """npsl_force_calculation / npsl_md_run (host arrays in, host arrays out) agree with the
+    resident path bit for bit."""
+    g = golden("rod_D4")
+    with make_ctx(g) as ctx:
+        ctx.force_init()
+        f_res = ctx.download_state()["force"]
+        f_host = ctx.force_calculation(np.ascontiguousarray(g["pos0"]))
+        assert np.array_equal(f_res, f_host)
+        ctx.upload_state(g["pos0"], np.zeros_like(g["pos0"]), g["q"])
+        ctx.force_init()
+        ctx.step(10)
+        e_res, st = ctx.energy(), ctx.download_state()
+    with make_ctx(g) as ctx:
+        e, pos, vel = ctx.md_run(g["pos0"], np.zeros_like(g["pos0"]), g["q"], 10)
+        assert np.array_equal(pos, st["pos"]) and np.array_equal(vel, st["vel"])
+        assert e == e_res
+
+
+def test_error_paths():
+    g = golden("disc_D4")
+    P = capi.make_params(g.params, g["k0_mesh_bath"], g["k0_ions_bath"])
+    bad_faces = np.array(g["faces"])
+    bad_faces[0] = bad_faces[0][::-1]  # inconsistent orientation
+    with pytest.raises(capi.NpslError) as ei:
+        capi.Context(g["edges"], bad_faces, g["l0"], P, n_vertices=g.nv())
+    assert ei.value.status == -1
+    with make_ctx(g) as ctx:
+        with pytest.raises(capi.NpslError) as ei:
+            ctx.step(1)  # before force_init
+        assert ei.value.status == -4
+        bad = np.array(g["pos0"])
+        bad[3] = np.nan
+        ctx.upload_state(pos=bad)
+        ctx.force_init()
+        with pytest.raises(capi.NpslError) as ei:
+            ctx.energy()
+        assert ei.value.status == -5
+
+
+def test_s64_properties():
+    """BASELINE's full-size mesh (40,962 vertices): no CPU reference is affordable for whole steps,
+    so check size-independent properties -- the oracle on a row sample, Newton's third law,
+    determinism, and energy conservation of the extended system over 20 steps."""
+    m = M.icosphere(64)
+    inp = M.PhysicalInputs(q=600.0, c=0.005)
+    p = M.derive_params(inp, m)
+    q = M.assign_charges(m, inp.q)
+    mb, ib = M.make_thermostats(inp, m.n_vertices)
+    P = capi.make_params(p, mb, ib)
+    with capi.Context(m.edges, m.faces, p["l0"], P, n_vertices=m.n_vertices) as ctx:
+        ctx.upload_state(m.pos, np.zeros_like(m.pos), q)
+        ctx.force_init()
+        e0 = ctx.energy()
+        comp = ctx.download_force_components()
+        assert np.abs(comp["pair"].sum(axis=0)).max() < 1e-12 * np.abs(comp["pair"]).sum()
+        # oracle on three row windows (first, middle, last 64 rows) of the pair term
+        from oracle import oracle as O
+        o = O.Oracle(m.edges, m.faces, p["l0"], {**p, "T": inp.T})
+        o.set_state(m.pos, np.zeros_like(m.pos), q)
+        o.dressup()
+        n = m.n_vertices
+        for lo in (0, n // 2, n - 64):
+            o.force(lo, lo + 63)
+            ref = o.vec("pforce")[lo:lo + 64]
+            assert relerr(comp["pair"][lo:lo + 64], ref) < TOL
+        assert relerr(comp["bending"], o.vec("bforce"), floor=1e-3) < 1e-9
+        assert relerr(comp["tension"], o.vec("tforce")) < TOL
+        ctx.step(20)
+        e1 = ctx.energy()
+        cons0 = e0["energy"] + e0["mesh_bath_ke"] + e0["mesh_bath_pe"] + e0["ions_bath_ke"] + e0["ions_bath_pe"]
+        cons1 = e1["energy"] + e1["mesh_bath_ke"] + e1["mesh_bath_pe"] + e1["ions_bath_ke"] + e1["ions_bath_pe"]
+        assert abs(cons1 / cons0 - 1.0) < 1e-6
+        st1 = ctx.download_state()
+    with capi.Context(m.edges, m.faces, p["l0"], P, n_vertices=m.n_vertices) as ctx:
+        ctx.upload_state(m.pos, np.zeros_like(m.pos), q)
+        ctx.force_init()
+        ctx.step(20)
+        st2 = ctx.download_state()
+    for k in ("pos", "vel", "force"):
+        assert np.array_equal(st1[k], st2[k])
