@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native np-shape-lab force/energy/integrator path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload S64_disc] [--impl b200|reference]
+
+A "step" is one iteration of the md_interface loop body (src/newmd.cpp:96-170): reverse
+Nose-Hoover half-chain, half-kick, drift, dressup, force_calculation (all-pairs screened Coulomb +
+bending / stretching / surface-tension / volume-tension), half-kick, kinetic energy, forward
+half-chain. Metric: MD steps/s (and ordered pair interactions/s = N(N-1) steps/s, counted as the
+reference evaluates them) on BASELINE.json's synthetic D=64 charged-disc mesh (40,962 vertices).
+
+One JSON line is printed by rank 0; see DESIGN.md "Measurement" for how each field is obtained.
+For N > 1 launch with torchrun (one rank per GPU); rows of the pair interaction and the owned
+vertex range are sharded, total work is fixed ("strong" scaling).
+
+--impl reference times the reference's own CPU implementation (oracle/_ref/npsl_ref = its unmodified
+sources compiled against shim headers) on the host cores; see run_reference().
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "md_steps_per_s"
+UNIT = "steps/s"
+# FP64-pipe instructions the pair kernel executes per ordered pair (counted in the SASS of the inner
+# loop, profiles/r01_pair_sass_count.txt; force-only variant used inside a step)
+DFMA_PER_PAIR = 33
+ALGORITHMIC_FLOPS_PER_PAIR = 24  # force-only, exp and rsqrt counted as one flop each
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(prefix="npsl_clocks_", suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"],
+                                     f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's CPU implementation (unmodified sources, oracle/_ref) on the host cores
+def reference_sample(workload_name: str, budget_s: float, threads: int, reps: int = 1, warm: int = 0):
+    """Times force_calculation of the reference (src/newforces.cpp:137-289) on a bounded row sample of
+    the workload -- its own MPI row slice [lowerBoundMesh, upperBoundMesh] (src/main.cpp:448-455) --
+    and extrapolates to a full step:  t_step = t_fixed + (t_sample - t_fixed) * N / rows, where t_fixed
+    (mesh terms + gather, evaluated in full on every rank) is measured with a 1-row slice.
+    Returns dict(value=steps/s, pairs_per_s, sample=..., per-call times)."""
+    from np_shape_lab_b200 import mesh as M
+    from np_shape_lab_b200 import workloads as W
+    from oracle import refdump as R
+    if not R.have_ref():
+        raise RuntimeError("oracle/_ref/npsl_ref is not built (run __graft_entry__.build() where /root/reference exists)")
+    w = W.build(workload_name)
+    n = w.n_vertices
+    wd = tempfile.mkdtemp(prefix="npsl_refbench_")
+    os.makedirs(os.path.join(wd, "infiles"))
+    os.makedirs(os.path.join(wd, "outfiles"))
+    M.write_dat(os.path.join(wd, "infiles", "3_%d.dat" % w.D), w.mesh)
+    flags = W.reference_flags(w)
+
+    def call(rows, reps_, warm_):
+        out = R.run_ref(wd, ["--mode", "force"] + flags + ["--row-lo", 0, "--row-hi", rows - 1, "--reps", reps_,
+                                                            "--warm", warm_], threads=threads, timeout=3600)
+        return R.last_json_line(out)
+
+    fixed = call(1, 2, 1)
+    t_fixed = fixed["best_s"]
+    probe_rows = min(n, 64 * max(1, threads))
+    probe = call(probe_rows, 1, 0)
+    per_row = max((probe["best_s"] - t_fixed) / probe_rows, 1e-9)
+    per_call_budget = budget_s / max(1, reps + warm)
+    rows = int(max(probe_rows, min(n, (per_call_budget - t_fixed) / per_row)))
+    res = call(rows, reps, warm)
+    t_sample = res["mean_s"]
+    t_step = t_fixed + (t_sample - t_fixed) * (n / rows)
+    import shutil
+    shutil.rmtree(wd, ignore_errors=True)
+    return {
+        "value": 1.0 / t_step, "pairs_per_s": n * (n - 1) / t_step, "t_step_s": t_step, "t_sample_s": t_sample,
+        "t_fixed_s": t_fixed, "rows": rows, "reps": reps, "threads": res["threads"], "n": n,
+        "sample": "reference force_calculation (unmodified src/newforces.cpp via oracle/_ref) on rows [0,%d) of %d "
+                  "x all %d columns, %d timed call(s), mesh terms in full; extrapolated to a full step as "
+                  "t_fixed + (t_sample - t_fixed) * N/rows with t_fixed = %.3f s from a 1-row slice; 1 process x %d "
+                  "OpenMP threads (no MPI launcher in the image)" % (rows, n, n, reps, t_fixed, res["threads"]),
+    }
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args) -> None:
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    threads = host_threads()
+    total = args.steps + args.warmup
+    # bounded: the whole run ends within a few minutes whatever K and W are
+    budget = min(180.0, max(20.0, 2.0 * total))
+    r = reference_sample(args.workload, budget, threads, reps=args.steps, warm=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["t_step_s"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64 (x87 80-bit vectors in the reference)",
+        "data": "synthetic", "pair_interactions_per_s": r["pairs_per_s"],
+        "config": {"workload": args.workload, "vertices": r["n"], "ordered_pairs_per_step": r["n"] * (r["n"] - 1)},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args) -> None:
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with %d ranks (one process per GPU)" % (args.gpus, args.gpus))
+        args.gpus = world
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from np_shape_lab_b200 import capi
+    from np_shape_lab_b200 import workloads as W
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    w = W.build(args.workload)
+    n = w.n_vertices
+    P = capi.make_params(w.params, w.mesh_bath, w.ions_bath)
+    nccl_id = None
+    if world > 1:
+        box = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+    ctx = capi.Context(w.mesh.edges, w.mesh.faces, w.params["l0"], P, n_vertices=n, rank=rank, world=world,
+                       nccl_id=nccl_id)
+    pos0 = np.ascontiguousarray(w.mesh.pos)
+    vel0 = np.zeros_like(pos0)
+    ctx.upload_state(pos0, vel0, w.q)
+    ctx.force_init()
+    e0 = ctx.energy()
+    launches0 = ctx.launch_count()
+
+    # ---- device-resident steps: W warm-up, then K timed (one CUDA-graph launch per step)
+    ctx.step(max(args.warmup, 3))
+    ctx.sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    l_before = ctx.launch_count()
+    t0 = time.perf_counter()
+    dev_ms = ctx.step_timing(args.steps, flush_l2=True)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    gpu_launches = ctx.launch_count() - l_before
+    dev_ms = max_over_ranks(dev_ms)
+    wall_ms = max_over_ranks(wall_ms)
+    clocks = sampler.stop() if rank == 0 else {}
+    ms_per_step = dev_ms / args.steps
+    steps_per_s = 1e3 / ms_per_step
+    e1 = ctx.energy()
+
+    # ---- the pair kernel alone (CUDA events on the context's stream around each launch)
+    n_pair = max(5, min(args.steps, 50))
+    ctx.pair_timing(True)
+    ctx.step(n_pair)
+    pair_ms, pair_count = ctx.pair_timing_read()
+    ctx.pair_timing(False)
+    pair_ms = max_over_ranks(pair_ms)
+    geo = ctx.pair_geometry()
+    lo, hi = ctx.owned_rows()
+
+    # ---- end to end through the host-buffer entry point: state lives in host memory between steps
+    pos = np.ascontiguousarray(ctx.download_state()["pos"])
+    st = ctx.download_state()
+    pos, vel, frc = [np.ascontiguousarray(st[k]) for k in ("pos", "vel", "force")]
+    for _ in range(3):
+        ctx.md_step_host(pos, vel, frc, 1)
+    n_e2e = max(5, min(args.steps, 200))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        ke = ctx.md_step_host(pos, vel, frc, 1)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_steps_per_s = n_e2e / e2e_s
+    bytes_dir = 3 * 3 * 8 * n  # pos, vel, force [n][3] doubles each way (+ 8 B of KE down)
+
+    # ---- roofline denominators
+    dfma_peak, nominal_mhz = capi.fp64_peak()
+    dfma_peak = max_over_ranks(dfma_peak) if world > 1 else dfma_peak
+    pairs_per_launch = (hi - lo) * (n - 1)
+    achieved_dfma = pairs_per_launch * DFMA_PER_PAIR / (pair_ms * 1e-3) if pair_ms > 0 else 0.0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    ctx.close()
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    cons = lambda e: e["energy"] + e["mesh_bath_ke"] + e["mesh_bath_pe"] + e["ions_bath_ke"] + e["ions_bath_pe"]
+    line = {
+        "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "pair_interactions_per_s": steps_per_s * n * (n - 1),
+        "config": {
+            "workload": args.workload, "vertices": n, "edges": w.mesh.n_edges, "faces": w.mesh.n_faces,
+            "ordered_pairs_per_step": n * (n - 1), "reference_cli": w.cli,
+            "sharding": "rows of the pair term and owned vertices split over %d GPU(s); NCCL all-gather of positions "
+                        "and of the per-rank kinetic energy each step" % world if world > 1 else "single GPU",
+            "l2": "flushed between timed steps (256 MiB memset outside each step's CUDA-event bracket); "
+                  "ms_per_step = sum of the per-step brackets / K, max over ranks",
+            "pair_plan": geo,
+        },
+        "wall_ms_per_step_incl_flush": wall_ms / args.steps,
+        "gpu_launches": int(gpu_launches),
+        "clocks": clocks,
+        "e2e": {"value": e2e_steps_per_s, "unit": UNIT, "h2d_bytes_per_step": bytes_dir,
+                "d2h_bytes_per_step": bytes_dir + 8, "steps": n_e2e,
+                "call": "npsl_md_step_host: posvec/velvec/forvec host->device, one step, device->host, wall clock"},
+        "roofline": {
+            "bound": "fp64", "achieved": 2e-12 * achieved_dfma, "peak": 2e-12 * dfma_peak, "unit": "TFLOP/s",
+            "frac": achieved_dfma / dfma_peak if dfma_peak else None, "traffic": None,
+            "kernel": "k_pair<%d,false>" % geo["rows_per_thread"], "kernel_ms": pair_ms, "kernel_launches_timed": pair_count,
+            "kernel_share_of_step": pair_ms / ms_per_step,
+            "fp64_instr_per_pair": DFMA_PER_PAIR, "pairs_per_launch": pairs_per_launch,
+            "algorithmic_tflops_%dflop_per_pair" % ALGORITHMIC_FLOPS_PER_PAIR:
+                1e-12 * pairs_per_launch * ALGORITHMIC_FLOPS_PER_PAIR / (pair_ms * 1e-3) if pair_ms > 0 else None,
+            "peak_source": "pure-DFMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 entry); "
+                           "nominal 148 SM x 64 DFMA/clk x %.0f MHz = %.2f TFLOP/s" %
+                           (nominal_mhz, 148 * 64 * 2 * nominal_mhz * 1e-6),
+            "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
+        },
+        "checks": {"conserved_energy_drift": cons(e1) / cons(e0) - 1.0, "finite": bool(np.isfinite(cons(e1))),
+                   "kinetic_after_e2e": ke},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = reference_sample(args.workload, args.cpu_budget, host_threads(), reps=1, warm=0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                                    "sample": r["sample"], "pair_interactions_per_s": r["pairs_per_s"]}
+        except Exception as ex:  # the baseline is reported, never required for the GPU numbers
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "reference",
+                                    "sample": "unavailable: %s" % ex}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="S64_disc")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

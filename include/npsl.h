@@ -172,6 +172,14 @@ int npsl_force_calculation(npsl_ctx *ctx, const double *pos, double *force);
 int npsl_md_run(npsl_ctx *ctx, const double *pos, const double *vel, const double *q, int n_steps,
                 npsl_energies *energies_out, double *pos_out, double *vel_out);
 
+/* The loop body of md_interface with the reference's host-resident state (src/newmd.cpp:96-170;
+ * the reference keeps VERTEX::posvec / velvec / forvec in host memory between steps): positions,
+ * velocities and forces [n][3] host -> device, n_steps iterations, the three arrays device -> host
+ * in place, and the kinetic energy of the final velocities (compute_kinetic_energy,
+ * src/newmd.cpp:156). force must hold the forces at pos (as left by npsl_force_calculation or by a
+ * previous call). The thermostat chains stay on the device (npsl_get/set_thermostat). */
+int npsl_md_step_host(npsl_ctx *ctx, double *pos, double *vel, double *force, int n_steps, double *kinetic_out);
+
 /* ---- introspection (measurement only) --------------------------------------------------- */
 
 /* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */

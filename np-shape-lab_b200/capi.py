@@ -25,7 +25,7 @@ SYMBOLS = [
     "npsl_download_mesh_fields", "npsl_get_thermostat", "npsl_set_thermostat", "npsl_dressup", "npsl_force_init",
     "npsl_force", "npsl_step", "npsl_energy", "npsl_sync", "npsl_launch_count", "npsl_pair_timing",
     "npsl_pair_timing_read", "npsl_owned_rows", "npsl_pair_geometry", "npsl_fp64_peak", "npsl_md_run",
-    "npsl_step_timing", "npsl_set_pair_plan", "npsl_force_calculation",
+    "npsl_step_timing", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_md_step_host",
 ]
 
 
@@ -108,6 +108,7 @@ def load() -> C.CDLL:
     L.npsl_md_run.argtypes = [vp, dp, dp, dp, C.c_int, C.POINTER(Energies), dp, dp]
     L.npsl_step_timing.argtypes = [vp, C.c_int, C.c_int, dp]
     L.npsl_force_calculation.argtypes = [vp, dp, dp]
+    L.npsl_md_step_host.argtypes = [vp, dp, dp, dp, C.c_int, dp]
     L.npsl_set_pair_plan.argtypes = [vp, C.c_int, C.c_int]
     if L.npsl_abi_version() != ABI_VERSION:
         raise NpslError(-1, "libnpsl.so ABI version %d, binding expects %d" % (L.npsl_abi_version(), ABI_VERSION))
@@ -313,6 +314,16 @@ class Context:
             force_out = np.empty((self.nv, 3))
         self._ck(self.L.npsl_force_calculation(self.h, _dp(pos), _dp(force_out)))
         return force_out
+
+    def md_step_host(self, pos: np.ndarray, vel: np.ndarray, force: np.ndarray, n_steps: int = 1) -> float:
+        """Loop body of md_interface over host-resident state (npsl_md_step_host): the three
+        C-contiguous float64 [n,3] arrays are updated in place; returns the kinetic energy."""
+        for a in (pos, vel, force):
+            if a.dtype != np.float64 or not a.flags.c_contiguous or a.shape != (self.nv, 3):
+                raise ValueError("pos, vel, force must be C-contiguous float64 [n,3]")
+        ke = C.c_double()
+        self._ck(self.L.npsl_md_step_host(self.h, _dp(pos), _dp(vel), _dp(force), int(n_steps), C.byref(ke)))
+        return ke.value
 
     def owned_rows(self):
         lo, hi = C.c_int32(), C.c_int32()

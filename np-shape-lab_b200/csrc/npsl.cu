@@ -122,8 +122,8 @@ struct npsl_ctx {
     int64_t t_count = 0;
 
     // host<->device staging for the packed [n][3] arrays of the boundary: pinned host + device
-    double *h_pin[2] = {nullptr, nullptr};
-    double *d_pack[2] = {nullptr, nullptr};
+    double *h_pin[3] = {nullptr, nullptr, nullptr};
+    double *d_pack[3] = {nullptr, nullptr, nullptr};
     // measurement: L2 flush buffer and per-step event brackets of npsl_step_timing
     void *flush_buf = nullptr;
     size_t flush_bytes = 0;
@@ -531,7 +531,7 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     CUB(cudaMemcpy(c->ring_l0, tb.ring_l0.data(), sizeof(double) * tb.ring_l0.size(), cudaMemcpyHostToDevice));
     CUB(cudaMemcpy(c->bslot_ref, tb.bslot_ref.data(), sizeof(int) * tb.bslot_ref.size(), cudaMemcpyHostToDevice));
 
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < 3; k++) {
         CUB(cudaMallocHost((void **) &c->h_pin[k], sizeof(double) * 3 * c->nv));
         CUB(dalloc(&c->d_pack[k], (size_t) 3 * c->nv));
     }
@@ -621,7 +621,7 @@ void npsl_destroy(npsl_ctx *c) {
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
     for (cudaEvent_t e : c->t_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->s_ev) cudaEventDestroy(e);
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < 3; k++) {
         if (c->h_pin[k]) cudaFreeHost(c->h_pin[k]);
         if (c->d_pack[k]) cudaFree(c->d_pack[k]);
     }
@@ -861,6 +861,48 @@ int npsl_md_run(npsl_ctx *c, const double *pos, const double *vel, const double 
     if ((r = npsl_step(c, n_steps))) return r;
     if (energies_out && (r = npsl_energy(c, energies_out))) return r;
     if ((r = npsl_download_state(c, pos_out, vel_out, nullptr))) return r;
+    return NPSL_OK;
+}
+
+int npsl_md_step_host(npsl_ctx *c, double *pos, double *vel, double *force, int n_steps, double *kinetic_out) {
+    if (!c || !pos || !vel || !force) return fail(c, NPSL_ERR_ARG, "NULL argument");
+    if (n_steps < 0) return fail(c, NPSL_ERR_ARG, "n_steps < 0");
+    int r = ensure_graph(c);
+    if (r) return r;
+    // host AoS -> pinned staging -> device records: three copies in flight, then the steps, then back
+    const size_t bytes = sizeof(double) * 3 * c->nv;
+    const int nb = (c->nv + 255) / 256;
+    double *in[3] = {pos, vel, force};
+    double4 *dev[3] = {c->xyzq, c->vel, c->force};
+    CU(cudaStreamSynchronize(c->s_main));
+    for (int k = 0; k < 3; k++) {
+        memcpy(c->h_pin[k], in[k], bytes);
+        CU(cudaMemcpyAsync(c->d_pack[k], c->h_pin[k], bytes, cudaMemcpyHostToDevice, c->s_main));
+        k_scatter3<<<nb, 256, 0, c->s_main>>>(dev[k], c->d_pack[k], c->nv, k == 0 ? 1 : 0);
+    }
+    c->launches += 3;
+    c->forces_valid = true;  // the caller's forvec is the force at the caller's posvec (src/newmd.cpp:114-117)
+    for (int k = 0; k < n_steps; k++) CU(cudaGraphLaunch(c->step_graph, c->s_main));
+    c->launches += (int64_t) c->launches_per_step * n_steps;
+    for (int k = 0; k < 3; k++) {
+        if (k > 0) {
+            r = gather_records(c, dev[k]);
+            if (r) return r;
+        }
+        k_gather3<<<nb, 256, 0, c->s_main>>>(dev[k], c->d_pack[k], c->nv);
+        CU(cudaMemcpyAsync(c->h_pin[k], c->d_pack[k], bytes, cudaMemcpyDeviceToHost, c->s_main));
+    }
+    c->launches += 3;
+    std::vector<double> ke(c->world);
+    CU(cudaMemcpyAsync(ke.data(), c->ke_parts, sizeof(double) * c->world, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    for (int k = 0; k < 3; k++) memcpy(in[k], c->h_pin[k], bytes);
+    if (kinetic_out) {
+        double s = 0;
+        for (int k = 0; k < c->world; k++) s += ke[k];  // fixed rank order
+        *kinetic_out = s;
+    }
+    CU(cudaGetLastError());
     return NPSL_OK;
 }
 
