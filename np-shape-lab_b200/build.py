@@ -21,7 +21,7 @@ DEPENDS = ["npsl.cu", "pair_kernel.cuh", "mesh_kernels.cuh", os.path.join(ROOT, 
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--fmad=true",
+    "-Xcompiler", "-fPIC", "-shared", "--fmad=false",  # explicit fma() only: see mesh_kernels.cuh
 ]
 
 

@@ -70,10 +70,14 @@ struct V3 {
 };
 __device__ __forceinline__ V3 mk(double x, double y, double z) { V3 r = {x, y, z}; return r; }
 __device__ __forceinline__ V3 sub(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+// The library is compiled with --fmad=false: every fused multiply-add is written out, so the
+// rounding of each expression is fixed by the source (not by per-instantiation contraction
+// choices of the compiler) and a force evaluated by k_vertex<FORCE> is bit-identical to the one
+// k_vertex<STEP> used.
 __device__ __forceinline__ V3 cross(V3 a, V3 b) {
-    return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+    return mk(fma(a.y, b.z, -(a.z * b.y)), fma(a.z, b.x, -(a.x * b.z)), fma(a.x, b.y, -(a.y * b.x)));
 }
-__device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return fma(a.z, b.z, fma(a.y, b.y, a.x * b.x)); }
 // 32-byte records are moved as two 16-byte halves (there is no 32-byte __ldg/__ldcg overload)
 __device__ __forceinline__ double4 ldg4(const double4 *p) {
     const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
