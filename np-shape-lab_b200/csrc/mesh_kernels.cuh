@@ -42,7 +42,7 @@ enum {
     SC_VOL,       // total_volume
     SC_BE,        // bending energy
     SC_SE,        // stretching energy (before the 1/2 sconstant (avg^2) prefactor is applied: final value)
-    SC_KE,        // kinetic energy of the owned vertices
+    SC_KE,        // kinetic energy of all vertices (all ranks)
     SC_ES,        // electrostatic energy of the owned rows
     SC_LJ,        // LJ energy of the owned rows
     SC_EXPFAC,    // exp(-dt/2 xi_0) of the current step
@@ -158,10 +158,17 @@ __device__ __forceinline__ void thermo_forward(Thermo &t, int chain, double dt, 
     for (int j = 0; j < chain; j++) chain_xi(t.ions, j, chain, dt, 0.0);
 }
 
-__device__ __forceinline__ double sum_ke_parts(const double *ke_parts, int n_ranks) {
-    double ke = 0;
-    for (int r = 0; r < n_ranks; r++) ke += ke_parts[r];  // fixed rank order
-    return ke;
+// Kinetic energy, summed the same way however the vertices are sharded: every warp of k_vertex
+// leaves the sum of its 32 vertices (fixed shuffle tree) in ke_warp[global vertex index / 32]; the
+// whole array (all ranks' warps, all-gathered when sharded) is then summed by one block with this
+// fixed pattern. Owned ranges are multiples of 32, so the warp partials, and with them the
+// thermostat and the trajectory, are bit-identical on 1 and on P GPUs. Result valid in thread 0.
+__device__ __forceinline__ double canonical_sum(const double *__restrict__ p, int n, double *smem /* [32] */) {
+    double v[1] = {0.0};
+    for (int b = threadIdx.x; b < n; b += blockDim.x) v[0] += __ldcg(p + b);
+    __syncthreads();
+    block_sum<1>(v, smem);
+    return v[0];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -170,12 +177,12 @@ __device__ __forceinline__ double sum_ke_parts(const double *ke_parts, int n_ran
 // to th_mid, which k_vertex<STEP> / k_thermo_post complete into th_cur.
 __global__ void __launch_bounds__(kMeshThreads)
 k_kick_drift(double4 *__restrict__ xyzq, double4 *__restrict__ vel, const double4 *__restrict__ force,
-             const Thermo *__restrict__ th_cur, Thermo *__restrict__ th_mid, const double *__restrict__ ke_parts,
-             double *__restrict__ scal, int *__restrict__ lj_hit, const MeshParams P) {
+             const Thermo *__restrict__ th_cur, Thermo *__restrict__ th_mid, double *__restrict__ scal,
+             int *__restrict__ lj_hit, const MeshParams P) {
     __shared__ double s_ef, s_kick;
     if (threadIdx.x == 0) {
         Thermo t = *th_cur;
-        const double ke = sum_ke_parts(ke_parts, P.n_ranks);
+        const double ke = __ldcg(scal + SC_KE);  // all vertices, all ranks
         const double ef = thermo_reverse(t, P.chain, P.dt, ke);
         const double kick = 0.5 * P.dt * sqrt(ef);
         s_ef = ef;
@@ -332,9 +339,9 @@ __global__ void __launch_bounds__(kMeshThreads)
 k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *__restrict__ force,
          const double4 *__restrict__ pair_partial, const double4 *__restrict__ lj_out, const int *__restrict__ lj_hit,
          const double4 *__restrict__ bslot, const VertexTables T, const ForceComponents C,
-         double *__restrict__ partials /* [3][nblocks] */, unsigned int *__restrict__ ticket,
-         double *__restrict__ scal, double *__restrict__ ke_parts, int rank, const Thermo *__restrict__ th_mid,
-         Thermo *__restrict__ th_cur, const MeshParams P) {
+         double *__restrict__ partials /* [2][nblocks] */, unsigned int *__restrict__ ticket,
+         double *__restrict__ scal, double *__restrict__ ke_warp /* [n_ke_warps] */, int n_ke_warps,
+         const Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur, const MeshParams P) {
     __shared__ double red[3 * 32];
     __shared__ bool s_last;
     const int nblocks = gridDim.x;
@@ -427,43 +434,67 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
         }
         acc[0] = 0.5 * (v.x * v.x + v.y * v.y + v.z * v.z);
     }
-    block_sum<3>(acc, red);
-    if (threadIdx.x == 0) {
+    // kinetic energy: one partial per warp at its global warp index (see canonical_sum)
+    {
+        double ke = acc[0];
 #pragma unroll
-        for (int k = 0; k < 3; k++) partials[k * nblocks + blockIdx.x] = acc[k];
-        s_last = take_last_ticket(ticket, nblocks);
+        for (int o = 16; o > 0; o >>= 1) ke += __shfl_down_sync(0xffffffffu, ke, o);
+        const int i0 = P.row_lo + blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+        if ((threadIdx.x & 31) == 0 && i0 < P.row_hi) ke_warp[i0 >> 5] = ke;
     }
+    if (MODE == VMODE_FORCE) {  // pair energies of the owned rows (summed over ranks by the host, rank order)
+        double e2[2] = {acc[1], acc[2]};
+        block_sum<2>(e2, red);
+        if (threadIdx.x == 0) {
+            partials[blockIdx.x] = e2[0];
+            partials[nblocks + blockIdx.x] = e2[1];
+        }
+    }
+    __syncthreads();  // every warp's ke_warp store precedes thread 0's fence + ticket
+    if (threadIdx.x == 0) s_last = take_last_ticket(ticket, nblocks);
     __syncthreads();
     if (!s_last) return;
-    double tot[3] = {0, 0, 0};
-    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) tot[k] += __ldcg(partials + k * nblocks + b);
+    if (MODE == VMODE_FORCE) {
+        double tot[2] = {0, 0};
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+            tot[0] += __ldcg(partials + b);
+            tot[1] += __ldcg(partials + nblocks + b);
+        }
+        __syncthreads();
+        block_sum<2>(tot, red);
+        if (threadIdx.x == 0) {
+            scal[SC_ES] = tot[0];
+            scal[SC_LJ] = tot[1];
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    block_sum<3>(tot, red);
+    if (P.n_ranks > 1) return;  // sharded: k_ke_post finishes after the all-gather of ke_warp
+    const double ke = canonical_sum(ke_warp, n_ke_warps, red);
     if (threadIdx.x == 0) {
-        scal[SC_KE] = tot[0];
-        ke_parts[rank] = tot[0];
-        if (MODE == VMODE_FORCE) {
-            scal[SC_ES] = tot[1];
-            scal[SC_LJ] = tot[2];
-        } else if (P.n_ranks == 1) {
+        scal[SC_KE] = ke;
+        if (MODE == VMODE_STEP) {
             Thermo t = *th_mid;
-            thermo_forward(t, P.chain, P.dt, tot[0]);
+            thermo_forward(t, P.chain, P.dt, ke);
             *th_cur = t;
         }
     }
 }
 
-// Sharded runs: the forward half-chain needs every rank's kinetic energy, so it runs after the
-// KE exchange as a one-thread kernel (identical arithmetic on every rank).
-__global__ void k_thermo_post(const Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur,
-                              const double *__restrict__ ke_parts, const MeshParams P) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    Thermo t = *th_mid;
-    thermo_forward(t, P.chain, P.dt, sum_ke_parts(ke_parts, P.n_ranks));
-    *th_cur = t;
+// Sharded runs: after the all-gather of every rank's warp partials, one block sums them in the
+// canonical order (identical arithmetic on every rank) and, inside a step, runs the forward half-chain.
+__global__ void __launch_bounds__(kMeshThreads)
+k_ke_post(const double *__restrict__ ke_warp, int n_ke_warps, double *__restrict__ scal,
+          const Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur, int step, const MeshParams P) {
+    __shared__ double red[32];
+    const double ke = canonical_sum(ke_warp, n_ke_warps, red);
+    if (threadIdx.x == 0) {
+        scal[SC_KE] = ke;
+        if (step) {
+            Thermo t = *th_mid;
+            thermo_forward(t, P.chain, P.dt, ke);
+            *th_cur = t;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -92,7 +92,8 @@ struct npsl_ctx {
     // work buffers
     double4 *bslot = nullptr, *pair_partial = nullptr, *lj_out = nullptr;
     int *lj_hit = nullptr;
-    double *scal = nullptr, *scal_all = nullptr, *ke_parts = nullptr;
+    double *scal = nullptr, *scal_all = nullptr, *ke_warp = nullptr;
+    int n_ke_warps = 0;  // world * range / 32
     Thermo *th_cur = nullptr, *th_mid = nullptr;
     double *part_mesh = nullptr, *part_vert = nullptr;
     unsigned int *tickets = nullptr;
@@ -272,23 +273,27 @@ int high_word(double x) {
     return (int) (b >> 32);
 }
 
-// Column split / row tile geometry of k_pair. The grid is sized to several CTAs per SM so that the
-// hardware scheduler balances the tail; every (split,row) partial has its own slot, so the choice
-// never changes which terms are summed in which order within a split.
+// Column chunk / row tile geometry of k_pair. The chunk width is a function of the vertex count
+// only -- never of the rank count, the owned row range or the SM count -- so every (chunk,row)
+// partial sum, and with it the whole trajectory, is bit-identical however the rows are sharded
+// across GPUs: 256 * max(2, ceil(N / 8192)) columns, i.e. at most 32 chunks (27 x 1536 at S64,
+// 31 x 5376 at S128). Rows per thread only changes which thread computes a row, not its value.
 void plan_pair(npsl_ctx *c, int n_sm) {
     const int rows = c->row_hi - c->row_lo;
-    c->pair_rows_per_thread = c->plan_rows ? c->plan_rows : 2;
+    const int col_tiles = (c->nv + kPairTileJ - 1) / kPairTileJ;
+    int tiles_per_cta = std::max(2, (c->nv + 32 * kPairTileJ - 1) / (32 * kPairTileJ));
+    if (c->plan_splits) {  // measurement override (changes the grouping of the column sum)
+        const int splits = std::max(1, std::min(c->plan_splits, col_tiles));
+        tiles_per_cta = (col_tiles + splits - 1) / splits;
+    }
+    c->pair_splits = (col_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    c->pair_cols_per_cta = tiles_per_cta * kPairTileJ;
+    // two rows per thread unless that leaves fewer than ~4 CTAs per SM (small shards)
+    int rpt = 2;
+    if ((long) ((rows + 2 * kPairThreads - 1) / (2 * kPairThreads)) * c->pair_splits < 4L * n_sm) rpt = 1;
+    c->pair_rows_per_thread = c->plan_rows ? c->plan_rows : rpt;
     const int tile_rows = kPairThreads * c->pair_rows_per_thread;
     c->pair_row_tiles = std::max(1, (rows + tile_rows - 1) / tile_rows);
-    const int col_tiles = (c->nv + kPairTileJ - 1) / kPairTileJ;
-    // aim for >= 16 CTAs per SM in flight over the launch, but keep at least 2 column tiles per CTA
-    int want = (16 * n_sm + c->pair_row_tiles - 1) / c->pair_row_tiles;
-    int splits = std::max(1, std::min(want, std::max(1, col_tiles / 2)));
-    if (c->plan_splits) splits = std::max(1, std::min(c->plan_splits, col_tiles));
-    int tiles_per_cta = (col_tiles + splits - 1) / splits;
-    splits = (col_tiles + tiles_per_cta - 1) / tiles_per_cta;
-    c->pair_splits = splits;
-    c->pair_cols_per_cta = tiles_per_cta * kPairTileJ;
     c->pair_row_stride = (rows + 31) / 32 * 32;
 }
 
@@ -318,8 +323,7 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
     int n = 0;
     if (step) {
         k_kick_drift<<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->force, c->th_cur,
-                                                                        c->th_mid, c->ke_parts, c->scal, c->lj_hit,
-                                                                        c->mp);
+                                                                        c->th_mid, c->scal, c->lj_hit, c->mp);
         n++;
         if (c->world > 1)
             NC(g_nccl.AllGather(c->xyzq + (size_t) c->rank * c->range, c->xyzq, (size_t) c->range * 4, ncclFloat64_,
@@ -368,20 +372,21 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
     if (step) {
         k_vertex<VMODE_STEP><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(
             c->xyzq, c->vel, c->force, c->pair_partial, c->lj_out, c->lj_hit, c->bslot, vt, fc, c->part_vert,
-            c->tickets + 1, c->scal, c->ke_parts, c->rank, c->th_mid, c->th_cur, c->mp);
+            c->tickets + 1, c->scal, c->ke_warp, c->n_ke_warps, c->th_mid, c->th_cur, c->mp);
         n++;
-        if (c->world > 1) {
-            NC(g_nccl.AllGather(c->scal + SC_KE, c->ke_parts, 1, ncclFloat64_, c->comm, c->s_main));
-            k_thermo_post<<<1, 32, 0, c->s_main>>>(c->th_mid, c->th_cur, c->ke_parts, c->mp);
-            n++;
-        }
     } else {
         k_vertex<VMODE_FORCE><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(
             c->xyzq, c->vel, c->force, c->pair_partial, c->lj_out, c->lj_hit, c->bslot, vt, fc, c->part_vert,
-            c->tickets + 1, c->scal, c->ke_parts, c->rank, c->th_mid, c->th_cur, c->mp);
+            c->tickets + 1, c->scal, c->ke_warp, c->n_ke_warps, c->th_mid, c->th_cur, c->mp);
         n++;
-        if (c->world > 1)
-            NC(g_nccl.AllGather(c->scal + SC_KE, c->ke_parts, 1, ncclFloat64_, c->comm, c->s_main));
+    }
+    if (c->world > 1) {
+        const size_t per_rank = (size_t) c->range / 32;
+        NC(g_nccl.AllGather(c->ke_warp + (size_t) c->rank * per_rank, c->ke_warp, per_rank, ncclFloat64_, c->comm,
+                            c->s_main));
+        k_ke_post<<<1, kMeshThreads, 0, c->s_main>>>(c->ke_warp, c->n_ke_warps, c->scal, c->th_mid, c->th_cur,
+                                                     step ? 1 : 0, c->mp);
+        n++;
     }
     CU(cudaGetLastError());
     return n;
@@ -502,6 +507,9 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     c->nv = mesh->n_vertices; c->ne = mesh->n_edges; c->nf = mesh->n_faces;
     c->rank = rank; c->world = world;
     c->range = (c->nv + world - 1) / world;  // src/main.cpp:448
+    // rounded up to a whole warp of vertices: keeps the per-warp kinetic-energy partials (and so the
+    // trajectory) bit-identical to the single-GPU run; a rank may then own a few rows more or less
+    c->range = (c->range + 31) / 32 * 32;
     c->row_lo = std::min(rank * c->range, c->nv);
     c->row_hi = std::min((rank + 1) * c->range, c->nv);
     if (c->row_hi <= c->row_lo) {
@@ -518,7 +526,8 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     CUB(dalloc(&c->bslot, (size_t) 4 * c->ne));
     CUB(dalloc(&c->lj_out, c->range)); CUB(dalloc(&c->lj_hit, 1));
     CUB(dalloc(&c->scal, SC_COUNT)); CUB(dalloc(&c->scal_all, (size_t) SC_COUNT * world));
-    CUB(dalloc(&c->ke_parts, world));
+    c->n_ke_warps = (int) (nrec / 32);
+    CUB(dalloc(&c->ke_warp, c->n_ke_warps));
     CUB(dalloc(&c->th_cur, 1)); CUB(dalloc(&c->th_mid, 1));
     CUB(dalloc(&c->tickets, 4));
     CUB(dalloc(&c->face_dir_area, c->nf)); CUB(dalloc(&c->face_vol, c->nf)); CUB(dalloc(&c->edge_S, c->ne));
@@ -545,7 +554,7 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     CUB(dalloc(&c->part_vert, (size_t) 3 * c->n_vertex_blocks));
 
     const double lam = prm->inv_kappa_out;
-    c->pp.c2 = -1.4426950408889634074 / lam;
+    c->pp.c2s = -1.4426950408889634074 / lam * (double) kExpTab;
     c->pp.inv_lambda = 1.0 / lam;
     c->pp.n = c->nv; c->pp.row_lo = c->row_lo; c->pp.row_hi = c->row_hi;
     const double d2 = prm->lj_length_mesh_mesh * prm->lj_length_mesh_mesh;
@@ -628,7 +637,7 @@ void npsl_destroy(npsl_ctx *c) {
     if (c->flush_buf) cudaFree(c->flush_buf);
     void *ptrs[] = {c->xyzq, c->vel, c->force, c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->face_v,
                     c->edge_rec, c->l0, c->degree, c->ring, c->bslot_ref, c->ring_l0, c->bslot, c->pair_partial,
-                    c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_parts, c->th_cur, c->th_mid, c->part_mesh,
+                    c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_warp, c->th_cur, c->th_mid, c->part_mesh,
                     c->part_vert, c->tickets, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -810,12 +819,12 @@ int npsl_energy(npsl_ctx *c, npsl_energies *out) {
     CU(cudaStreamSynchronize(c->s_main));
     double ke = 0, es = 0, lj = 0;
     for (int k = 0; k < c->world; k++) {  // fixed rank order
-        ke += all[(size_t) k * SC_COUNT + SC_KE];
         es += all[(size_t) k * SC_COUNT + SC_ES];
         lj += all[(size_t) k * SC_COUNT + SC_LJ];
     }
     const double *s = all.data() + (size_t) c->rank * SC_COUNT;
     const npsl_params &p = c->prm;
+    ke = s[SC_KE];  // already the sum over all ranks (canonical order, mesh_kernels.cuh)
     out->kinetic = ke;
     out->bending = s[SC_BE];
     out->stretching = s[SC_SE];
@@ -893,15 +902,11 @@ int npsl_md_step_host(npsl_ctx *c, double *pos, double *vel, double *force, int 
         CU(cudaMemcpyAsync(c->h_pin[k], c->d_pack[k], bytes, cudaMemcpyDeviceToHost, c->s_main));
     }
     c->launches += 3;
-    std::vector<double> ke(c->world);
-    CU(cudaMemcpyAsync(ke.data(), c->ke_parts, sizeof(double) * c->world, cudaMemcpyDeviceToHost, c->s_main));
+    double ke = 0;
+    CU(cudaMemcpyAsync(&ke, c->scal + SC_KE, sizeof(double), cudaMemcpyDeviceToHost, c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
     for (int k = 0; k < 3; k++) memcpy(in[k], c->h_pin[k], bytes);
-    if (kinetic_out) {
-        double s = 0;
-        for (int k = 0; k < c->world; k++) s += ke[k];  // fixed rank order
-        *kinetic_out = s;
-    }
+    if (kinetic_out) *kinetic_out = ke;
     CU(cudaGetLastError());
     return NPSL_OK;
 }

@@ -19,41 +19,38 @@
 // independent of how rows are sharded across GPUs. No atomics, no tensor cores (this is an
 // N-body with a transcendental per pair, not a contraction).
 //
-// FP64-pipe work per ordered pair: 33 instructions force-only, 34 with energy.
-// exp: x = -r/lambda is always <= 0, so the range-reduced 2^k * p(f) needs no overflow / NaN
-// handling; k is clamped at -1000 on the integer pipe. rsqrt: MUFU.RSQ64H seed + one third-order
-// step. Both hold <= ~4e-16 relative error (tests/test_pair_math.py).
+// FP64-pipe work per ordered pair: 28 instructions force-only, 30 with energy:
+//   3 sub, 3 r^2, 5 rsqrt (MUFU.RSQ64H seed + one third-order step), 1 r, 3 range reduction,
+//   5 exp (128-entry 2^(j/128) table in shared memory + degree-4 polynomial), 5 force factor, 3 FMA.
+// exp: x = -r/lambda <= 0, so 2^x = 2^k T[j] (1 + f g(f)) needs no overflow / NaN handling; k is
+// clamped at -1000 on the integer pipe. exp and rsqrt hold <= 3e-16 relative error.
+// On B200 the FP64 pipe is limited by register-file operand bandwidth (tools/ubench/fp64_pipe.cu): an
+// instruction with one register source issues every 2.0 cycles, two 2.3, three 3.1. The arithmetic
+// below is arranged so that constants sit in uniform registers / immediates wherever possible.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "exp2_table.inc"
 
 namespace npsl {
 
 constexpr int kPairThreads = 128;  // threads per CTA
 constexpr int kPairTileJ = 256;    // columns staged per shared-memory tile (8 KB)
+constexpr int kExpTab = 1 << NPSL_EXP2_TB;
+
+__constant__ double c_exp2_tab[kExpTab] = {NPSL_EXP2_TABLE};
 
 struct PairParams {
-    double c2;          // -log2(e)/lambda
+    double c2s;         // -log2(e)/lambda * 2^TB
     double inv_lambda;  // 1/lambda
     int n;              // number of vertices (columns)
     int row_lo, row_hi; // owned rows, half-open
-    int cols_per_cta;   // columns handled by one CTA (column split width, multiple of 32)
-    int n_splits;       // number of column splits
+    int cols_per_cta;   // columns handled by one CTA (column chunk width, multiple of kPairTileJ)
+    int n_splits;       // number of column chunks
     int row_stride;     // rows in a partial slab (>= row_hi-row_lo, padded)
     int lj_cut_hi;      // high word of the LJ cutoff r^2 (conservative detection on the integer pipe)
 };
-
-// minimax 2^f on [-1/2,1/2], degree 10, relative error 2.2e-16 (tools/gen_exp2_poly.py)
-#define NPSL_EXP2_C1 0x1.62e42fefa3a18p-1
-#define NPSL_EXP2_C2 0x1.ebfbdff82c3bbp-3
-#define NPSL_EXP2_C3 0x1.c6b08d703d19ep-5
-#define NPSL_EXP2_C4 0x1.3b2ab6fbdd924p-7
-#define NPSL_EXP2_C5 0x1.5d87fe9d1a4e7p-10
-#define NPSL_EXP2_C6 0x1.430912621b2e9p-13
-#define NPSL_EXP2_C7 0x1.ffcb550660fa1p-17
-#define NPSL_EXP2_C8 0x1.62c15334047bfp-20
-#define NPSL_EXP2_C9 0x1.b674d8d969e02p-24
-#define NPSL_EXP2_C10 0x1.e3a189a9bbae9p-28
 
 __device__ __forceinline__ double rsqrt_seed(double a) {
     double y;
@@ -71,26 +68,23 @@ __device__ __forceinline__ double rsqrt_fast(double a) {
     return fma(ye, p, y0);
 }
 
-// 2^(r*c2) for r*c2 <= 0 (no overflow / NaN paths). Magic-number rounding gives k in the low
-// word of tt; f = r*c2 - k in one fused step.
-__device__ __forceinline__ double exp2_neg(double r, double c2) {
+// 2^(r*c2s/2^TB) for r*c2s <= 0 (no overflow / NaN paths). Magic-number rounding leaves
+// n = round(r*c2s) in the low word of tt; f = r*c2s - n in one fused step; T[n mod 2^TB] comes from
+// shared memory and takes the exponent k = n >> TB on the integer pipe.
+__device__ __forceinline__ double exp2_neg(double r, double c2s, const double *__restrict__ tab) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-    double tt = fma(r, c2, MAGIC);
+    double tt = fma(r, c2s, MAGIC);
     double kf = tt - MAGIC;
-    double f = fma(r, c2, -kf);
-    double p = NPSL_EXP2_C10;
-    p = fma(p, f, NPSL_EXP2_C9);
-    p = fma(p, f, NPSL_EXP2_C8);
-    p = fma(p, f, NPSL_EXP2_C7);
-    p = fma(p, f, NPSL_EXP2_C6);
-    p = fma(p, f, NPSL_EXP2_C5);
-    p = fma(p, f, NPSL_EXP2_C4);
-    p = fma(p, f, NPSL_EXP2_C3);
-    p = fma(p, f, NPSL_EXP2_C2);
-    p = fma(p, f, NPSL_EXP2_C1);
-    p = fma(p, f, 1.0);
-    int k = max(__double2loint(tt), -1000);
-    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    double f = fma(r, c2s, -kf);
+    const int n = __double2loint(tt);
+    const double T = tab[n & (kExpTab - 1)];
+    const int k = max(n >> NPSL_EXP2_TB, -1000);
+    const double Tk = __hiloint2double(__double2hiint(T) + (k << 20), __double2loint(T));
+    double g = fma(f, NPSL_EXP2_G4, NPSL_EXP2_G3);
+    g = fma(g, f, NPSL_EXP2_G2);
+    g = fma(g, f, NPSL_EXP2_G1);
+    double q = f * g;
+    return fma(Tk, q, Tk);
 }
 
 struct PairAcc {
@@ -99,33 +93,40 @@ struct PairAcc {
 
 template <bool ENERGY>
 __device__ __forceinline__ void pair_accumulate(double xi, double yi, double zi, double xj, double yj, double zj,
-                                                double qj, const double c2, const double inv_lambda, PairAcc &a,
-                                                int &min_r2_hi) {
+                                                double qj, const double c2s, const double inv_lambda,
+                                                const double *__restrict__ tab, PairAcc &a, int &min_r2_hi) {
     double dx = xi - xj, dy = yi - yj, dz = zi - zj;
     double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
     min_r2_hi = min(min_r2_hi, __double2hiint(r2));
     double rinv = rsqrt_fast(r2);
     double r = r2 * rinv;
-    double ex = exp2_neg(r, c2);
-    double qe = qj * ex;
-    double pe = qe * rinv;                      // q_j e^{-r/lambda} / r
-    double rinv2 = rinv * rinv;
-    double g = fma(rinv, inv_lambda, rinv2);    // 1/r^2 + 1/(lambda r)
-    double s = pe * g;
+    double ex = exp2_neg(r, c2s, tab);
+    double qe = qj * ex;                  // q_j e^{-r/lambda}
+    double u = rinv * rinv;
+    double g = rinv + inv_lambda;         // one register source
+    double w = u * g;                     // 1/r^3 + 1/(lambda r^2)
+    double s = qe * w;
     a.fx = fma(s, dx, a.fx);
     a.fy = fma(s, dy, a.fy);
     a.fz = fma(s, dz, a.fz);
-    if (ENERGY) a.ue += pe;
+    if (ENERGY) a.ue = fma(qe, rinv, a.ue);
 }
 
-// grid = (row tiles, column splits); block = kPairThreads; ROWS rows per thread.
+template <int ROWS>
+struct PairUnroll {
+    static constexpr int value = ROWS >= 4 ? 1 : 2;
+};
+
+// grid = (row tiles, column chunks); block = kPairThreads; ROWS rows per thread.
 // partial: [n_splits][row_stride] records (fx,fy,fz,ue); row index is relative to row_lo.
 // lj_hit: set to 1 when any evaluated pair may lie inside the LJ cutoff (exact test in k_lj).
 template <int ROWS, bool ENERGY>
 __global__ void __launch_bounds__(kPairThreads) k_pair(const double4 *__restrict__ xyzq, double4 *__restrict__ partial,
                                                       int *__restrict__ lj_hit, const PairParams P) {
     __shared__ double4 sj[kPairTileJ];
+    __shared__ double tab[kExpTab];
     const int t = threadIdx.x;
+    for (int k = t; k < kExpTab; k += kPairThreads) tab[k] = c_exp2_tab[k];
     const int row0 = P.row_lo + blockIdx.x * (kPairThreads * ROWS);
     const int col0 = blockIdx.y * P.cols_per_cta;
     const int col1 = min(col0 + P.cols_per_cta, P.n);
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(const double4 *__restrict
         acc[r].fx = acc[r].fy = acc[r].fz = acc[r].ue = 0.0;
         irow[r] = ic;
     }
-    const double c2 = P.c2, inv_lambda = P.inv_lambda;
+    const double c2s = P.c2s, inv_lambda = P.inv_lambda;
     int min_r2_hi = 0x7fffffff;
     const int row_end = min(row0 + kPairThreads * ROWS, P.row_hi);
 
@@ -153,12 +154,12 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(const double4 *__restrict
         __syncthreads();
         const bool diag = (j0 < row_end) && (j0 + cnt > row0);  // tile contains some i == j
         if (!diag) {
-#pragma unroll 2
+#pragma unroll(PairUnroll<ROWS>::value)
             for (int k = 0; k < cnt; k++) {
                 const double4 pj = sj[k];
 #pragma unroll
                 for (int r = 0; r < ROWS; r++)
-                    pair_accumulate<ENERGY>(xi[r], yi[r], zi[r], pj.x, pj.y, pj.z, pj.w, c2, inv_lambda, acc[r],
+                    pair_accumulate<ENERGY>(xi[r], yi[r], zi[r], pj.x, pj.y, pj.z, pj.w, c2s, inv_lambda, tab, acc[r],
                                             min_r2_hi);
             }
         } else {
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(const double4 *__restrict
                     // by moving the column to unit distance along x and zeroing its charge.
                     const bool self = (j0 + k == irow[r]);
                     pair_accumulate<ENERGY>(xi[r], yi[r], zi[r], self ? xi[r] - 1.0 : pj.x, pj.y, pj.z,
-                                            self ? 0.0 : pj.w, c2, inv_lambda, acc[r], min_r2_hi);
+                                            self ? 0.0 : pj.w, c2s, inv_lambda, tab, acc[r], min_r2_hi);
                 }
             }
         }

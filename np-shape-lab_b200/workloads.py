@@ -14,15 +14,11 @@ below for D=128). The synthetic workloads therefore pass ``-d 2e-4`` (D=64) and 
 from __future__ import annotations
 
 import dataclasses
-import os
 from typing import Optional
 
 import numpy as np
 
 from . import mesh as M
-
-INFILES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "infiles")
-
 
 @dataclasses.dataclass
 class Workload:
@@ -80,7 +76,7 @@ def build(name: str, mesh: Optional[M.Mesh] = None) -> Workload:
 
 
 def reference_flags(w: Workload) -> list:
-    """Arguments for oracle/_ref/npsl_ref (the reference's own CLI letters, src/main.cpp:109-185)."""
+    """The workload as a command line in the reference's own CLI letters (src/main.cpp:109-185)."""
     i = w.inp
     return ["-R", i.R, "-q", i.q, "-c", i.c, "-t", i.t, "-v", i.v, "-b", i.b, "-s", i.s, "-B", i.B, "-F", "n",
             "-N", i.N, "-p", i.p, "-d", i.dt, "-T", i.T, "-Q", i.Q_mesh, "-Y", i.Q_ions, "-C", i.chain, "-D", w.D]
