@@ -1,0 +1,427 @@
+// Bodies of the host mirror (npsl_host.hpp): set-up on the host exactly as main() does it before the
+// time loop (src/main.cpp:196-294), the five path functions as thin adapters over the C ABI.
+#include "npsl_host.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <utility>
+
+using std::string;
+using std::vector;
+
+const double unitenergy = 1.3807 * std::pow(10.0, -16) * room_temperature;
+
+namespace {
+
+void check(npsl_ctx *ctx, int st, const char *what) {
+    if (st != NPSL_OK) throw npsl_error(st, string(what) + ": " + npsl_last_error(ctx));
+}
+
+void require_no_ions(const vector<PARTICLE> &ions) {
+    if (!ions.empty()) throw npsl_error(NPSL_ERR_ARG, "explicit counterions are not on the device path yet");
+}
+
+void append_line(const string &dir, const char *file, const string &line) {
+    if (dir.empty()) return;
+    std::ofstream out((dir + "/" + file).c_str(), std::ios::app);
+    out << line << "\n";
+}
+
+template <class T>
+string cell(const T &v) {  // one setw(15) column in the reference's default stream format
+    std::ostringstream s;
+    s << std::setw(15) << v;
+    return s.str();
+}
+
+void fill_links(npsl_bath_link *dst, const vector<THERMOSTAT> &src) {
+    for (size_t j = 0; j < src.size() && j < NPSL_MAX_CHAIN; j++) {
+        dst[j].Q = src[j].Q; dst[j].T = src[j].T; dst[j].dof = src[j].dof; dst[j].xi = src[j].xi; dst[j].eta = src[j].eta;
+    }
+}
+
+void read_links(vector<THERMOSTAT> &dst, const npsl_bath_link *src) {
+    for (size_t j = 0; j < dst.size() && j < NPSL_MAX_CHAIN; j++) {
+        dst[j].Q = src[j].Q; dst[j].T = src[j].T; dst[j].dof = src[j].dof; dst[j].xi = src[j].xi; dst[j].eta = src[j].eta;
+    }
+}
+
+}  // namespace
+
+double VECTOR3D::GetMagnitude() const { return std::sqrt(x * x + y * y + z * z); }
+double EDGE::length() const { return (itsV[0]->posvec - itsV[1]->posvec).GetMagnitude(); }  // src/edge.cpp:24-31
+
+INTERFACE::INTERFACE() { std::memset(&parts, 0, sizeof parts); }
+INTERFACE::~INTERFACE() { drop_context(); }
+
+void INTERFACE::drop_context() {
+    if (ctx) npsl_destroy(ctx);
+    ctx = nullptr;
+}
+
+void INTERFACE::set_up(double unit_radius_sphere) {
+    em = 0.5 * (ein + eout);
+    lB_out = (lB_water * epsilon_water / eout) / unit_radius_sphere;
+}
+
+void INTERFACE::discretize(unsigned int disc1, unsigned int disc2) {
+    std::ostringstream name;
+    name << "infiles/" << disc1 << "_" << disc2 << ".dat";
+    discretize_file(name.str());
+}
+
+// The reference's text format: three sections, each opened by six header tokens
+// ("# Number of Vertices= n vertices"); records "idx x y z q", "idx v1 v2 tag", "idx v1 v2 v3 sign tag".
+void INTERFACE::discretize_file(const string &path) {
+    std::ifstream in(path.c_str());
+    if (!in) throw npsl_error(NPSL_ERR_ARG, "mesh file could not be opened: " + path);
+    drop_context();
+    V.clear(); E.clear(); F.clear();
+    string tok;
+    unsigned int n = 0, a, b, c, idx;
+    double x, y, z, q0;
+    in >> tok >> tok >> tok >> tok >> n >> tok;
+    number_of_vertices = n;
+    V.resize(n);
+    for (unsigned int i = 0; i < n; i++) {
+        in >> idx >> x >> y >> z >> q0;
+        V.at(idx).posvec = VECTOR3D(x, y, z);
+        V[idx].index = idx;
+        V[idx].q = q0;
+    }
+    in >> tok >> tok >> tok >> tok >> n >> tok;
+    number_of_edges = n;
+    E.resize(n);
+    std::map<std::pair<unsigned, unsigned>, EDGE *> by_ends;
+    for (unsigned int i = 0; i < n; i++) {
+        in >> idx >> a >> b >> tok;
+        EDGE &e = E.at(idx);
+        e.index = idx;
+        e.itsV.push_back(&V.at(a));
+        e.itsV.push_back(&V.at(b));
+        V[a].itsE.push_back(&e);
+        V[b].itsE.push_back(&e);
+        by_ends[std::make_pair(std::min(a, b), std::max(a, b))] = &e;
+    }
+    in >> tok >> tok >> tok >> tok >> n >> tok;
+    number_of_faces = n;
+    F.resize(n);
+    int sign;
+    for (unsigned int i = 0; i < n; i++) {
+        in >> idx >> a >> b >> c >> sign >> tok;
+        FACE &f = F.at(idx);
+        f.index = idx;
+        const unsigned w[3] = {sign == 1 ? a : c, b, sign == 1 ? c : a};  // stored winding
+        for (int k = 0; k < 3; k++) f.itsV.push_back(&V.at(w[k]));
+        V[a].itsF.push_back(&f); V[b].itsF.push_back(&f); V[c].itsF.push_back(&f);
+        const unsigned side[3][2] = {{w[1], w[2]}, {w[2], w[0]}, {w[0], w[1]}};  // edge opposite corner k
+        for (int k = 0; k < 3; k++) {
+            auto it = by_ends.find(std::make_pair(std::min(side[k][0], side[k][1]), std::max(side[k][0], side[k][1])));
+            if (it == by_ends.end()) throw npsl_error(NPSL_ERR_ARG, "face side without an edge record");
+            f.itsE.push_back(it->second);
+            it->second->itsF.push_back(&f);
+        }
+    }
+    if (!in) throw npsl_error(NPSL_ERR_ARG, "mesh file truncated: " + path);
+    avg_edge_length = 0;
+    for (size_t i = 0; i < E.size(); i++) {
+        E[i].l0 = E[i].length();
+        avg_edge_length += E[i].l0;
+    }
+    avg_edge_length /= E.size();
+}
+
+// Deterministic branch only: vertices ranked by (z, index); the vertex of rank i receives the area share of
+// vertex i; total rescaled to an integer number of charges.
+void INTERFACE::assign_random_q_values(double q_strength, double /*alpha*/, int num_divisions, double frac_patch,
+                                       char randomFlag, char functionFlag) {
+    if (randomFlag != 'n' || functionFlag != 'n' || num_divisions < 1 || num_divisions > 2)
+        throw npsl_error(NPSL_ERR_ARG, "only the deterministic patterns -F n -H n with -N 1|2 are mirrored");
+    const size_t n = V.size();
+    // face areas at the current positions
+    vector<double> farea(F.size());
+    double total = 0;
+    for (size_t f = 0; f < F.size(); f++) {
+        const VECTOR3D d = (F[f].itsV[1]->posvec - F[f].itsV[0]->posvec) % (F[f].itsV[2]->posvec - F[f].itsV[1]->posvec);
+        farea[f] = 0.5 * d.GetMagnitude();
+        total += farea[f];
+    }
+    vector<double> varea(n, 0.0);
+    for (size_t f = 0; f < F.size(); f++)
+        for (int k = 0; k < 3; k++) varea[F[f].itsV[k]->index] += farea[f];
+    for (size_t i = 0; i < n; i++) varea[i] /= 3.0;
+    vector<std::pair<double, unsigned>> rank(n);
+    for (size_t i = 0; i < n; i++) rank[i] = std::make_pair(V[i].posvec.z, (unsigned) i);
+    std::sort(rank.begin(), rank.end());
+    for (size_t i = 0; i < n; i++) V[i].q = 0;
+    if (q_strength == 0) return;
+    const size_t n_patch = num_divisions == 1 ? n : (size_t) (frac_patch * n);
+    for (size_t i = 0; i < n_patch; i++) V[rank[i].second].q = q_strength * varea[i] / total;
+    const double target = std::round(num_divisions == 1 ? q_strength : frac_patch * q_strength);
+    double actual = 0;
+    for (size_t i = 0; i < n; i++) actual += V[i].q;
+    for (size_t i = 0; i < n; i++) V[i].q = V[i].q * (target / actual);
+}
+
+npsl_ctx *INTERFACE::context(double scalefactor, char bucklingFlag, const vector<THERMOSTAT> *mesh_bath,
+                             const vector<THERMOSTAT> *ions_bath, double dt) {
+    const double key[10] = {scalefactor, (double) bucklingFlag, bkappa, sconstant, sigma_a, sigma_v, ref_volume,
+                            inv_kappa_out, dt, (double) (mesh_bath ? mesh_bath->size() : 0)};
+    if (ctx && std::memcmp(key, ctx_key, sizeof key) == 0) return ctx;
+    drop_context();
+    vector<int32_t> ev(2 * E.size()), fv(3 * F.size());
+    vector<double> l0(E.size());
+    for (size_t e = 0; e < E.size(); e++) {
+        ev[2 * e] = E[e].itsV[0]->index; ev[2 * e + 1] = E[e].itsV[1]->index;
+        l0[e] = E[e].l0;
+    }
+    for (size_t f = 0; f < F.size(); f++)
+        for (int k = 0; k < 3; k++) fv[3 * f + k] = F[f].itsV[k]->index;
+    npsl_mesh_desc md = {(int32_t) V.size(), (int32_t) E.size(), (int32_t) F.size(), ev.data(), fv.data(), l0.data()};
+    npsl_params p;
+    std::memset(&p, 0, sizeof p);
+    p.scalefactor = scalefactor; p.em = em; p.inv_kappa_out = inv_kappa_out; p.elj = elj;
+    p.lj_length_mesh_mesh = lj_length_mesh_mesh; p.bkappa = bkappa; p.sconstant = sconstant;
+    p.sigma_a = sigma_a; p.sigma_v = sigma_v; p.ref_volume = ref_volume; p.avg_edge_length = avg_edge_length;
+    p.dt = dt; p.buckling = bucklingFlag == 'y' ? 1 : 0;
+    p.chain = mesh_bath ? (int32_t) mesh_bath->size() : 1;
+    if (mesh_bath) fill_links(p.mesh_bath, *mesh_bath);
+    if (ions_bath) fill_links(p.ions_bath, *ions_bath);
+    check(nullptr, npsl_create(&md, &p, &ctx), "npsl_create");
+    std::memcpy(ctx_key, key, sizeof key);
+    push_state();
+    return ctx;
+}
+
+void INTERFACE::push_state() {
+    const size_t n = V.size();
+    buf_a.resize(3 * n); buf_b.resize(3 * n); buf_c.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        buf_a[3 * i] = V[i].posvec.x; buf_a[3 * i + 1] = V[i].posvec.y; buf_a[3 * i + 2] = V[i].posvec.z;
+        buf_b[3 * i] = V[i].velvec.x; buf_b[3 * i + 1] = V[i].velvec.y; buf_b[3 * i + 2] = V[i].velvec.z;
+        buf_c[i] = V[i].q;
+    }
+    check(ctx, npsl_upload_state(ctx, buf_a.data(), buf_b.data(), buf_c.data()), "npsl_upload_state");
+}
+
+void INTERFACE::pull_state() {
+    const size_t n = V.size();
+    vector<double> f(3 * n);
+    buf_a.resize(3 * n); buf_b.resize(3 * n);
+    check(ctx, npsl_download_state(ctx, buf_a.data(), buf_b.data(), f.data()), "npsl_download_state");
+    for (size_t i = 0; i < n; i++) {
+        V[i].posvec = VECTOR3D(buf_a[3 * i], buf_a[3 * i + 1], buf_a[3 * i + 2]);
+        V[i].velvec = VECTOR3D(buf_b[3 * i], buf_b[3 * i + 1], buf_b[3 * i + 2]);
+        V[i].forvec = VECTOR3D(f[3 * i], f[3 * i + 1], f[3 * i + 2]);
+    }
+}
+
+void INTERFACE::pull_forces() {
+    const size_t n = V.size();
+    vector<double> f(3 * n), c[5];
+    check(ctx, npsl_download_state(ctx, nullptr, nullptr, f.data()), "npsl_download_state");
+    for (int k = 0; k < 5; k++) c[k].resize(3 * n);
+    check(ctx, npsl_download_force_components(ctx, c[0].data(), c[1].data(), c[2].data(), c[3].data(), c[4].data()),
+          "npsl_download_force_components");
+    for (size_t i = 0; i < n; i++) {
+        V[i].forvec = VECTOR3D(f[3 * i], f[3 * i + 1], f[3 * i + 2]);
+        V[i].bforce = VECTOR3D(c[1][3 * i], c[1][3 * i + 1], c[1][3 * i + 2]);
+        V[i].sforce = VECTOR3D(c[2][3 * i], c[2][3 * i + 1], c[2][3 * i + 2]);
+        V[i].TForce = VECTOR3D(c[3][3 * i], c[3][3 * i + 1], c[3][3 * i + 2]);
+        V[i].VolTForce = VECTOR3D(c[4][3 * i], c[4][3 * i + 1], c[4][3 * i + 2]);
+    }
+    vector<double> fa(F.size()), fvv(F.size()), fd(3 * F.size()), es(E.size());
+    check(ctx, npsl_download_mesh_fields(ctx, fa.data(), fvv.data(), fd.data(), es.data()), "npsl_download_mesh_fields");
+    for (size_t k = 0; k < F.size(); k++) {
+        F[k].itsarea = fa[k]; F[k].subtends_volume = fvv[k];
+        F[k].itsdirection = VECTOR3D(fd[3 * k], fd[3 * k + 1], fd[3 * k + 2]);
+    }
+    for (size_t k = 0; k < E.size(); k++) E[k].itsS = es[k];
+}
+
+void INTERFACE::dressup(double la, double lv) {
+    lambda_a = la; lambda_v = lv;
+    if (!ctx) {
+        // before the first force call (src/main.cpp:262,421): a context with neutral physics suffices for geometry
+        inv_kappa_out = inv_kappa_out > 0 ? inv_kappa_out : 1.0;
+        context(epsilon_water * lB_water, 'n');
+    } else {
+        push_state();
+    }
+    check(ctx, npsl_dressup(ctx, &total_area, &total_volume), "npsl_dressup");
+    vector<double> fa(F.size()), fvv(F.size()), fd(3 * F.size());
+    check(ctx, npsl_download_mesh_fields(ctx, fa.data(), fvv.data(), fd.data(), nullptr), "npsl_download_mesh_fields");
+    for (size_t k = 0; k < F.size(); k++) {
+        F[k].itsarea = fa[k]; F[k].subtends_volume = fvv[k];
+        F[k].itsdirection = VECTOR3D(fd[3 * k], fd[3 * k + 1], fd[3 * k + 2]);
+    }
+    for (size_t i = 0; i < V.size(); i++) {  // VERTEX::itsarea = a third of the incident faces
+        double a = 0;
+        for (size_t k = 0; k < V[i].itsF.size(); k++) a += V[i].itsF[k]->itsarea;
+        V[i].itsarea = a / 3.0;
+    }
+}
+
+void INTERFACE::compute_energy(int num, vector<PARTICLE> &counterions, const double scalefactor, char bucklingFlag) {
+    require_no_ions(counterions);
+    context(scalefactor, bucklingFlag);
+    check(ctx, npsl_energy(ctx, &parts), "npsl_energy");
+    netMeshKE = parts.kinetic; penergy = parts.potential; energy = parts.energy;
+    total_area = parts.total_area; total_volume = parts.total_volume;
+    std::ostringstream row;  // "num KE bE sE tE ljE esE volE", src/interface.cpp:987-1113
+    row << num << " " << parts.kinetic << " " << parts.bending << " " << parts.stretching << " " << parts.tension << " "
+        << parts.lj << " " << parts.electrostatic << " " << parts.volume;
+    append_line(outdir, "energy_in_parts_kE_bE_sE_tE_ljE_esE.dat", row.str());
+}
+
+void force_calculation_init(INTERFACE &boundary, vector<PARTICLE> &counterions, const double scalefactor, char bucklingFlag) {
+    require_no_ions(counterions);
+    npsl_ctx *c = boundary.context(scalefactor, bucklingFlag);
+    boundary.push_state();
+    check(c, npsl_force_init(c), "npsl_force_init");
+    boundary.pull_forces();
+}
+
+void force_calculation(INTERFACE &boundary, vector<PARTICLE> &counterions, const double scalefactor, char bucklingFlag) {
+    require_no_ions(counterions);
+    npsl_ctx *c = boundary.context(scalefactor, bucklingFlag);
+    boundary.push_state();
+    check(c, npsl_force(c), "npsl_force");
+    boundary.pull_forces();
+}
+
+long double compute_kinetic_energy(vector<VERTEX> &V) {
+    long double ke = 0;
+    for (size_t i = 0; i < V.size(); i++) {
+        V[i].ke = 0.5 * V[i].m * (V[i].velvec * V[i].velvec);
+        ke += V[i].ke;
+    }
+    return ke;
+}
+
+double bath_kinetic_energy(vector<THERMOSTAT> &bath) {
+    double s = 0;
+    for (size_t j = 0; j < bath.size(); j++) s += bath[j].kinetic_energy();
+    return s;
+}
+
+double bath_potential_energy(vector<THERMOSTAT> &bath) {
+    double s = 0;
+    for (size_t j = 0; j < bath.size(); j++) s += bath[j].potential_energy();
+    return s;
+}
+
+void initialize_velocities_to_zero(vector<VERTEX> &V, vector<PARTICLE> &ions) {
+    for (size_t i = 0; i < V.size(); i++) V[i].velvec = VECTOR3D(0, 0, 0);
+    for (size_t i = 0; i < ions.size(); i++) ions[i].velvec = VECTOR3D(0, 0, 0);
+}
+
+// The loop body runs on the device (one CUDA-graph launch per step); the host touches the state only
+// when the reference writes (num < 3 or num % writedata == 0), anneals, or at the end.
+void md_interface(INTERFACE &boundary, vector<PARTICLE> &counterions, vector<THERMOSTAT> &mesh_bath,
+                  vector<THERMOSTAT> &ions_bath, CONTROL &mdremote, char geomConstraint, char bucklingFlag,
+                  char /*constraintForm*/, const double scalefactor, double /*box_radius*/) {
+    require_no_ions(counterions);
+    if (geomConstraint != 'N') throw npsl_error(NPSL_ERR_ARG, "SHAKE/RATTLE constraints are not on the device path yet");
+    if (mesh_bath.size() != ions_bath.size() || mesh_bath.empty() || mesh_bath.size() > NPSL_MAX_CHAIN)
+        throw npsl_error(NPSL_ERR_ARG, "thermostat chains must have equal length in [1, NPSL_MAX_CHAIN]");
+    initialize_velocities_to_zero(boundary.V, counterions);
+    boundary.drop_context();
+    npsl_ctx *c = boundary.context(scalefactor, bucklingFlag, &mesh_bath, &ions_bath, mdremote.timestep);
+    check(c, npsl_force_init(c), "npsl_force_init");
+    npsl_bath_link mb[NPSL_MAX_CHAIN], ib[NPSL_MAX_CHAIN];
+    const string &dir = boundary.outdir;
+
+    auto sync_baths = [&]() {
+        check(c, npsl_get_thermostat(c, mb, ib), "npsl_get_thermostat");
+        read_links(mesh_bath, mb);
+        read_links(ions_bath, ib);
+    };
+    double initNetEnergy = 0;
+    int abortCounter = 0;
+    auto write_row = [&](int num) -> double {
+        boundary.compute_energy(num, counterions, scalefactor, bucklingFlag);
+        sync_baths();
+        const npsl_energies &e = boundary.parts;
+        const double bke = e.mesh_bath_ke + e.ions_bath_ke, bpe = e.mesh_bath_pe + e.ions_bath_pe;
+        const double global = boundary.energy + bke + bpe;
+        std::ostringstream s;
+        s << num << cell(boundary.netMeshKE) << cell(boundary.penergy) << cell(boundary.energy) << cell(global)
+          << cell(bke) << cell(bpe);
+        append_line(dir, "energy_nanomembrane.dat", s.str());
+        std::ostringstream a, v, t;
+        a << num << cell(boundary.total_area);
+        v << num << cell(boundary.total_volume);
+        t << num << cell(2 * boundary.netMeshKE / (mesh_bath[0].dof * kB));
+        append_line(dir, "area.dat", a.str());
+        append_line(dir, "volume.dat", v.str());
+        append_line(dir, "temperature.dat", t.str());
+        return global;
+    };
+    const double g0 = write_row(0);
+    initNetEnergy = boundary.energy + boundary.parts.mesh_bath_ke + boundary.parts.mesh_bath_pe;  // src/newmd.cpp:62
+    (void) g0;
+
+    double fT = std::pow(1.0 / mdremote.TAnnealFac, 1.0 / mdremote.annealDuration);
+    double fQ = std::pow(1.0 / mdremote.QAnnealFac, 1.0 / mdremote.annealDuration);
+    auto anneal_step = [&](int n) {
+        return mdremote.anneal == 'y' && n > mdremote.annealDuration &&
+               (n % mdremote.annealfreq == 0 || n % mdremote.annealfreq < mdremote.annealDuration);
+    };
+    int num = 0;
+    while (num < mdremote.steps) {
+        // run on the device up to the next step at which the host has something to do
+        int nxt = mdremote.steps;
+        nxt = std::min(nxt, num < 2 ? num + 1 : (num / mdremote.writedata + 1) * mdremote.writedata);
+        if (mdremote.anneal == 'y') {
+            if (anneal_step(num + 1)) nxt = std::min(nxt, num + 1);
+            nxt = std::min(nxt, (num / mdremote.annealfreq + 1) * mdremote.annealfreq);
+            if (num < mdremote.annealDuration + 1) nxt = std::min(nxt, mdremote.annealDuration + 1);
+        }
+        check(c, npsl_step(c, nxt - num), "npsl_step");
+        num = nxt;
+        if (num % mdremote.writedata == 0 || num < 3) {
+            const double global = write_row(num);
+            const double ratio = global / initNetEnergy;
+            std::ostringstream d;
+            d << num << "\t" << ratio << "\t" << global << "\t" << initNetEnergy << "\t" << abortCounter;
+            append_line(dir, "net_Energy_Drift.dat", d.str());
+            if (!(1.05 < ratio) && num < mdremote.annealfreq && ratio < 0.95) {  // src/newmd.cpp:205-220
+                abortCounter++;
+                if (abortCounter == 10)
+                    throw npsl_error(NPSL_ERR_NUMERIC, "aborting: >5% net energy drift downwards prior to annealing");
+            }
+        }
+        if (anneal_step(num)) {  // gradual annealing, src/newmd.cpp:258-299
+            sync_baths();
+            if (mesh_bath[0].T >= 0.000000000000001) {
+                if (num % mdremote.annealfreq == 0) {
+                    if (num == mdremote.annealfreq) mdremote.TAnnealFac = 1.25;
+                    else if (num <= 3 * mdremote.annealfreq) mdremote.TAnnealFac = 2;
+                    else if (num <= 6 * mdremote.annealfreq) mdremote.TAnnealFac = 4;
+                    else if (num <= 7 * mdremote.annealfreq) mdremote.TAnnealFac = 8;
+                    else mdremote.TAnnealFac = 10;
+                    mdremote.QAnnealFac = 1.0 + mdremote.TAnnealFac / 10.0;
+                    fT = std::pow(1.0 / mdremote.TAnnealFac, 1.0 / mdremote.annealDuration);
+                    fQ = std::pow(1.0 / mdremote.QAnnealFac, 1.0 / mdremote.annealDuration);
+                }
+                for (size_t b = 0; b < mesh_bath.size(); b++) {
+                    mesh_bath[b].T = fT * mesh_bath[b].T;
+                    mesh_bath[b].Q = fQ * mesh_bath[b].Q;
+                }
+                fill_links(mb, mesh_bath);
+                fill_links(ib, ions_bath);
+                check(c, npsl_set_thermostat(c, mb, ib), "npsl_set_thermostat");
+            }
+        }
+    }
+    boundary.pull_state();
+    sync_baths();
+}

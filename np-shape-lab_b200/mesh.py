@@ -308,3 +308,13 @@ def row_partition(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
     lo = min(rank * rng, n_rows)
     hi = min((rank + 1) * rng, n_rows)
     return lo, hi
+
+
+def shard_range(n_rows: int, rank: int, world: int, align: int = 32) -> Tuple[int, int]:
+    """Rows / vertices owned by one GPU rank of a sharded context (csrc/npsl.cu, create_impl): the
+    reference's ``ceil(N/P)`` rounded up to a whole warp of vertices, so that the per-warp
+    kinetic-energy partials -- and with them the trajectory -- are bit-identical to the single-GPU
+    run. Half-open interval; the last rank takes the remainder."""
+    rng = (n_rows + world - 1) // world
+    rng = (rng + align - 1) // align * align
+    return min(rank * rng, n_rows), min((rank + 1) * rng, n_rows)

@@ -1,0 +1,78 @@
+"""The C++ host mirror (np-shape-lab_b200/host_cpp): same call surface as the reference, bodies over
+the C ABI. CPU: it builds, links against libnpsl.so and fails loudly without a device. GPU: the
+README disc / Janus / buckled recipes run through its command-line driver reproduce the reference's
+own trajectories (tests/golden, written by the compiled reference)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+from np_shape_lab_b200 import mesh as M
+
+HOST = os.path.join(ROOT, "np-shape-lab_b200", "host_cpp")
+BIN = os.path.join(HOST, "np_shape_lab_b200")
+
+
+def build_host():
+    from np_shape_lab_b200 import build as B
+    B.build()
+    subprocess.check_call(["make", "-s", "-C", HOST])
+
+
+def test_host_cpp_builds_and_has_no_cpu_path(tmp_path):
+    build_host()
+    out = subprocess.run([BIN, "--help"], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0 and "no CPU path" in out.stdout
+    src = open(os.path.join(HOST, "npsl_host.hpp")).read()
+    for name in ("force_calculation_init", "force_calculation", "compute_energy", "dressup", "md_interface",
+                 "compute_kinetic_energy", "bath_kinetic_energy", "bath_potential_energy", "class VERTEX",
+                 "class EDGE", "class FACE", "class INTERFACE", "class THERMOSTAT", "class CONTROL"):
+        assert name in src, name
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        g = golden("disc_D4")
+        M.write_dat(str(tmp_path / "m.dat"), M.Mesh(pos=g["pos0"], edges=g["edges"], faces=g["faces"]))
+        r = subprocess.run([BIN, "--mesh", str(tmp_path / "m.dat"), "-S", "1", "--out", str(tmp_path / "o")],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 1 and "no CPU path" in r.stderr
+
+
+RECIPES = {
+    "disc_D4": ["-q", "600", "-c", "0.005"],
+    "janus_D8": ["-q", "600", "-c", "0.005", "-N", "2", "-p", "0.5"],
+    "buckled_D4": ["-q", "0", "-c", "0.005", "-t", "0", "-v", "0", "-b", "1", "-s", "1000", "-B", "y"],
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(RECIPES))
+def test_host_cpp_reproduces_reference_trajectory(name, tmp_path):
+    build_host()
+    g = golden(name)
+    M.write_dat(str(tmp_path / "m.dat"), M.Mesh(pos=g["pos0"], edges=g["edges"], faces=g["faces"]))
+    k = g.traj_steps[-1]
+    r = subprocess.run([BIN, "--mesh", str(tmp_path / "m.dat"), "-S", str(k), "--out", str(tmp_path / "outfiles")]
+                       + RECIPES[name], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    s = g.scalars(k)
+    cons = s["energy"] + s["mesh_bath_ke"] + s["mesh_bath_pe"] + s["ions_bath_ke"] + s["ions_bath_pe"]
+    assert abs(res["A"] - s["total_area"]) <= 1e-6 * s["total_area"]
+    assert abs(res["U"] - s["penergy"]) <= 1e-6 * abs(s["penergy"])
+    assert abs(res["E"] - cons) <= 1e-6 * abs(cons)
+    # the series files the reference writes (rows at 0, 1, 2 and every writedata steps)
+    rows = [l.split() for l in open(tmp_path / "outfiles" / "energy_nanomembrane.dat")]
+    assert [int(x[0]) for x in rows[:3]] == [0, 1, 2] and int(rows[-1][0]) == k
+    s0 = g.scalars(0)
+    assert abs(float(rows[0][2]) - s0["penergy"]) <= 2e-5 * abs(s0["penergy"])  # 6 printed digits
+    parts = [l.split() for l in open(tmp_path / "outfiles" / "energy_in_parts_kE_bE_sE_tE_ljE_esE.dat")]
+    assert len(parts) == len(rows) and len(parts[0]) == 8
+    for f in ("area.dat", "volume.dat", "temperature.dat", "net_Energy_Drift.dat"):
+        assert os.path.getsize(tmp_path / "outfiles" / f) > 0

@@ -1,0 +1,18 @@
+"""Profiling target (GPU box): force_calculation_init + a few MD steps of a named workload, nothing else.
+    python tools/profile_target.py [workload] [steps] [rows_per_thread] [col_splits]"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from np_shape_lab_b200 import capi, workloads as W
+name = sys.argv[1] if len(sys.argv) > 1 else "S64_disc"
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+w = W.build(name)
+P = capi.make_params(w.params, w.mesh_bath, w.ions_bath)
+with capi.Context(w.mesh.edges, w.mesh.faces, w.params["l0"], P, n_vertices=w.n_vertices) as ctx:
+    ctx.upload_state(w.mesh.pos, np.zeros_like(w.mesh.pos), w.q)
+    if len(sys.argv) > 4:
+        ctx.set_pair_plan(int(sys.argv[3]), int(sys.argv[4]))
+    ctx.force_init()
+    ctx.step(steps)
+    e = ctx.energy()
+    print("ok", name, steps, "steps, E =", e["energy"], ctx.pair_geometry())
