@@ -174,7 +174,9 @@ npsl_ctx *INTERFACE::context(double scalefactor, char bucklingFlag, const vector
                              const vector<THERMOSTAT> *ions_bath, double dt) {
     const double key[10] = {scalefactor, (double) bucklingFlag, bkappa, sconstant, sigma_a, sigma_v, ref_volume,
                             inv_kappa_out, dt, (double) (mesh_bath ? mesh_bath->size() : 0)};
-    if (ctx && std::memcmp(key, ctx_key, sizeof key) == 0) return ctx;
+    // calls that carry no thermostat (force_calculation, compute_energy, dressup) reuse whatever context the
+    // last md_interface / force call created for the same physics
+    if (ctx && std::memcmp(key, ctx_key, (mesh_bath ? 10 : 8) * sizeof(double)) == 0) return ctx;
     drop_context();
     vector<int32_t> ev(2 * E.size()), fv(3 * F.size());
     vector<double> l0(E.size());

@@ -76,3 +76,33 @@ def test_host_cpp_reproduces_reference_trajectory(name, tmp_path):
     assert len(parts) == len(rows) and len(parts[0]) == 8
     for f in ("area.dat", "volume.dat", "temperature.dat", "net_Energy_Drift.dat"):
         assert os.path.getsize(tmp_path / "outfiles" / f) > 0
+
+
+# README.md:29-65 of the reference: final area A, potential energy U and conserved energy E after
+# 25 000 steps on the 372-vertex mesh, "on order of a percent".
+README_FINALS = {
+    "disc_D4": (["-q", "600", "-c", "0.005"], 15.675, 2620.98, 2699.97),
+    "rod_D4": (["-q", "600", "-c", "0.01"], 13.259, 1919.14, 1939.96),
+    "janus_D4": (["-q", "600", "-c", "0.005", "-N", "2", "-p", "0.5"], 12.53, 1224.0, 1437.0),
+    "buckled_D4": (["-q", "0", "-c", "0.005", "-t", "0", "-v", "0", "-b", "1", "-s", "1000", "-B", "y"],
+                   12.3795, 26.86, 127.69),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(README_FINALS))
+def test_readme_final_values(name, tmp_path):
+    """The four README recipes, 25 000 steps each, through the C++ host driver."""
+    build_host()
+    flags, A, U, E = README_FINALS[name]
+    g = golden(name)
+    M.write_dat(str(tmp_path / "m.dat"), M.Mesh(pos=g["pos0"], edges=g["edges"], faces=g["faces"]))
+    r = subprocess.run([BIN, "--mesh", str(tmp_path / "m.dat"), "-S", "25000", "--out", str(tmp_path / "outfiles")]
+                       + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert abs(res["A"] - A) <= 0.01 * A, (res, A)
+    assert abs(res["U"] - U) <= 0.01 * U, (res, U)
+    assert abs(res["E"] - E) <= 0.01 * E, (res, E)
+    rows = [l.split() for l in open(tmp_path / "outfiles" / "energy_nanomembrane.dat")]
+    assert len(rows) == 3 + 25000 // 500  # steps 0,1,2 and every 500
