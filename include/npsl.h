@@ -196,6 +196,11 @@ int npsl_step_timing(npsl_ctx *ctx, int n_steps, int flush_l2, double *total_ms)
  * the automatic choice for that field. Results do not depend on rows_per_thread; they depend on
  * col_splits only through the (fixed, ordered) grouping of the column sum. */
 int npsl_set_pair_plan(npsl_ctx *ctx, int rows_per_thread, int col_splits);
+/* Pair kernel selection: 0 automatic (symmetric from 4096 vertices up), 1 ordered -- k_pair walks all
+ * N(N-1) ordered pairs like the reference loop --, 2 symmetric -- k_pair_sym evaluates each unordered pair
+ * once and applies it to both vertices. npsl_pair_mode returns the kernel in use (1 or 2). */
+int npsl_set_pair_mode(npsl_ctx *ctx, int mode);
+int npsl_pair_mode(const npsl_ctx *ctx);
 /* Owned row range of this context, half-open. */
 int npsl_owned_rows(const npsl_ctx *ctx, int32_t *lo, int32_t *hi);
 /* Launch geometry of the pair kernel: rows per thread, row tiles x column splits, columns per CTA. */

@@ -25,7 +25,8 @@ SYMBOLS = [
     "npsl_download_mesh_fields", "npsl_get_thermostat", "npsl_set_thermostat", "npsl_dressup", "npsl_force_init",
     "npsl_force", "npsl_step", "npsl_energy", "npsl_sync", "npsl_launch_count", "npsl_pair_timing",
     "npsl_pair_timing_read", "npsl_owned_rows", "npsl_pair_geometry", "npsl_fp64_peak", "npsl_md_run",
-    "npsl_step_timing", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_md_step_host",
+    "npsl_step_timing", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_md_step_host", "npsl_set_pair_mode",
+    "npsl_pair_mode",
 ]
 
 
@@ -110,6 +111,8 @@ def load() -> C.CDLL:
     L.npsl_force_calculation.argtypes = [vp, dp, dp]
     L.npsl_md_step_host.argtypes = [vp, dp, dp, dp, C.c_int, dp]
     L.npsl_set_pair_plan.argtypes = [vp, C.c_int, C.c_int]
+    L.npsl_set_pair_mode.argtypes = [vp, C.c_int]
+    L.npsl_pair_mode.argtypes = [vp]
     if L.npsl_abi_version() != ABI_VERSION:
         raise NpslError(-1, "libnpsl.so ABI version %d, binding expects %d" % (L.npsl_abi_version(), ABI_VERSION))
     _lib = L
@@ -334,6 +337,13 @@ class Context:
         a, b, c, d = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         self._ck(self.L.npsl_pair_geometry(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return {"rows_per_thread": a.value, "row_tiles": b.value, "col_splits": c.value, "cols_per_cta": d.value}
+
+    def set_pair_mode(self, mode: int) -> None:
+        """0 automatic, 1 ordered (k_pair), 2 symmetric (k_pair_sym)."""
+        self._ck(self.L.npsl_set_pair_mode(self.h, int(mode)))
+
+    def pair_mode(self) -> int:
+        return int(self.L.npsl_pair_mode(self.h))
 
     def set_pair_plan(self, rows_per_thread: int, col_splits: int) -> None:
         self._ck(self.L.npsl_set_pair_plan(self.h, int(rows_per_thread), int(col_splits)))

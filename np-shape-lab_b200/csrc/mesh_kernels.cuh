@@ -58,6 +58,8 @@ struct MeshParams {
     int buckling;
     int n_splits, row_stride;  // layout of the pair partial sums
     int use_pair;              // 0 when every charge is zero (pair partials are not read)
+    int pair_sym;              // 1: pair forces come from the 8 virtual-rank sums of k_pair_reduce
+    int npad;                  // plane length of those sums
     double dt;
     double pair_coef;  // scalefactor / em
     double bkappa, sconstant, sigma_a, sigma_v, ref_volume, avg_edge;
@@ -337,7 +339,8 @@ struct ForceComponents {  // FORCE mode only
 template <int MODE>
 __global__ void __launch_bounds__(kMeshThreads)
 k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *__restrict__ force,
-         const double4 *__restrict__ pair_partial, const double4 *__restrict__ lj_out, const int *__restrict__ lj_hit,
+         const double4 *__restrict__ pair_partial, const double *__restrict__ pair_fv,
+         const double4 *__restrict__ lj_out, const int *__restrict__ lj_hit,
          const double4 *__restrict__ bslot, const VertexTables T, const ForceComponents C,
          double *__restrict__ partials /* [2][nblocks] */, unsigned int *__restrict__ ticket,
          double *__restrict__ scal, double *__restrict__ ke_warp /* [n_ke_warps] */, int n_ke_warps,
@@ -355,9 +358,20 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
         V3 fp = mk(0, 0, 0);
         double ue = 0;
         if (P.use_pair) {
-            for (int s = 0; s < P.n_splits; s++) {
-                const double4 a = ldcg4(pair_partial + (size_t) s * P.row_stride + (i - P.row_lo));
-                fp.x += a.x; fp.y += a.y; fp.z += a.z; ue += a.w;
+            if (P.pair_sym) {  // fixed order over the 8 virtual ranks (pair_sym_kernel.cuh)
+#pragma unroll
+                for (int v = 0; v < 8; v++) {
+                    const double *f = pair_fv + (size_t) v * 3 * P.npad + i;
+                    fp.x += __ldcg(f); fp.y += __ldcg(f + P.npad); fp.z += __ldcg(f + 2 * (size_t) P.npad);
+                }
+                if (MODE == VMODE_FORCE)
+                    for (int s = 0; s < P.n_splits; s++)
+                        ue += ldcg4(pair_partial + (size_t) s * P.row_stride + (i - P.row_lo)).w;
+            } else {
+                for (int s = 0; s < P.n_splits; s++) {
+                    const double4 a = ldcg4(pair_partial + (size_t) s * P.row_stride + (i - P.row_lo));
+                    fp.x += a.x; fp.y += a.y; fp.z += a.z; ue += a.w;
+                }
             }
             const double cq = P.pair_coef * xi4.w;
             fp.x *= cq; fp.y *= cq; fp.z *= cq;

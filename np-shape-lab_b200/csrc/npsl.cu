@@ -24,6 +24,7 @@
 
 #include "mesh_kernels.cuh"
 #include "pair_kernel.cuh"
+#include "pair_sym_kernel.cuh"
 
 using namespace npsl;
 
@@ -130,6 +131,14 @@ struct npsl_ctx {
     size_t flush_bytes = 0;
     std::vector<cudaEvent_t> s_ev;
     int plan_rows = 0, plan_splits = 0;  // overrides of npsl_set_pair_plan (0 = automatic)
+    // symmetric (Newton's-third-law) pair path, pair_sym_kernel.cuh
+    int pair_mode = 0;       // 0 automatic, 1 ordered (k_pair), 2 symmetric (k_pair_sym)
+    bool use_sym = false;
+    SymParams sp;
+    int2 *sym_units = nullptr;   // this rank's units, heaviest first
+    int *sym_unit_id = nullptr;  // [row blocks][chunks] -> global unit index or -1
+    double *sym_rowpart = nullptr, *sym_colpart = nullptr, *sym_fv = nullptr;
+    int sym_n_units = 0, sym_n_units_total = 0, sym_v_first = 0, sym_v_count = kSymV;
     int n_sm = 148;
     std::string err;
 };
@@ -306,6 +315,58 @@ void apply_pair_plan(npsl_ctx *c) {
     c->mp.row_stride = c->pair_row_stride;
 }
 
+// Units of the symmetric pair kernel. Everything here depends on the vertex count only, except which of
+// the 8 virtual ranks (unit id mod 8) this rank computes: [rank*8/world, (rank+1)*8/world).
+int plan_sym(npsl_ctx *c) {
+    const int nv = c->nv;
+    SymParams &sp = c->sp;
+    sp.n = nv;
+    sp.npad = (nv + kSymRB - 1) / kSymRB * kSymRB;
+    sp.chunk_tiles = std::max(2, (nv + 64 * kSymCT - 1) / (64 * kSymCT));
+    const int n_tiles = (nv + kSymCT - 1) / kSymCT;
+    sp.n_chunks = (n_tiles + sp.chunk_tiles - 1) / sp.chunk_tiles;
+    sp.c2s = c->pp.c2s; sp.inv_lambda = c->pp.inv_lambda; sp.lj_cut_hi = c->pp.lj_cut_hi;
+    const int n_rb = sp.npad / kSymRB;
+    const bool want = c->pair_mode == 2 || (c->pair_mode == 0 && nv >= 4096);
+    c->use_sym = want && (kSymV % c->world == 0);
+    c->mp.pair_sym = c->use_sym ? 1 : 0;
+    c->mp.npad = sp.npad;
+    if (!c->use_sym) return 0;
+    c->sym_v_count = kSymV / c->world;
+    c->sym_v_first = c->rank * c->sym_v_count;
+    std::vector<int> unit_id((size_t) n_rb * sp.n_chunks, -1);
+    struct U { int I, cc, work; };
+    std::vector<U> mine;
+    int id = 0;
+    for (int I = 0; I < n_rb; I++)
+        for (int cc = 0; cc < sp.n_chunks; cc++) {
+            const int tile_end = std::min((cc + 1) * sp.chunk_tiles, n_tiles);
+            const int tile_begin = std::max(cc * sp.chunk_tiles, I * kSymRB / kSymCT);
+            if (tile_end <= tile_begin) continue;
+            unit_id[(size_t) I * sp.n_chunks + cc] = id;
+            const int v = id % kSymV;
+            if (v >= c->sym_v_first && v < c->sym_v_first + c->sym_v_count) mine.push_back({I, cc, tile_end - tile_begin});
+            id++;
+        }
+    c->sym_n_units_total = id;
+    std::stable_sort(mine.begin(), mine.end(), [](const U &a, const U &b) { return a.work > b.work; });
+    std::vector<int2> units(mine.size());
+    for (size_t k = 0; k < mine.size(); k++) units[k] = make_int2(mine[k].I, mine[k].cc);
+    c->sym_n_units = (int) units.size();
+    void *old[] = {c->sym_units, c->sym_unit_id, c->sym_rowpart, c->sym_colpart, c->sym_fv};
+    for (void *q : old)
+        if (q) cudaFree(q);
+    c->sym_units = nullptr; c->sym_unit_id = nullptr; c->sym_rowpart = c->sym_colpart = c->sym_fv = nullptr;
+    CU(dalloc(&c->sym_units, units.size()));
+    CU(dalloc(&c->sym_unit_id, unit_id.size()));
+    CU(dalloc(&c->sym_rowpart, (size_t) sp.n_chunks * 3 * sp.npad));
+    CU(dalloc(&c->sym_colpart, (size_t) n_rb * 3 * sp.npad));
+    CU(dalloc(&c->sym_fv, (size_t) kSymV * 3 * sp.npad));
+    CU(cudaMemcpy(c->sym_units, units.data(), sizeof(int2) * units.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->sym_unit_id, unit_id.data(), sizeof(int) * unit_id.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 template <int ROWS>
 void launch_pair(npsl_ctx *c, bool energy, cudaStream_t s) {
     dim3 grid(c->pair_row_tiles, c->pair_splits);
@@ -357,13 +418,31 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
             c->t_used += 2;
             CU(cudaEventRecord(e0, c->s_main));
         }
-        switch (c->pair_rows_per_thread) {
-            case 1: launch_pair<1>(c, energy, c->s_main); break;
-            case 2: launch_pair<2>(c, energy, c->s_main); break;
-            default: launch_pair<4>(c, energy, c->s_main); break;
+        const bool ordered = !c->use_sym || energy;  // the energy sum always comes from the ordered kernel
+        if (c->use_sym) {
+            k_pair_sym<<<c->sym_n_units, kPairThreads, 0, c->s_main>>>(c->xyzq, c->sym_units, c->sym_rowpart,
+                                                                       c->sym_colpart, c->lj_hit, c->sp);
+            n++;
+            if (e1) CU(cudaEventRecord(e1, c->s_main));
+            dim3 rg((c->nv + 127) / 128, c->sym_v_count);
+            k_pair_reduce<<<rg, 128, 0, c->s_main>>>(c->sym_rowpart, c->sym_colpart, c->sym_unit_id, c->sym_fv,
+                                                     c->sym_v_first, c->sp);
+            n++;
+            if (c->world > 1) {
+                const size_t per_rank = (size_t) c->sym_v_count * 3 * c->sp.npad;
+                NC(g_nccl.AllGather(c->sym_fv + (size_t) c->rank * per_rank, c->sym_fv, per_rank, ncclFloat64_, c->comm,
+                                    c->s_main));
+            }
         }
-        n++;
-        if (e1) CU(cudaEventRecord(e1, c->s_main));
+        if (ordered) {
+            switch (c->pair_rows_per_thread) {
+                case 1: launch_pair<1>(c, energy, c->s_main); break;
+                case 2: launch_pair<2>(c, energy, c->s_main); break;
+                default: launch_pair<4>(c, energy, c->s_main); break;
+            }
+            n++;
+            if (e1 && !c->use_sym) CU(cudaEventRecord(e1, c->s_main));
+        }
     }
     k_lj<<<(c->row_hi - c->row_lo + 127) / 128, 128, 0, c->s_main>>>(c->xyzq, c->lj_out, c->lj_hit,
                                                                       c->all_q_zero ? 1 : 0, c->ljp);
@@ -371,12 +450,12 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
     CU(cudaStreamWaitEvent(c->s_main, c->ev_join, 0));
     if (step) {
         k_vertex<VMODE_STEP><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(
-            c->xyzq, c->vel, c->force, c->pair_partial, c->lj_out, c->lj_hit, c->bslot, vt, fc, c->part_vert,
+            c->xyzq, c->vel, c->force, c->pair_partial, c->sym_fv, c->lj_out, c->lj_hit, c->bslot, vt, fc, c->part_vert,
             c->tickets + 1, c->scal, c->ke_warp, c->n_ke_warps, c->th_mid, c->th_cur, c->mp);
         n++;
     } else {
         k_vertex<VMODE_FORCE><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(
-            c->xyzq, c->vel, c->force, c->pair_partial, c->lj_out, c->lj_hit, c->bslot, vt, fc, c->part_vert,
+            c->xyzq, c->vel, c->force, c->pair_partial, c->sym_fv, c->lj_out, c->lj_hit, c->bslot, vt, fc, c->part_vert,
             c->tickets + 1, c->scal, c->ke_warp, c->n_ke_warps, c->th_mid, c->th_cur, c->mp);
         n++;
     }
@@ -576,6 +655,7 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     CUB(cudaMemcpy(c->th_cur, &th, sizeof th, cudaMemcpyHostToDevice));
     CUB(cudaMemcpy(c->th_mid, &th, sizeof th, cudaMemcpyHostToDevice));
 
+    if (plan_sym(c)) return bail(NPSL_ERR_CUDA);
     CUB(cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->s_side, cudaStreamNonBlocking));
     CUB(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -638,7 +718,8 @@ void npsl_destroy(npsl_ctx *c) {
     void *ptrs[] = {c->xyzq, c->vel, c->force, c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->face_v,
                     c->edge_rec, c->l0, c->degree, c->ring, c->bslot_ref, c->ring_l0, c->bslot, c->pair_partial,
                     c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_warp, c->th_cur, c->th_mid, c->part_mesh,
-                    c->part_vert, c->tickets, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out};
+                    c->part_vert, c->tickets, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units,
+                    c->sym_unit_id, c->sym_rowpart, c->sym_colpart, c->sym_fv};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -1011,6 +1092,21 @@ int npsl_set_pair_plan(npsl_ctx *c, int rows_per_thread, int col_splits) {
     c->forces_valid = false;
     return NPSL_OK;
 }
+
+int npsl_set_pair_mode(npsl_ctx *c, int mode) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    if (mode < 0 || mode > 2) return fail(c, NPSL_ERR_ARG, "mode must be 0 (automatic), 1 (ordered) or 2 (symmetric)");
+    CU(cudaStreamSynchronize(c->s_main));
+    c->pair_mode = mode;
+    int r = plan_sym(c);
+    if (r) return r;
+    if (mode == 2 && !c->use_sym) return fail(c, NPSL_ERR_ARG, "symmetric pair kernel needs a rank count that divides 8");
+    drop_graph(c);
+    c->forces_valid = false;
+    return NPSL_OK;
+}
+
+int npsl_pair_mode(const npsl_ctx *c) { return c ? (c->use_sym ? 2 : 1) : NPSL_ERR_ARG; }
 
 int npsl_owned_rows(const npsl_ctx *c, int32_t *lo, int32_t *hi) {
     if (!c) return NPSL_ERR_ARG;

@@ -14,7 +14,11 @@ print("dfma peak %.3e /s" % peak)
 with capi.Context(w.mesh.edges, w.mesh.faces, w.params["l0"], P, n_vertices=n) as ctx:
     ctx.upload_state(w.mesh.pos, np.zeros_like(w.mesh.pos), w.q)
     for rows, splits in plans:
-        ctx.set_pair_plan(rows, splits)
+        if rows < 0:  # symmetric kernel
+            ctx.set_pair_mode(2)
+        else:
+            ctx.set_pair_mode(1)
+            ctx.set_pair_plan(rows, splits)
         ctx.force_init()
         ctx.step(3)
         ctx.pair_timing(True)
