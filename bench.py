@@ -33,9 +33,11 @@ if ROOT not in sys.path:
 
 METRIC = "md_steps_per_s"
 UNIT = "steps/s"
-# FP64-pipe instructions the pair kernel executes per ordered pair (counted in the SASS of the inner
-# loop, profiles/r01_pair_sass_count.txt; force-only variant used inside a step)
-DFMA_PER_PAIR = 33
+# FP64-pipe instructions the pair kernel executes per ORDERED pair, counted in the SASS of the inner loops
+# (tools/sass_count.py -> profiles/r01_pair_sass_count.txt): k_pair_sym evaluates each unordered pair once
+# with 32.75 instructions (131 per 4 pairs, incl. the column accumulator update) = 16.375 per ordered pair;
+# the ordered k_pair needs 28 (force only).
+DFMA_PER_PAIR = {2: 16.375, 1: 28}
 ALGORITHMIC_FLOPS_PER_PAIR = 24  # force-only, exp and rsqrt counted as one flop each
 
 
@@ -277,7 +279,10 @@ def run_b200(args) -> None:
     dfma_peak, nominal_mhz = capi.fp64_peak()
     dfma_peak = max_over_ranks(dfma_peak) if world > 1 else dfma_peak
     pairs_per_launch = (hi - lo) * (n - 1)
-    achieved_dfma = pairs_per_launch * DFMA_PER_PAIR / (pair_ms * 1e-3) if pair_ms > 0 else 0.0
+    mode = ctx.pair_mode()
+    # the symmetric kernel's launch covers this rank's share (1/world) of all unordered pairs
+    pairs_per_launch = n * (n - 1) // world if mode == 2 else pairs_per_launch
+    achieved_dfma = pairs_per_launch * DFMA_PER_PAIR[mode] / (pair_ms * 1e-3) if pair_ms > 0 else 0.0
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -315,9 +320,11 @@ def run_b200(args) -> None:
         "roofline": {
             "bound": "fp64", "achieved": 2e-12 * achieved_dfma, "peak": 2e-12 * dfma_peak, "unit": "TFLOP/s",
             "frac": achieved_dfma / dfma_peak if dfma_peak else None, "traffic": None,
-            "kernel": "k_pair<%d,false>" % geo["rows_per_thread"], "kernel_ms": pair_ms, "kernel_launches_timed": pair_count,
+            "kernel": "k_pair_sym<4,128,3> (each unordered pair once, applied to both vertices)" if mode == 2
+                      else "k_pair<%d,false>" % geo["rows_per_thread"],
+            "kernel_ms": pair_ms, "kernel_launches_timed": pair_count,
             "kernel_share_of_step": pair_ms / ms_per_step,
-            "fp64_instr_per_pair": DFMA_PER_PAIR, "pairs_per_launch": pairs_per_launch,
+            "fp64_instr_per_ordered_pair": DFMA_PER_PAIR[mode], "ordered_pairs_per_launch": pairs_per_launch,
             "algorithmic_tflops_%dflop_per_pair" % ALGORITHMIC_FLOPS_PER_PAIR:
                 1e-12 * pairs_per_launch * ALGORITHMIC_FLOPS_PER_PAIR / (pair_ms * 1e-3) if pair_ms > 0 else None,
             "peak_source": "pure-DFMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 entry); "

@@ -133,6 +133,7 @@ struct npsl_ctx {
     int plan_rows = 0, plan_splits = 0;  // overrides of npsl_set_pair_plan (0 = automatic)
     // symmetric (Newton's-third-law) pair path, pair_sym_kernel.cuh
     int pair_mode = 0;       // 0 automatic, 1 ordered (k_pair), 2 symmetric (k_pair_sym)
+    int sym_rows = 4, sym_threads = 128, sym_minb = 0;  // k_pair_sym variant: rows per thread, threads per CTA
     bool use_sym = false;
     SymParams sp;
     int2 *sym_units = nullptr;   // this rank's units, heaviest first
@@ -321,12 +322,13 @@ int plan_sym(npsl_ctx *c) {
     const int nv = c->nv;
     SymParams &sp = c->sp;
     sp.n = nv;
-    sp.npad = (nv + kSymRB - 1) / kSymRB * kSymRB;
+    sp.npad = (nv + kSymPad - 1) / kSymPad * kSymPad;
+    sp.rb = c->sym_rows * c->sym_threads;
     sp.chunk_tiles = std::max(2, (nv + 64 * kSymCT - 1) / (64 * kSymCT));
     const int n_tiles = (nv + kSymCT - 1) / kSymCT;
     sp.n_chunks = (n_tiles + sp.chunk_tiles - 1) / sp.chunk_tiles;
     sp.c2s = c->pp.c2s; sp.inv_lambda = c->pp.inv_lambda; sp.lj_cut_hi = c->pp.lj_cut_hi;
-    const int n_rb = sp.npad / kSymRB;
+    const int n_rb = (nv + sp.rb - 1) / sp.rb;
     const bool want = c->pair_mode == 2 || (c->pair_mode == 0 && nv >= 4096);
     c->use_sym = want && (kSymV % c->world == 0);
     c->mp.pair_sym = c->use_sym ? 1 : 0;
@@ -341,7 +343,7 @@ int plan_sym(npsl_ctx *c) {
     for (int I = 0; I < n_rb; I++)
         for (int cc = 0; cc < sp.n_chunks; cc++) {
             const int tile_end = std::min((cc + 1) * sp.chunk_tiles, n_tiles);
-            const int tile_begin = std::max(cc * sp.chunk_tiles, I * kSymRB / kSymCT);
+            const int tile_begin = std::max(cc * sp.chunk_tiles, I * sp.rb / kSymCT);
             if (tile_end <= tile_begin) continue;
             unit_id[(size_t) I * sp.n_chunks + cc] = id;
             const int v = id % kSymV;
@@ -420,8 +422,19 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
         }
         const bool ordered = !c->use_sym || energy;  // the energy sum always comes from the ordered kernel
         if (c->use_sym) {
-            k_pair_sym<<<c->sym_n_units, kPairThreads, 0, c->s_main>>>(c->xyzq, c->sym_units, c->sym_rowpart,
-                                                                       c->sym_colpart, c->lj_hit, c->sp);
+#define SYM(R, T, B)                                                                                              \
+    k_pair_sym<R, T, B><<<c->sym_n_units, T, 0, c->s_main>>>(c->xyzq, c->sym_units, c->sym_rowpart, c->sym_colpart, \
+                                                             c->lj_hit, c->sp)
+            switch (c->sym_rows * 1000 + c->sym_threads) {
+                case 4128: if (c->sym_minb >= 8) SYM(4, 128, 4); else SYM(4, 128, 3); break;
+                case 2256: SYM(2, 256, 3); break;
+                case 2128: if (c->sym_minb >= 8) SYM(2, 128, 8); else SYM(2, 128, 6); break;
+                case 1512: SYM(1, 512, 2); break;
+                case 1256: SYM(1, 256, 4); break;
+                case 1128: SYM(1, 128, 8); break;
+                default: return fail(c, NPSL_ERR_ARG, "no k_pair_sym variant for %d rows x %d threads", c->sym_rows, c->sym_threads);
+            }
+#undef SYM
             n++;
             if (e1) CU(cudaEventRecord(e1, c->s_main));
             dim3 rg((c->nv + 127) / 128, c->sym_v_count);
@@ -1083,6 +1096,14 @@ int npsl_set_pair_plan(npsl_ctx *c, int rows_per_thread, int col_splits) {
     CU(cudaStreamSynchronize(c->s_main));
     c->plan_rows = rows_per_thread;
     c->plan_splits = col_splits;
+    if (c->use_sym) {  // measurement knob for the symmetric kernel: (rows per thread, threads per CTA [+1: tighter register cap])
+        if (rows_per_thread) c->sym_rows = rows_per_thread;
+        if (col_splits >= 128) { c->sym_threads = col_splits & ~1; c->sym_minb = (col_splits & 1) ? 8 : 0; }
+        c->plan_rows = c->plan_splits = 0;
+        plan_pair(c, c->n_sm);
+        int r = plan_sym(c);
+        if (r) return r;
+    }
     plan_pair(c, c->n_sm);
     if (c->pair_partial) cudaFree(c->pair_partial);
     c->pair_partial = nullptr;

@@ -2,11 +2,11 @@
 // FP64, sm_100a. Force-only twin of k_pair (pair_kernel.cuh) for the per-step path; it replaces the
 // same reference loop (src/newforces.cpp:153-177), which walks all N(N-1) ordered pairs.
 //
-// Work unit = (row block I of 512 rows) x (column chunk c of chunk_tiles x 128 columns); a unit exists
+// Work unit = (row block I of ROWS x THREADS rows) x (column chunk c of chunk_tiles x 128 columns); a unit exists
 // when the chunk reaches past the start of the row block, and it covers the pairs (i,j), i in I, j in c,
-// j > i. Each thread keeps 4 rows in registers (position, charge, force accumulator). A 128-column tile is
-// staged in shared memory (SoA) together with one force accumulator per column. Within a tile the four
-// warps work on the four 32-column groups, rotating groups between four phases; inside a phase lane l
+// j > i. Each thread keeps ROWS rows in registers (position, charge, force accumulator). A THREADS-column tile is
+// staged in shared memory (SoA) together with one force accumulator per column. Within a tile the
+// warps work on the 32-column groups, rotating groups between phases; inside a phase lane l
 // visits column (l + s) mod 32 at step s, so at any time every column is touched by exactly one thread:
 // the column accumulators need no atomics and receive their contributions in a fixed order.
 //   row partials    rowpart[c][k][i]   sum over the columns of chunk c        (k = x,y,z)
@@ -15,26 +15,27 @@
 // fixed order, and k_vertex adds the 8 results: the value does not depend on which GPU computed which
 // unit, so trajectories are bit-identical on 1, 2, 4 and 8 GPUs.
 //
-// FP64-pipe work per unordered pair: 32 instructions (20 for r, 1/r, exp; 4 for the geometry factor;
-// 2 charge products; 6 FMA into the two accumulators) = 16 per ordered pair, against 28 in k_pair.
+// FP64-pipe work per unordered pair: 32.75 instructions (20 for r, 1/r, exp; 4 for the geometry factor;
+// 2 charge products; 6 FMA into the two accumulators; 3 adds per 4 pairs for the column update)
+// = 16.4 per ordered pair, against 28 in k_pair (tools/sass_count.py).
 #pragma once
 #include "pair_kernel.cuh"
 
 namespace npsl {
 
-constexpr int kSymRows = 4;                          // rows per thread
-constexpr int kSymRB = kPairThreads * kSymRows;      // rows per row block (512)
-constexpr int kSymCT = 128;                          // columns per tile: 4 warps x 32
-constexpr int kSymV = 8;                             // virtual ranks (fixed grouping of the units)
+constexpr int kSymPad = 512;  // partial-buffer planes are padded to a multiple of this
+constexpr int kSymV = 8;      // virtual ranks (fixed grouping of the units)
 
 struct SymParams {
     double c2s, inv_lambda;
     int n;            // vertices
-    int npad;         // plane length of the partial buffers (>= n, multiple of kSymRB)
-    int chunk_tiles;  // tiles per column chunk
+    int npad;         // plane length of the partial buffers (>= n, multiple of kSymPad)
+    int rb;           // rows per row block = threads per CTA x rows per thread
+    int chunk_tiles;  // 128-column tiles per column chunk
     int n_chunks;
     int lj_cut_hi;
 };
+constexpr int kSymCT = 128;   // granularity of the column chunks (the kernels' column tile is THREADS wide)
 
 // e^{-r/lambda} (1/r^3 + 1/(lambda r^2)) of one pair; d = x_i - x_j
 __device__ __forceinline__ double pair_geom(double dx, double dy, double dz, const double c2s, const double inv_lambda,
@@ -55,36 +56,86 @@ struct SymRow {
     double fx, fy, fz;
 };
 
-template <bool DIAG>
-__device__ __forceinline__ void sym_phase(SymRow (&row)[kSymRows], const int (&gi)[kSymRows], const int gj0,
+// One phase: this warp against one 32-column group. Lane l visits column (l + s) mod 32 at step s. The
+// ROWS pair evaluations of a step are written stage by stage across the rows, so that the instruction
+// stream offers ROWS independent FP64 chains (the dependent-issue latency of the FP64 pipe is ~13 cycles).
+template <int ROWS, bool DIAG>
+__device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[ROWS], const int gj0,
                                           const double *__restrict__ sx, const double *__restrict__ sy,
                                           const double *__restrict__ sz, const double *__restrict__ sq,
                                           double *__restrict__ sax, double *__restrict__ say, double *__restrict__ saz,
                                           const int lane, const double c2s, const double inv_lambda,
                                           const double *__restrict__ tab, int &min_r2_hi) {
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
 #pragma unroll 1
     for (int s = 0; s < 32; s++) {
         const int col = (lane + s) & 31;
         const double xj = sx[col], yj = sy[col], zj = sz[col], qj = sq[col];
-        double ax = 0.0, ay = 0.0, az = 0.0;
+        double dx[ROWS], dy[ROWS], dz[ROWS], qc[ROWS], qr[ROWS], a[ROWS], b[ROWS], y[ROWS];
 #pragma unroll
-        for (int r = 0; r < kSymRows; r++) {
-            double cx = xj, qc = qj, qr = row[r].q;
+        for (int r = 0; r < ROWS; r++) {
+            double cx = xj;
+            qc[r] = qj;
+            qr[r] = row[r].q;
             if (DIAG) {  // inside the row block: count (i,j) once, j > i; everything else contributes exactly zero
                 const bool on = (gj0 + col) > gi[r];
                 cx = on ? xj : row[r].x - 1.0;  // keeps r finite for the self pair
-                qc = on ? qj : 0.0;
-                qr = on ? qr : 0.0;
+                qc[r] = on ? qj : 0.0;
+                qr[r] = on ? qr[r] : 0.0;
             }
-            const double dx = row[r].x - cx, dy = row[r].y - yj, dz = row[r].z - zj;
-            const double t = pair_geom(dx, dy, dz, c2s, inv_lambda, tab, min_r2_hi);
-            const double sj = qc * t, si = qr * t;
-            row[r].fx = fma(sj, dx, row[r].fx);
-            row[r].fy = fma(sj, dy, row[r].fy);
-            row[r].fz = fma(sj, dz, row[r].fz);
-            ax = fma(si, dx, ax);
-            ay = fma(si, dy, ay);
-            az = fma(si, dz, az);
+            dx[r] = row[r].x - cx; dy[r] = row[r].y - yj; dz[r] = row[r].z - zj;
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) a[r] = fma(dz[r], dz[r], fma(dy[r], dy[r], dx[r] * dx[r]));  // r^2
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            min_r2_hi = min(min_r2_hi, __double2hiint(a[r]));
+            y[r] = rsqrt_seed(a[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) b[r] = a[r] * y[r];
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) b[r] = fma(-b[r], y[r], 1.0);  // e
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            const double p = fma(b[r], 0.375, 0.5);
+            y[r] = fma(y[r] * b[r], p, y[r]);  // 1/r
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) a[r] = a[r] * y[r];  // r
+        double tt[ROWS], f[ROWS], T[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) tt[r] = fma(a[r], c2s, MAGIC);
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            f[r] = fma(a[r], c2s, -(tt[r] - MAGIC));
+            const int n = __double2loint(tt[r]);
+            const double Tj = tab[n & (kExpTab - 1)];
+            const int k = max(n >> NPSL_EXP2_TB, -1000);
+            T[r] = __hiloint2double(__double2hiint(Tj) + (k << 20), __double2loint(Tj));
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) b[r] = fma(f[r], NPSL_EXP2_G4, NPSL_EXP2_G3);
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) b[r] = fma(b[r], f[r], NPSL_EXP2_G2);
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) b[r] = fma(b[r], f[r], NPSL_EXP2_G1);
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            const double ex = fma(T[r], f[r] * b[r], T[r]);
+            const double w = (y[r] * y[r]) * (y[r] + inv_lambda);
+            a[r] = ex * w;  // e^{-r/lambda} (1/r^3 + 1/(lambda r^2))
+        }
+        double ax = 0.0, ay = 0.0, az = 0.0;
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            const double sj = qc[r] * a[r], si = qr[r] * a[r];
+            row[r].fx = fma(sj, dx[r], row[r].fx);
+            row[r].fy = fma(sj, dy[r], row[r].fy);
+            row[r].fz = fma(sj, dz[r], row[r].fz);
+            ax = fma(si, dx[r], ax);
+            ay = fma(si, dy[r], ay);
+            az = fma(si, dz[r], az);
         }
         sax[col] -= ax;
         say[col] -= ay;
@@ -93,24 +144,27 @@ __device__ __forceinline__ void sym_phase(SymRow (&row)[kSymRows], const int (&g
     }
 }
 
-// grid = units of this rank (heaviest first); block = kPairThreads.
-__global__ void __launch_bounds__(kPairThreads)
+// grid = units of this rank (heaviest first); block = THREADS; row block = ROWS * THREADS rows (== P.rb).
+template <int ROWS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, double *__restrict__ rowpart,
            double *__restrict__ colpart, int *__restrict__ lj_hit, const SymParams P) {
-    __shared__ double sx[kSymCT], sy[kSymCT], sz[kSymCT], sq[kSymCT];
-    __shared__ double sax[kSymCT], say[kSymCT], saz[kSymCT];
+    constexpr int RB = ROWS * THREADS;
+    constexpr int GROUPS = THREADS / 32;
+    __shared__ double sx[THREADS], sy[THREADS], sz[THREADS], sq[THREADS];
+    __shared__ double sax[THREADS], say[THREADS], saz[THREADS];
     __shared__ double tab[kExpTab];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    for (int k = t; k < kExpTab; k += kPairThreads) tab[k] = c_exp2_tab[k];
+    for (int k = t; k < kExpTab; k += THREADS) tab[k] = c_exp2_tab[k];
     const int2 unit = units[blockIdx.x];
     const int I = unit.x, c = unit.y;
-    const int row0 = I * kSymRB;
+    const int row0 = I * RB;
 
-    SymRow row[kSymRows];
-    int gi[kSymRows];
+    SymRow row[ROWS];
+    int gi[ROWS];
 #pragma unroll
-    for (int r = 0; r < kSymRows; r++) {
-        gi[r] = row0 + r * kPairThreads + t;
+    for (int r = 0; r < ROWS; r++) {
+        gi[r] = row0 + r * THREADS + t;
         const double4 v = xyzq[min(gi[r], P.n - 1)];
         row[r].x = v.x; row[r].y = v.y; row[r].z = v.z;
         row[r].q = gi[r] < P.n ? v.w : 0.0;  // rows past the end exert nothing and are never stored
@@ -118,15 +172,14 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
     }
     const double c2s = P.c2s, inv_lambda = P.inv_lambda;
     int min_r2_hi = 0x7fffffff;
-    const int n_tiles = (P.n + kSymCT - 1) / kSymCT;
-    const int tile_end = min((c + 1) * P.chunk_tiles, n_tiles);
-    const int tile_begin = max(c * P.chunk_tiles, row0 / kSymCT);  // tiles below the row block belong to other units
+    // columns of this unit: the chunk, from the start of the row block on (what lies below belongs to other units)
+    const int col_begin = max(c * P.chunk_tiles * kSymCT, row0);
+    const int col_end = min((c + 1) * P.chunk_tiles * kSymCT, P.n);
 
-    for (int tile = tile_begin; tile < tile_end; tile++) {
-        const int j0 = tile * kSymCT;
+    for (int j0 = col_begin; j0 < col_end; j0 += THREADS) {
         const int j = j0 + t;
         __syncthreads();
-        if (j < P.n) {
+        if (j < col_end) {
             const double4 v = xyzq[j];
             sx[t] = v.x; sy[t] = v.y; sz[t] = v.z; sq[t] = v.w;
         } else {  // padding columns: far away, no charge
@@ -134,19 +187,21 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
         }
         sax[t] = 0.0; say[t] = 0.0; saz[t] = 0.0;
         __syncthreads();
-        const bool diag = j0 < row0 + kSymRB;
+        const bool diag = j0 < row0 + RB;
 #pragma unroll 1
-        for (int p = 0; p < 4; p++) {
-            const int o = ((warp + p) & 3) * 32;
-            if (!diag)
-                sym_phase<false>(row, gi, j0 + o, sx + o, sy + o, sz + o, sq + o, sax + o, say + o, saz + o, lane, c2s,
-                                 inv_lambda, tab, min_r2_hi);
-            else
-                sym_phase<true>(row, gi, j0 + o, sx + o, sy + o, sz + o, sq + o, sax + o, say + o, saz + o, lane, c2s,
-                                inv_lambda, tab, min_r2_hi);
+        for (int p = 0; p < GROUPS; p++) {
+            const int o = ((warp + p) % GROUPS) * 32;
+            if (j0 + o < col_end) {  // whole group of padding columns: nothing to do
+                if (!diag)
+                    sym_phase<ROWS, false>(row, gi, j0 + o, sx + o, sy + o, sz + o, sq + o, sax + o, say + o, saz + o,
+                                           lane, c2s, inv_lambda, tab, min_r2_hi);
+                else
+                    sym_phase<ROWS, true>(row, gi, j0 + o, sx + o, sy + o, sz + o, sq + o, sax + o, say + o, saz + o,
+                                          lane, c2s, inv_lambda, tab, min_r2_hi);
+            }
             __syncthreads();
         }
-        if (j < P.n) {
+        if (j < col_end) {
             double *cp = colpart + (size_t) I * 3 * P.npad + j;
             cp[0] = sax[t];
             cp[P.npad] = say[t];
@@ -154,7 +209,7 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
         }
     }
 #pragma unroll
-    for (int r = 0; r < kSymRows; r++) {
+    for (int r = 0; r < ROWS; r++) {
         if (gi[r] < P.n) {
             double *rp = rowpart + (size_t) c * 3 * P.npad + gi[r];
             rp[0] = row[r].fx;
@@ -174,7 +229,7 @@ k_pair_reduce(const double *__restrict__ rowpart, const double *__restrict__ col
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = v_first + blockIdx.y;
     if (x >= P.n) return;
-    const int Ix = x / kSymRB, cx = x / (P.chunk_tiles * kSymCT);
+    const int Ix = x / P.rb, cx = x / (P.chunk_tiles * kSymCT);
     double fx = 0.0, fy = 0.0, fz = 0.0;
     for (int c = cx; c < P.n_chunks; c++) {
         const int id = __ldg(unit_id + Ix * P.n_chunks + c);

@@ -14,8 +14,9 @@ print("dfma peak %.3e /s" % peak)
 with capi.Context(w.mesh.edges, w.mesh.faces, w.params["l0"], P, n_vertices=n) as ctx:
     ctx.upload_state(w.mesh.pos, np.zeros_like(w.mesh.pos), w.q)
     for rows, splits in plans:
-        if rows < 0:  # symmetric kernel
+        if rows < 0:  # symmetric kernel: [-rows_per_thread, threads (+1: tighter register cap)]
             ctx.set_pair_mode(2)
+            ctx.set_pair_plan(-rows, splits)
         else:
             ctx.set_pair_mode(1)
             ctx.set_pair_plan(rows, splits)
@@ -27,6 +28,6 @@ with capi.Context(w.mesh.edges, w.mesh.faces, w.params["l0"], P, n_vertices=n) a
         ctx.pair_timing(False)
         g = ctx.pair_geometry()
         pairs = n * (n - 1)
-        print("rows=%d splits=%d grid=%dx%d cols/cta=%d  %.4f ms  %.3e pairs/s  frac33=%.3f" % (
-            g["rows_per_thread"], g["col_splits"], g["row_tiles"], g["col_splits"], g["cols_per_cta"], ms,
-            pairs / ms * 1e3, pairs * 33 / (ms * 1e-3) / peak), flush=True)
+        per_pair = 16 if rows < 0 else 28
+        print("plan=%s mode=%d geom=%s  %.4f ms  %.3e ordered pairs/s  fp64 pipe frac=%.3f" % (
+            [rows, splits], ctx.pair_mode(), g, ms, pairs / ms * 1e3, pairs * per_pair / (ms * 1e-3) / peak), flush=True)
