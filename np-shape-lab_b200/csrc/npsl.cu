@@ -324,7 +324,8 @@ int plan_sym(npsl_ctx *c) {
     sp.n = nv;
     sp.npad = (nv + kSymPad - 1) / kSymPad * kSymPad;
     sp.rb = c->sym_rows * c->sym_threads;
-    sp.chunk_tiles = std::max(2, (nv + 64 * kSymCT - 1) / (64 * kSymCT));
+    // 256 columns per unit up to 32768 vertices, at most 256 chunks beyond: fine-grained enough to fill 8 GPUs
+    sp.chunk_tiles = std::max(2, (nv + 256 * kSymCT - 1) / (256 * kSymCT));
     const int n_tiles = (nv + kSymCT - 1) / kSymCT;
     sp.n_chunks = (n_tiles + sp.chunk_tiles - 1) / sp.chunk_tiles;
     sp.c2s = c->pp.c2s; sp.inv_lambda = c->pp.inv_lambda; sp.lj_cut_hi = c->pp.lj_cut_hi;
