@@ -259,6 +259,8 @@ def run_b200(args) -> None:
     geo = ctx.pair_geometry()
     lo, hi = ctx.owned_rows()
 
+    profile_txt = ctx.step_profile(20) if args.profile else None
+
     # ---- end to end through the host-buffer entry point: state lives in host memory between steps
     pos = np.ascontiguousarray(ctx.download_state()["pos"])
     st = ctx.download_state()
@@ -280,6 +282,7 @@ def run_b200(args) -> None:
     dfma_peak = max_over_ranks(dfma_peak) if world > 1 else dfma_peak
     pairs_per_launch = (hi - lo) * (n - 1)
     mode = ctx.pair_mode()
+    ctx_pair_mode, ctx_xchg_mode = mode, ctx.exchange_mode()
     # the symmetric kernel's launch covers this rank's share (1/world) of all unordered pairs
     pairs_per_launch = n * (n - 1) // world if mode == 2 else pairs_per_launch
     achieved_dfma = pairs_per_launch * DFMA_PER_PAIR[mode] / (pair_ms * 1e-3) if pair_ms > 0 else 0.0
@@ -305,11 +308,13 @@ def run_b200(args) -> None:
         "config": {
             "workload": args.workload, "vertices": n, "edges": w.mesh.n_edges, "faces": w.mesh.n_faces,
             "ordered_pairs_per_step": n * (n - 1), "reference_cli": w.cli,
-            "sharding": "rows of the pair term and owned vertices split over %d GPU(s); NCCL all-gather of positions "
-                        "and of the per-rank kinetic energy each step" % world if world > 1 else "single GPU",
+            "sharding": "units of the pair term (8 virtual ranks) and owned vertices split over %d GPU(s); positions, "
+                        "pair-force sums and kinetic-energy partials exchanged each step" % world if world > 1 else "single GPU",
             "l2": "flushed between timed steps (256 MiB memset outside each step's CUDA-event bracket); "
                   "ms_per_step = sum of the per-step brackets / K, max over ranks",
-            "pair_plan": geo,
+            "pair_plan": geo, "pair_kernel": {1: "ordered (k_pair)", 2: "symmetric (k_pair_sym)"}[ctx_pair_mode],
+            "exchange": {0: "none (single GPU)", 1: "NCCL all-gathers", 2: "direct stores into peer memory over NVLink "
+                         "(CUDA IPC) with epoch flags"}[ctx_xchg_mode],
         },
         "wall_ms_per_step_incl_flush": wall_ms / args.steps,
         "gpu_launches": int(gpu_launches),
@@ -344,6 +349,8 @@ def run_b200(args) -> None:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "reference",
                                     "sample": "unavailable: %s" % ex}
     print(json.dumps(line), flush=True)
+    if profile_txt:
+        sys.stderr.write("step breakdown on rank 0 (%d GPU(s)):\n%s" % (world, profile_txt))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -358,6 +365,7 @@ def main() -> None:
     ap.add_argument("--workload", default="S64_disc")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="also print a per-segment device-time breakdown of a step to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -192,6 +192,9 @@ int npsl_pair_timing_read(npsl_ctx *ctx, double *mean_ms, int64_t *launches);
  * context's own stream. flush_l2 != 0: a buffer larger than L2 is overwritten before every step,
  * outside that step's event bracket; the result is the sum of the per-step brackets. */
 int npsl_step_timing(npsl_ctx *ctx, int n_steps, int flush_l2, double *total_ms);
+/* Per-segment device time of a step (CUDA events between the launches of n_steps directly launched steps),
+ * formatted as text into out. Measurement only. */
+int npsl_step_profile(npsl_ctx *ctx, int n_steps, char *out, int out_len);
 /* Override the pair kernel's launch plan (rows per thread in {1,2,4}, column splits >= 1); 0 keeps
  * the automatic choice for that field. Results do not depend on rows_per_thread; they depend on
  * col_splits only through the (fixed, ordered) grouping of the column sum. */
@@ -201,6 +204,10 @@ int npsl_set_pair_plan(npsl_ctx *ctx, int rows_per_thread, int col_splits);
  * once and applies it to both vertices. npsl_pair_mode returns the kernel in use (1 or 2). */
 int npsl_set_pair_mode(npsl_ctx *ctx, int mode);
 int npsl_pair_mode(const npsl_ctx *ctx);
+/* How a sharded context exchanges positions, pair-force sums and kinetic-energy partials each step:
+ * 0 single GPU, 1 NCCL all-gathers, 2 direct stores into peer memory over NVLink (CUDA IPC; default when the
+ * buffers can be mapped; NPSL_EXCHANGE=nccl in the environment forces 1). */
+int npsl_exchange_mode(const npsl_ctx *ctx);
 /* Owned row range of this context, half-open. */
 int npsl_owned_rows(const npsl_ctx *ctx, int32_t *lo, int32_t *hi);
 /* Launch geometry of the pair kernel: rows per thread, row tiles x column splits, columns per CTA. */

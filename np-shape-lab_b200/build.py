@@ -17,7 +17,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libnpsl.so")
 SOURCES = ["npsl.cu"]
-DEPENDS = ["npsl.cu", "pair_kernel.cuh", "pair_sym_kernel.cuh", "mesh_kernels.cuh", "exp2_table.inc", os.path.join(ROOT, "include", "npsl.h")]
+DEPENDS = ["npsl.cu", "pair_kernel.cuh", "pair_sym_kernel.cuh", "mesh_kernels.cuh", "xchg.cuh", "exp2_table.inc", os.path.join(ROOT, "include", "npsl.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

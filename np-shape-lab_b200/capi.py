@@ -26,7 +26,7 @@ SYMBOLS = [
     "npsl_force", "npsl_step", "npsl_energy", "npsl_sync", "npsl_launch_count", "npsl_pair_timing",
     "npsl_pair_timing_read", "npsl_owned_rows", "npsl_pair_geometry", "npsl_fp64_peak", "npsl_md_run",
     "npsl_step_timing", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_md_step_host", "npsl_set_pair_mode",
-    "npsl_pair_mode",
+    "npsl_pair_mode", "npsl_exchange_mode", "npsl_step_profile",
 ]
 
 
@@ -113,6 +113,8 @@ def load() -> C.CDLL:
     L.npsl_set_pair_plan.argtypes = [vp, C.c_int, C.c_int]
     L.npsl_set_pair_mode.argtypes = [vp, C.c_int]
     L.npsl_pair_mode.argtypes = [vp]
+    L.npsl_exchange_mode.argtypes = [vp]
+    L.npsl_step_profile.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
     if L.npsl_abi_version() != ABI_VERSION:
         raise NpslError(-1, "libnpsl.so ABI version %d, binding expects %d" % (L.npsl_abi_version(), ABI_VERSION))
     _lib = L
@@ -344,6 +346,15 @@ class Context:
 
     def pair_mode(self) -> int:
         return int(self.L.npsl_pair_mode(self.h))
+
+    def step_profile(self, n_steps: int = 20) -> str:
+        buf = C.create_string_buffer(4096)
+        self._ck(self.L.npsl_step_profile(self.h, int(n_steps), buf, 4096))
+        return buf.value.decode()
+
+    def exchange_mode(self) -> int:
+        """0 single GPU, 1 NCCL all-gathers, 2 stores into peer memory over NVLink."""
+        return int(self.L.npsl_exchange_mode(self.h))
 
     def set_pair_plan(self, rows_per_thread: int, col_splits: int) -> None:
         self._ck(self.L.npsl_set_pair_plan(self.h, int(rows_per_thread), int(col_splits)))

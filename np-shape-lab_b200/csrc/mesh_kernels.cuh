@@ -17,10 +17,12 @@
 // so every kernel is a coalesced sweep plus L2-resident gathers, with no atomics on data and a
 // fixed summation order (run-to-run deterministic, independent of the row sharding).
 //
-// Step = k_kick_drift -> { k_pair || k_mesh } -> k_vertex<STEP>, captured in a CUDA Graph.
+// Step = k_kick_drift -> { pair kernels || k_mesh -> k_vertex_mesh } -> k_vertex<STEP>, captured in a CUDA Graph.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "xchg.cuh"
 
 namespace npsl {
 
@@ -144,22 +146,6 @@ __device__ __forceinline__ void chain_eta(BathLink *b, int chain, double dt) {
     for (int j = 0; j < chain; j++)
         if (b[j].Q != 0) b[j].eta = b[j].eta + 0.5 * dt * b[j].xi;
 }
-// first half of a step, src/newmd.cpp:99-110
-__device__ __forceinline__ double thermo_reverse(Thermo &t, int chain, double dt, double ke) {
-    for (int j = chain - 1; j > -1; j--) chain_xi(t.mesh, j, chain, dt, ke);
-    for (int j = chain - 1; j > -1; j--) chain_xi(t.ions, j, chain, dt, 0.0);
-    chain_eta(t.mesh, chain, dt);
-    chain_eta(t.ions, chain, dt);
-    return exp(-0.5 * dt * t.mesh[0].xi);
-}
-// second half of a step, src/newmd.cpp:161-170
-__device__ __forceinline__ void thermo_forward(Thermo &t, int chain, double dt, double ke) {
-    chain_eta(t.mesh, chain, dt);
-    chain_eta(t.ions, chain, dt);
-    for (int j = 0; j < chain; j++) chain_xi(t.mesh, j, chain, dt, ke);
-    for (int j = 0; j < chain; j++) chain_xi(t.ions, j, chain, dt, 0.0);
-}
-
 // Kinetic energy, summed the same way however the vertices are sharded: every warp of k_vertex
 // leaves the sum of its 32 vertices (fixed shuffle tree) in ke_warp[global vertex index / 32]; the
 // whole array (all ranks' warps, all-gathered when sharded) is then summed by one block with this
@@ -173,44 +159,67 @@ __device__ __forceinline__ double canonical_sum(const double *__restrict__ p, in
     return v[0];
 }
 
+// End of a force evaluation, called by the first two lanes of the block that holds the total kinetic
+// energy: lane 0 advances the mesh chain, lane 1 the ion chain (they are independent, src/newmd.cpp:99-110).
+// Inside a step: forward half-chain, th_mid -> th_cur (src/newmd.cpp:161-170). Always: the reverse half-chain
+// of the step that may follow from th_cur into th_mid, with exp(-dt/2 xi_0) and dt/2 sqrt(.) left in the
+// scalar block, so that k_kick_drift is a pure streaming kernel.
+__device__ __forceinline__ void thermo_finish(Thermo *th_mid, Thermo *th_cur, double *scal, const double ke_mesh,
+                                              const bool step, const MeshParams &P) {
+    const int who = threadIdx.x;  // 0: mesh chain, 1: ion chain
+    if (who > 1) return;
+    BathLink *mid = who == 0 ? th_mid->mesh : th_mid->ions;
+    BathLink *cur = who == 0 ? th_cur->mesh : th_cur->ions;
+    const double ke = who == 0 ? ke_mesh : 0.0;
+    const int n = P.chain;
+    if (step) {  // th_mid -> (eta, then xi forward) -> th_cur
+        for (int j = 0; j < n; j++) cur[j] = mid[j];
+        chain_eta(cur, n, P.dt);
+        for (int j = 0; j < n; j++) chain_xi(cur, j, n, P.dt, ke);
+    }
+    for (int j = 0; j < n; j++) mid[j] = cur[j];
+    for (int j = n - 1; j > -1; j--) chain_xi(mid, j, n, P.dt, ke);
+    chain_eta(mid, n, P.dt);
+    if (who == 0) {
+        const double ef = exp(-0.5 * P.dt * mid[0].xi);
+        scal[SC_EXPFAC] = ef;
+        scal[SC_KICK] = 0.5 * P.dt * sqrt(ef);
+    }
+}
+
+// After npsl_set_thermostat (annealing): th_cur changed, prepare th_mid and the kick scalars again.
+__global__ void k_thermo_prepare(Thermo *th_cur, Thermo *th_mid, double *scal, const MeshParams P) {
+    if (blockIdx.x == 0) thermo_finish(th_mid, th_cur, scal, scal[SC_KE], false, P);
+}
+
 // ------------------------------------------------------------------------------------------------
-// k_kick_drift: reverse half-chain (once per block, thread 0), first half-kick, drift.
-// src/newmd.cpp:99-123. th_cur is read by every block; block 0 publishes the half-updated chain
-// to th_mid, which k_vertex<STEP> / k_thermo_post complete into th_cur.
+// k_kick_drift: first half-kick and drift of the owned vertices, src/newmd.cpp:114-123. The reverse
+// half-chain of this step was already done by thermo_finish at the end of the previous force evaluation.
 __global__ void __launch_bounds__(kMeshThreads)
 k_kick_drift(double4 *__restrict__ xyzq, double4 *__restrict__ vel, const double4 *__restrict__ force,
-             const Thermo *__restrict__ th_cur, Thermo *__restrict__ th_mid, double *__restrict__ scal,
-             int *__restrict__ lj_hit, const MeshParams P) {
-    __shared__ double s_ef, s_kick;
-    if (threadIdx.x == 0) {
-        Thermo t = *th_cur;
-        const double ke = __ldcg(scal + SC_KE);  // all vertices, all ranks
-        const double ef = thermo_reverse(t, P.chain, P.dt, ke);
-        const double kick = 0.5 * P.dt * sqrt(ef);
-        s_ef = ef;
-        s_kick = kick;
-        if (blockIdx.x == 0) {
-            *th_mid = t;
-            scal[SC_EXPFAC] = ef;
-            scal[SC_KICK] = kick;
-            *lj_hit = 0;
+             const double *__restrict__ scal, int *__restrict__ lj_hit, double4 *const *__restrict__ peer_xyzq,
+             const Xchg X, const MeshParams P) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *lj_hit = 0;
+    const int i = P.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.row_hi) {
+        const double ef = __ldcg(scal + SC_EXPFAC), kick = __ldcg(scal + SC_KICK), dt = P.dt;
+        double4 v = vel[i];
+        const double4 f = force[i];
+        double4 x = xyzq[i];
+        v.x = fma(v.x, ef, f.x * kick);
+        v.y = fma(v.y, ef, f.y * kick);
+        v.z = fma(v.z, ef, f.z * kick);
+        x.x = fma(v.x, dt, x.x);
+        x.y = fma(v.y, dt, x.y);
+        x.z = fma(v.z, dt, x.z);
+        vel[i] = v;
+        if (X.on) {  // the new position goes straight into every rank's copy (NVLink peer stores)
+            for (int r = 0; r < X.world; r++) peer_xyzq[r][i] = x;
+        } else {
+            xyzq[i] = x;
         }
     }
-    __syncthreads();
-    const int i = P.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.row_hi) return;
-    const double ef = s_ef, kick = s_kick, dt = P.dt;
-    double4 v = vel[i];
-    const double4 f = force[i];
-    double4 x = xyzq[i];
-    v.x = v.x * ef + f.x * kick;
-    v.y = v.y * ef + f.y * kick;
-    v.z = v.z * ef + f.z * kick;
-    x.x = x.x + v.x * dt;
-    x.y = x.y + v.y * dt;
-    x.z = x.z + v.z * dt;
-    vel[i] = v;
-    xyzq[i] = x;
+    if (X.on) xchg_signal(X, XK_POS, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -315,14 +324,14 @@ k_mesh(const double4 *__restrict__ xyzq, const int4 *__restrict__ face_v, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_vertex: gather-by-vertex of every force term, then (STEP) the second half-kick, the kinetic
-// energy and the forward half-chain, or (FORCE) the per-term forces and the pair energies.
-//   pair       (scalefactor/em) q_i sum_splits partial                src/newforces.cpp:173-176
+// k_vertex_mesh: gather-by-vertex of the mesh-elastic force terms of the owned vertices. Runs on the side
+// stream right after k_mesh, i.e. concurrently with the pair kernel, and leaves their sum in fmesh.
 //   bending    sum of the vertex's 2*degree slots                     src/edge.cpp:38-58
 //   stretching -s avg^2 sum_e (l-l0)/l (x_v-x_o)/l0^2  (or -B y form)  src/vertex.cpp:56-89
 //   tension    sigma_a * sum_F -grad A_F ; 2 sigma_v (V-V0) sum_F -grad V_F   src/vertex.cpp:34-53,92-106
-//   forvec = sum of the five                                          src/newforces.cpp:279-280
-//   v <- v expfac + f dt/2 sqrt(expfac); ke = 1/2 v.v                 src/newmd.cpp:146-157
+// k_vertex: pair term + fmesh = forvec (src/newforces.cpp:279-280), then (STEP) the second half-kick
+//   v <- v expfac + f dt/2 sqrt(expfac) and ke = 1/2 v.v (src/newmd.cpp:146-157) and the thermostat, or
+//   (FORCE) the pair force component and the pair energies.
 enum { VMODE_STEP = 0, VMODE_FORCE = 1 };
 
 struct VertexTables {
@@ -338,27 +347,87 @@ struct ForceComponents {  // FORCE mode only
 
 template <int MODE>
 __global__ void __launch_bounds__(kMeshThreads)
+k_vertex_mesh(const double4 *__restrict__ xyzq, const double4 *__restrict__ bslot, const VertexTables T,
+              const ForceComponents C, const double *__restrict__ scal, double4 *__restrict__ fmesh,
+              const MeshParams P) {
+    const int i = P.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.row_hi) return;
+    const int nv = P.nv;
+    const V3 p = ld3(xyzq, i);
+    // ---- bending: gather the slots written by k_mesh
+    V3 fb = mk(0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 2 * kMaxDeg; k++) {
+        const int s = __ldg(T.bslot_ref + k * nv + i);
+        if (s >= 0) {
+            const double4 a = ldcg4(bslot + s);
+            fb.x += a.x; fb.y += a.y; fb.z += a.z;
+        }
+    }
+    // ---- one-ring: stretching, surface tension, volume tension
+    V3 fs = mk(0, 0, 0), gA = mk(0, 0, 0), gV = mk(0, 0, 0);
+    const int deg = __ldg(T.degree + i);
+    const V3 pfirst = ld3(xyzq, __ldg(T.ring + i));
+    V3 pn = pfirst;
+#pragma unroll
+    for (int k = 0; k < kMaxDeg; k++) {
+        if (k >= deg) break;
+        // pn = position of ring[k]; pnn = position of ring[k+1] (cyclic)
+        const V3 pnn = (k + 1 < deg) ? ld3(xyzq, __ldg(T.ring + (k + 1) * nv + i)) : pfirst;
+        // stretching along edge (v, ring[k])
+        const V3 d = sub(p, pn);
+        const double l = sqrt(dot(d, d));
+        double c;
+        if (!P.buckling) {
+            const double le = __ldg(T.ring_l0 + k * nv + i);
+            c = ((l - le) / l) * (1.0 / (le * le));
+        } else {
+            c = (l - P.avg_edge) / l;
+        }
+        fs.x += c * d.x; fs.y += c * d.y; fs.z += c * d.z;
+        // face (p, pn, pnn): FACE::computegradients, src/face.cpp:47-91
+        const V3 cv = cross(pn, pnn);
+        gV.x -= (1. / 6.) * cv.x; gV.y -= (1. / 6.) * cv.y; gV.z -= (1. / 6.) * cv.z;
+        const V3 cp = cross(sub(pn, p), sub(pnn, p));
+        const V3 num = cross(sub(pn, pnn), cp);
+        const double inv_den = 1.0 / (2.0 * sqrt(dot(cp, cp)));
+        gA.x -= num.x * inv_den; gA.y -= num.y * inv_den; gA.z -= num.z * inv_den;
+        pn = pnn;
+    }
+    const double ks = P.buckling ? -P.sconstant : -P.sconstant * P.avg_edge * P.avg_edge;
+    fs.x *= ks; fs.y *= ks; fs.z *= ks;
+    const double kv = 2.0 * P.sigma_v * (__ldcg(scal + SC_VOL) - P.ref_volume);
+    const V3 ft = mk(P.sigma_a * gA.x, P.sigma_a * gA.y, P.sigma_a * gA.z);
+    const V3 fv = mk(kv * gV.x, kv * gV.y, kv * gV.z);
+    fmesh[i] = make_double4(fb.x + fs.x + ft.x + fv.x, fb.y + fs.y + ft.y + fv.y, fb.z + fs.z + ft.z + fv.z, 0.0);
+    if (MODE == VMODE_FORCE) {
+        C.bend[i] = make_double4(fb.x, fb.y, fb.z, 0.0);
+        C.stretch[i] = make_double4(fs.x, fs.y, fs.z, 0.0);
+        C.tension[i] = make_double4(ft.x, ft.y, ft.z, 0.0);
+        C.voltension[i] = make_double4(fv.x, fv.y, fv.z, 0.0);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kMeshThreads)
 k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *__restrict__ force,
-         const double4 *__restrict__ pair_partial, const double *__restrict__ pair_fv,
-         const double4 *__restrict__ lj_out, const int *__restrict__ lj_hit,
-         const double4 *__restrict__ bslot, const VertexTables T, const ForceComponents C,
-         double *__restrict__ partials /* [2][nblocks] */, unsigned int *__restrict__ ticket,
+         const double4 *__restrict__ fmesh, const double4 *__restrict__ pair_partial,
+         const double *__restrict__ pair_fv, const double4 *__restrict__ lj_out, const int *__restrict__ lj_hit,
+         const ForceComponents C, double *__restrict__ partials /* [2][nblocks] */, unsigned int *__restrict__ ticket,
          double *__restrict__ scal, double *__restrict__ ke_warp /* [n_ke_warps] */, int n_ke_warps,
-         const Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur, const MeshParams P) {
+         Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur, double *const *__restrict__ peer_ke,
+         const Xchg X, const MeshParams P) {
     __shared__ double red[3 * 32];
     __shared__ bool s_last;
     const int nblocks = gridDim.x;
     const int i = P.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
     double acc[3] = {0, 0, 0};  // ke, es energy, lj energy
     if (i < P.row_hi) {
-        const int nv = P.nv;
-        const double4 xi4 = ldg4(xyzq + i);
-        const V3 p = mk(xi4.x, xi4.y, xi4.z);
-        // ---- pair term: ordered sum over the column splits
+        // ---- pair term: fixed-order sum of the partial results
         V3 fp = mk(0, 0, 0);
         double ue = 0;
         if (P.use_pair) {
-            if (P.pair_sym) {  // fixed order over the 8 virtual ranks (pair_sym_kernel.cuh)
+            if (P.pair_sym) {  // the 8 virtual ranks (pair_sym_kernel.cuh)
 #pragma unroll
                 for (int v = 0; v < 8; v++) {
                     const double *f = pair_fv + (size_t) v * 3 * P.npad + i;
@@ -367,13 +436,13 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
                 if (MODE == VMODE_FORCE)
                     for (int s = 0; s < P.n_splits; s++)
                         ue += ldcg4(pair_partial + (size_t) s * P.row_stride + (i - P.row_lo)).w;
-            } else {
+            } else {  // the column chunks of the ordered kernel (pair_kernel.cuh)
                 for (int s = 0; s < P.n_splits; s++) {
                     const double4 a = ldcg4(pair_partial + (size_t) s * P.row_stride + (i - P.row_lo));
                     fp.x += a.x; fp.y += a.y; fp.z += a.z; ue += a.w;
                 }
             }
-            const double cq = P.pair_coef * xi4.w;
+            const double cq = P.pair_coef * __ldg(&xyzq[i].w);
             fp.x *= cq; fp.y *= cq; fp.z *= cq;
             ue *= 0.5 * cq;
         }
@@ -382,67 +451,18 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
             const double4 a = ldcg4(lj_out + (i - P.row_lo));
             fp.x += a.x; fp.y += a.y; fp.z += a.z; ulj = a.w;
         }
-        // ---- bending: gather the slots written by k_mesh
-        V3 fb = mk(0, 0, 0);
-#pragma unroll
-        for (int k = 0; k < 2 * kMaxDeg; k++) {
-            const int s = __ldg(T.bslot_ref + k * nv + i);
-            if (s >= 0) {
-                const double4 a = ldcg4(bslot + s);
-                fb.x += a.x; fb.y += a.y; fb.z += a.z;
-            }
-        }
-        // ---- one-ring: stretching, surface tension, volume tension
-        V3 fs = mk(0, 0, 0), gA = mk(0, 0, 0), gV = mk(0, 0, 0);
-        const int deg = __ldg(T.degree + i);
-        const V3 pfirst = ld3(xyzq, __ldg(T.ring + i));
-        V3 pn = pfirst;
-#pragma unroll
-        for (int k = 0; k < kMaxDeg; k++) {
-            if (k >= deg) break;
-            // pn = position of ring[k]; pnn = position of ring[k+1] (cyclic)
-            const V3 pnn = (k + 1 < deg) ? ld3(xyzq, __ldg(T.ring + (k + 1) * nv + i)) : pfirst;
-            // stretching along edge (v, ring[k])
-            const V3 d = sub(p, pn);
-            const double l = sqrt(dot(d, d));
-            double c;
-            if (!P.buckling) {
-                const double le = __ldg(T.ring_l0 + k * nv + i);
-                c = ((l - le) / l) * (1.0 / (le * le));
-            } else {
-                c = (l - P.avg_edge) / l;
-            }
-            fs.x += c * d.x; fs.y += c * d.y; fs.z += c * d.z;
-            // face (p, pn, pnn): FACE::computegradients, src/face.cpp:47-91
-            const V3 cv = cross(pn, pnn);
-            gV.x -= (1. / 6.) * cv.x; gV.y -= (1. / 6.) * cv.y; gV.z -= (1. / 6.) * cv.z;
-            const V3 cp = cross(sub(pn, p), sub(pnn, p));
-            const V3 num = cross(sub(pn, pnn), cp);
-            const double inv_den = 1.0 / (2.0 * sqrt(dot(cp, cp)));
-            gA.x -= num.x * inv_den; gA.y -= num.y * inv_den; gA.z -= num.z * inv_den;
-            pn = pnn;
-        }
-        const double ks = P.buckling ? -P.sconstant : -P.sconstant * P.avg_edge * P.avg_edge;
-        fs.x *= ks; fs.y *= ks; fs.z *= ks;
-        const double kv = 2.0 * P.sigma_v * (__ldcg(scal + SC_VOL) - P.ref_volume);
-        const V3 ft = mk(P.sigma_a * gA.x, P.sigma_a * gA.y, P.sigma_a * gA.z);
-        const V3 fv = mk(kv * gV.x, kv * gV.y, kv * gV.z);
-        const V3 f = mk(fp.x + fb.x + fs.x + ft.x + fv.x, fp.y + fb.y + fs.y + ft.y + fv.y,
-                        fp.z + fb.z + fs.z + ft.z + fv.z);
+        const double4 fm = ldcg4(fmesh + i);
+        const V3 f = mk(fp.x + fm.x, fp.y + fm.y, fp.z + fm.z);
         force[i] = make_double4(f.x, f.y, f.z, 0.0);
         double4 v = vel[i];
         if (MODE == VMODE_STEP) {
             const double ef = __ldcg(scal + SC_EXPFAC), kick = __ldcg(scal + SC_KICK);
-            v.x = v.x * ef + f.x * kick;
-            v.y = v.y * ef + f.y * kick;
-            v.z = v.z * ef + f.z * kick;
+            v.x = fma(v.x, ef, f.x * kick);
+            v.y = fma(v.y, ef, f.y * kick);
+            v.z = fma(v.z, ef, f.z * kick);
             vel[i] = v;
         } else {
             C.pair[i] = make_double4(fp.x, fp.y, fp.z, 0.0);
-            C.bend[i] = make_double4(fb.x, fb.y, fb.z, 0.0);
-            C.stretch[i] = make_double4(fs.x, fs.y, fs.z, 0.0);
-            C.tension[i] = make_double4(ft.x, ft.y, ft.z, 0.0);
-            C.voltension[i] = make_double4(fv.x, fv.y, fv.z, 0.0);
             acc[1] = ue;
             acc[2] = ulj;
         }
@@ -454,7 +474,13 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ke += __shfl_down_sync(0xffffffffu, ke, o);
         const int i0 = P.row_lo + blockIdx.x * blockDim.x + (threadIdx.x & ~31);
-        if ((threadIdx.x & 31) == 0 && i0 < P.row_hi) ke_warp[i0 >> 5] = ke;
+        if ((threadIdx.x & 31) == 0 && i0 < P.row_hi) {
+            if (X.on) {
+                for (int r = 0; r < X.world; r++) peer_ke[r][i0 >> 5] = ke;
+            } else {
+                ke_warp[i0 >> 5] = ke;
+            }
+        }
     }
     if (MODE == VMODE_FORCE) {  // pair energies of the owned rows (summed over ranks by the host, rank order)
         double e2[2] = {acc[1], acc[2]};
@@ -464,6 +490,7 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
             partials[nblocks + blockIdx.x] = e2[1];
         }
     }
+    if (X.on) xchg_signal(X, XK_KE, nblocks);
     __syncthreads();  // every warp's ke_warp store precedes thread 0's fence + ticket
     if (threadIdx.x == 0) s_last = take_last_ticket(ticket, nblocks);
     __syncthreads();
@@ -482,33 +509,35 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
         }
         __syncthreads();
     }
-    if (P.n_ranks > 1) return;  // sharded: k_ke_post finishes after the all-gather of ke_warp
+    if (P.n_ranks > 1) return;  // sharded: k_ke_post finishes after the exchange of ke_warp
+    __shared__ double s_ke;
     const double ke = canonical_sum(ke_warp, n_ke_warps, red);
     if (threadIdx.x == 0) {
         scal[SC_KE] = ke;
-        if (MODE == VMODE_STEP) {
-            Thermo t = *th_mid;
-            thermo_forward(t, P.chain, P.dt, ke);
-            *th_cur = t;
-        }
+        s_ke = ke;
     }
+    __syncthreads();
+    thermo_finish(th_mid, th_cur, scal, s_ke, MODE == VMODE_STEP, P);
 }
 
 // Sharded runs: after the all-gather of every rank's warp partials, one block sums them in the
 // canonical order (identical arithmetic on every rank) and, inside a step, runs the forward half-chain.
 __global__ void __launch_bounds__(kMeshThreads)
 k_ke_post(const double *__restrict__ ke_warp, int n_ke_warps, double *__restrict__ scal,
-          const Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur, int step, const MeshParams P) {
+          Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur, int step, const Xchg X, const MeshParams P) {
     __shared__ double red[32];
+    if (X.on) {
+        if (threadIdx.x < 32) xchg_wait_warp(X, XK_KE);
+        __syncthreads();
+    }
+    __shared__ double s_ke;
     const double ke = canonical_sum(ke_warp, n_ke_warps, red);
     if (threadIdx.x == 0) {
         scal[SC_KE] = ke;
-        if (step) {
-            Thermo t = *th_mid;
-            thermo_forward(t, P.chain, P.dt, ke);
-            *th_cur = t;
-        }
+        s_ke = ke;
     }
+    __syncthreads();
+    thermo_finish(th_mid, th_cur, scal, s_ke, step != 0, P);
 }
 
 // ------------------------------------------------------------------------------------------------

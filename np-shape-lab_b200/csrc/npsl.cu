@@ -83,7 +83,7 @@ struct npsl_ctx {
     bool forces_valid = false;
 
     // state, one 32-byte record per vertex (coalesced 16-byte accesses everywhere)
-    double4 *xyzq = nullptr, *vel = nullptr, *force = nullptr;
+    double4 *xyzq = nullptr, *vel = nullptr, *force = nullptr, *fmesh = nullptr;
     double4 *comp[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // pair, bend, stretch, tension, voltension
     // topology
     int4 *face_v = nullptr, *edge_rec = nullptr;
@@ -137,10 +137,24 @@ struct npsl_ctx {
     bool use_sym = false;
     SymParams sp;
     int2 *sym_units = nullptr;   // this rank's units, heaviest first
-    int *sym_unit_id = nullptr;  // [row blocks][chunks] -> global unit index or -1
     double *sym_rowpart = nullptr, *sym_colpart = nullptr, *sym_fv = nullptr;
     int sym_n_units = 0, sym_n_units_total = 0, sym_v_first = 0, sym_v_count = kSymV;
     int n_sm = 148;
+    // npsl_step_profile: events recorded between the launches of a step
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<const char *> prof_names;
+    size_t prof_used = 0;
+    // exchanges over NVLink peer memory (xchg.cuh); NCCL all-gathers are the fallback
+    bool p2p = false;
+    Xchg xg;                                      // kernel parameter block
+    unsigned long long *xflags = nullptr;         // [XK_KINDS][kMaxRanks], written by the peers
+    unsigned long long *xstate = nullptr;         // epochs
+    unsigned int *xtickets = nullptr;
+    void *peer_map[4][kMaxRanks] = {};            // host copies of the mapped peer pointers (xyzq, fv, ke, flags)
+    double4 **d_peer_xyzq = nullptr;
+    double **d_peer_fv = nullptr, **d_peer_ke = nullptr;
+    unsigned long long **d_peer_flags = nullptr;
     std::string err;
 };
 
@@ -317,7 +331,8 @@ void apply_pair_plan(npsl_ctx *c) {
 }
 
 // Units of the symmetric pair kernel. Everything here depends on the vertex count only, except which of
-// the 8 virtual ranks (unit id mod 8) this rank computes: [rank*8/world, (rank+1)*8/world).
+// the 8 virtual ranks this rank computes: [rank*8/world, (rank+1)*8/world). A row block's units all belong
+// to sym_vrank(row block).
 int plan_sym(npsl_ctx *c) {
     const int nv = c->nv;
     SymParams &sp = c->sp;
@@ -337,36 +352,33 @@ int plan_sym(npsl_ctx *c) {
     if (!c->use_sym) return 0;
     c->sym_v_count = kSymV / c->world;
     c->sym_v_first = c->rank * c->sym_v_count;
-    std::vector<int> unit_id((size_t) n_rb * sp.n_chunks, -1);
     struct U { int I, cc, work; };
     std::vector<U> mine;
-    int id = 0;
-    for (int I = 0; I < n_rb; I++)
+    int total = 0;
+    for (int I = 0; I < n_rb; I++) {
+        const int v = sym_vrank(I);
         for (int cc = 0; cc < sp.n_chunks; cc++) {
             const int tile_end = std::min((cc + 1) * sp.chunk_tiles, n_tiles);
             const int tile_begin = std::max(cc * sp.chunk_tiles, I * sp.rb / kSymCT);
             if (tile_end <= tile_begin) continue;
-            unit_id[(size_t) I * sp.n_chunks + cc] = id;
-            const int v = id % kSymV;
+            total++;
             if (v >= c->sym_v_first && v < c->sym_v_first + c->sym_v_count) mine.push_back({I, cc, tile_end - tile_begin});
-            id++;
         }
-    c->sym_n_units_total = id;
+    }
+    c->sym_n_units_total = total;
     std::stable_sort(mine.begin(), mine.end(), [](const U &a, const U &b) { return a.work > b.work; });
     std::vector<int2> units(mine.size());
     for (size_t k = 0; k < mine.size(); k++) units[k] = make_int2(mine[k].I, mine[k].cc);
     c->sym_n_units = (int) units.size();
-    void *old[] = {c->sym_units, c->sym_unit_id, c->sym_rowpart, c->sym_colpart, c->sym_fv};
+    void *old[] = {c->sym_units, c->sym_rowpart, c->sym_colpart};
     for (void *q : old)
         if (q) cudaFree(q);
-    c->sym_units = nullptr; c->sym_unit_id = nullptr; c->sym_rowpart = c->sym_colpart = c->sym_fv = nullptr;
+    c->sym_units = nullptr; c->sym_rowpart = c->sym_colpart = nullptr;
     CU(dalloc(&c->sym_units, units.size()));
-    CU(dalloc(&c->sym_unit_id, unit_id.size()));
     CU(dalloc(&c->sym_rowpart, (size_t) sp.n_chunks * 3 * sp.npad));
     CU(dalloc(&c->sym_colpart, (size_t) n_rb * 3 * sp.npad));
-    CU(dalloc(&c->sym_fv, (size_t) kSymV * 3 * sp.npad));
+    if (!c->sym_fv) CU(dalloc(&c->sym_fv, (size_t) kSymV * 3 * sp.npad));  // fixed size: peers map it
     CU(cudaMemcpy(c->sym_units, units.data(), sizeof(int2) * units.size(), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->sym_unit_id, unit_id.data(), sizeof(int) * unit_id.size(), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -385,13 +397,31 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
     const VertexTables vt = {c->degree, c->ring, c->ring_l0, c->bslot_ref};
     const ForceComponents fc = {c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4]};
     int n = 0;
+    auto mark = [&](const char *name) {
+        if (!c->prof) return;
+        if (c->prof_used == c->prof_ev.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            c->prof_ev.push_back(e);
+            c->prof_names.push_back(name);
+        }
+        c->prof_names[c->prof_used] = name;
+        cudaEventRecord(c->prof_ev[c->prof_used++], c->s_main);
+    };
+    mark("begin");
     if (step) {
-        k_kick_drift<<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->force, c->th_cur,
-                                                                        c->th_mid, c->scal, c->lj_hit, c->mp);
+        k_kick_drift<<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->force, c->scal, c->lj_hit,
+                                                                        c->d_peer_xyzq, c->xg, c->mp);
         n++;
-        if (c->world > 1)
+        mark("k_kick_drift");
+        if (c->p2p) {
+            k_xchg_wait<<<1, 32, 0, c->s_main>>>(c->xg, XK_POS);
+            n++;
+        } else if (c->world > 1) {
             NC(g_nccl.AllGather(c->xyzq + (size_t) c->rank * c->range, c->xyzq, (size_t) c->range * 4, ncclFloat64_,
                                 c->comm, c->s_main));
+        }
+        if (c->world > 1) mark("exchange positions");
     } else {
         CU(cudaMemsetAsync(c->lj_hit, 0, sizeof(int), c->s_main));
     }
@@ -410,6 +440,13 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
         else if (store) MESH(false, true);
         else MESH(false, false);
 #undef MESH
+        n++;
+        if (step)
+            k_vertex_mesh<VMODE_STEP><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_side>>>(c->xyzq, c->bslot, vt, fc, c->scal,
+                                                                                       c->fmesh, c->mp);
+        else
+            k_vertex_mesh<VMODE_FORCE><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_side>>>(c->xyzq, c->bslot, vt, fc, c->scal,
+                                                                                        c->fmesh, c->mp);
         n++;
     }
     CU(cudaEventRecord(c->ev_join, c->s_side));
@@ -438,15 +475,17 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
 #undef SYM
             n++;
             if (e1) CU(cudaEventRecord(e1, c->s_main));
-            dim3 rg((c->nv + 127) / 128, c->sym_v_count);
-            k_pair_reduce<<<rg, 128, 0, c->s_main>>>(c->sym_rowpart, c->sym_colpart, c->sym_unit_id, c->sym_fv,
-                                                     c->sym_v_first, c->sp);
+            mark("k_pair_sym");
+            k_pair_reduce<<<(c->nv + 31) / 32, dim3(32, 8), 0, c->s_main>>>(c->sym_rowpart, c->sym_colpart, c->sym_fv,
+                                                                            c->sym_v_first, c->sym_v_count,
+                                                                            c->d_peer_fv, c->range, c->xg, c->sp);
             n++;
-            if (c->world > 1) {
+            if (c->world > 1 && !c->p2p) {
                 const size_t per_rank = (size_t) c->sym_v_count * 3 * c->sp.npad;
                 NC(g_nccl.AllGather(c->sym_fv + (size_t) c->rank * per_rank, c->sym_fv, per_rank, ncclFloat64_, c->comm,
                                     c->s_main));
             }
+            mark(c->world > 1 && !c->p2p ? "k_pair_reduce + all-gather" : "k_pair_reduce");
         }
         if (ordered) {
             switch (c->pair_rows_per_thread) {
@@ -461,24 +500,33 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
     k_lj<<<(c->row_hi - c->row_lo + 127) / 128, 128, 0, c->s_main>>>(c->xyzq, c->lj_out, c->lj_hit,
                                                                       c->all_q_zero ? 1 : 0, c->ljp);
     n++;
+    mark("k_pair (ordered) + k_lj");
     CU(cudaStreamWaitEvent(c->s_main, c->ev_join, 0));
+    if (c->p2p && c->use_sym && !c->all_q_zero) {  // the virtual-rank sums for the owned vertices have arrived
+        k_xchg_wait<<<1, 32, 0, c->s_main>>>(c->xg, XK_FV);
+        n++;
+    }
+    mark("join k_mesh + wait pair sums");
     if (step) {
         k_vertex<VMODE_STEP><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(
-            c->xyzq, c->vel, c->force, c->pair_partial, c->sym_fv, c->lj_out, c->lj_hit, c->bslot, vt, fc, c->part_vert,
-            c->tickets + 1, c->scal, c->ke_warp, c->n_ke_warps, c->th_mid, c->th_cur, c->mp);
+            c->xyzq, c->vel, c->force, c->fmesh, c->pair_partial, c->sym_fv, c->lj_out, c->lj_hit, fc, c->part_vert,
+            c->tickets + 1, c->scal, c->ke_warp, c->n_ke_warps, c->th_mid, c->th_cur, c->d_peer_ke, c->xg, c->mp);
         n++;
     } else {
         k_vertex<VMODE_FORCE><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(
-            c->xyzq, c->vel, c->force, c->pair_partial, c->sym_fv, c->lj_out, c->lj_hit, c->bslot, vt, fc, c->part_vert,
-            c->tickets + 1, c->scal, c->ke_warp, c->n_ke_warps, c->th_mid, c->th_cur, c->mp);
+            c->xyzq, c->vel, c->force, c->fmesh, c->pair_partial, c->sym_fv, c->lj_out, c->lj_hit, fc, c->part_vert,
+            c->tickets + 1, c->scal, c->ke_warp, c->n_ke_warps, c->th_mid, c->th_cur, c->d_peer_ke, c->xg, c->mp);
         n++;
     }
+    mark("k_vertex");
     if (c->world > 1) {
         const size_t per_rank = (size_t) c->range / 32;
-        NC(g_nccl.AllGather(c->ke_warp + (size_t) c->rank * per_rank, c->ke_warp, per_rank, ncclFloat64_, c->comm,
-                            c->s_main));
+        if (!c->p2p)
+            NC(g_nccl.AllGather(c->ke_warp + (size_t) c->rank * per_rank, c->ke_warp, per_rank, ncclFloat64_, c->comm,
+                                c->s_main));
         k_ke_post<<<1, kMeshThreads, 0, c->s_main>>>(c->ke_warp, c->n_ke_warps, c->scal, c->th_mid, c->th_cur,
-                                                     step ? 1 : 0, c->mp);
+                                                     step ? 1 : 0, c->xg, c->mp);
+        mark("exchange KE + k_ke_post");
         n++;
     }
     CU(cudaGetLastError());
@@ -559,6 +607,70 @@ void drop_graph(npsl_ctx *c) {
     }
 }
 
+// Maps every rank's exchange buffers (positions, virtual-rank force sums, kinetic-energy partials, arrival
+// flags) into this process with CUDA IPC. The handles travel through one NCCL all-gather. Any failure leaves
+// the context on the NCCL exchanges.
+int setup_p2p(npsl_ctx *c) {
+    c->xg.world = c->world; c->xg.rank = c->rank; c->xg.on = 0;
+    c->xg.peer_flags = nullptr; c->xg.state = nullptr; c->xg.tickets = nullptr;
+    if (c->world == 1) return 0;
+    const char *env = getenv("NPSL_EXCHANGE");
+    if (env && strcmp(env, "nccl") == 0) return 0;
+    if (c->world > kMaxRanks || !c->sym_fv) return 0;
+    CU(dalloc(&c->xflags, XK_KINDS * kMaxRanks));
+    CU(dalloc(&c->xstate, 2 * XK_KINDS));
+    CU(dalloc(&c->xtickets, XK_KINDS));
+    struct Handles { cudaIpcMemHandle_t h[4]; int ok; int pad[15]; };
+    Handles mine;
+    memset(&mine, 0, sizeof mine);
+    void *bufs[4] = {c->xyzq, c->sym_fv, c->ke_warp, c->xflags};
+    mine.ok = 1;
+    for (int k = 0; k < 4; k++)
+        if (cudaIpcGetMemHandle(&mine.h[k], bufs[k]) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+    Handles *d_all = nullptr;
+    CU(dalloc(&d_all, c->world));
+    CU(cudaMemcpy(d_all + c->rank, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    NC(g_nccl.AllGather(d_all + c->rank, d_all, sizeof(Handles), 1 /* ncclChar */, c->comm, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    std::vector<Handles> all(c->world);
+    CU(cudaMemcpy(all.data(), d_all, sizeof(Handles) * c->world, cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+    bool ok = true;
+    for (int r = 0; r < c->world; r++) ok = ok && all[r].ok;
+    for (int r = 0; r < c->world && ok; r++)
+        for (int k = 0; k < 4; k++) {
+            if (r == c->rank) { c->peer_map[k][r] = bufs[k]; continue; }
+            if (cudaIpcOpenMemHandle(&c->peer_map[k][r], all[r].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                ok = false;
+                cudaGetLastError();
+                c->peer_map[k][r] = nullptr;
+                break;
+            }
+        }
+    // every rank must take the same decision: agree through a second tiny all-gather
+    int *d_ok = nullptr;
+    CU(dalloc(&d_ok, c->world));
+    int my_ok = ok ? 1 : 0;
+    CU(cudaMemcpy(d_ok + c->rank, &my_ok, sizeof(int), cudaMemcpyHostToDevice));
+    NC(g_nccl.AllGather(d_ok + c->rank, d_ok, sizeof(int), 1, c->comm, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    std::vector<int> oks(c->world);
+    CU(cudaMemcpy(oks.data(), d_ok, sizeof(int) * c->world, cudaMemcpyDeviceToHost));
+    cudaFree(d_ok);
+    for (int r = 0; r < c->world; r++) ok = ok && oks[r];
+    if (!ok) return 0;
+    CU(dalloc(&c->d_peer_xyzq, c->world)); CU(dalloc(&c->d_peer_fv, c->world));
+    CU(dalloc(&c->d_peer_ke, c->world)); CU(dalloc(&c->d_peer_flags, c->world));
+    CU(cudaMemcpy(c->d_peer_xyzq, c->peer_map[0], sizeof(void *) * c->world, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_peer_fv, c->peer_map[1], sizeof(void *) * c->world, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_peer_ke, c->peer_map[2], sizeof(void *) * c->world, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_peer_flags, c->peer_map[3], sizeof(void *) * c->world, cudaMemcpyHostToDevice));
+    c->xg.peer_flags = c->d_peer_flags; c->xg.state = c->xstate; c->xg.tickets = c->xtickets;
+    c->p2p = true;
+    c->xg.on = 1;
+    return 0;
+}
+
 int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, int world, const void *nccl_id,
                 npsl_ctx **out) {
     npsl_ctx *c = nullptr;
@@ -611,7 +723,7 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     }
     c->prm = *prm;
     const size_t nrec = (size_t) c->range * world;
-    CUB(dalloc(&c->xyzq, nrec)); CUB(dalloc(&c->vel, nrec)); CUB(dalloc(&c->force, nrec));
+    CUB(dalloc(&c->xyzq, nrec)); CUB(dalloc(&c->vel, nrec)); CUB(dalloc(&c->force, nrec)); CUB(dalloc(&c->fmesh, nrec));
     for (int k = 0; k < 5; k++) CUB(dalloc(&c->comp[k], nrec));
     CUB(dalloc(&c->face_v, c->nf)); CUB(dalloc(&c->edge_rec, c->ne)); CUB(dalloc(&c->l0, c->ne));
     CUB(dalloc(&c->degree, c->nv)); CUB(dalloc(&c->ring, (size_t) kMaxDeg * c->nv));
@@ -670,6 +782,7 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     CUB(cudaMemcpy(c->th_mid, &th, sizeof th, cudaMemcpyHostToDevice));
 
     if (plan_sym(c)) return bail(NPSL_ERR_CUDA);
+    if (!c->sym_fv) CUB(dalloc(&c->sym_fv, (size_t) kSymV * 3 * c->sp.npad));
     CUB(cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->s_side, cudaStreamNonBlocking));
     CUB(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -682,6 +795,10 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
         memcpy(&id, nccl_id, sizeof id);
         int r = g_nccl.CommInitRank(&c->comm, world, id, rank);
         if (r != 0) { fail(c, NPSL_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); return bail(NPSL_ERR_NCCL); }
+    }
+    {
+        int r = setup_p2p(c);
+        if (r) return bail(r);
     }
     *out = c;
     return NPSL_OK;
@@ -722,18 +839,23 @@ void npsl_destroy(npsl_ctx *c) {
     if (c->s_side) cudaStreamSynchronize(c->s_side);
     if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
+    for (int k = 0; k < 4; k++)
+        for (int r = 0; r < kMaxRanks; r++)
+            if (c->peer_map[k][r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_map[k][r]);
     for (cudaEvent_t e : c->t_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->s_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     for (int k = 0; k < 3; k++) {
         if (c->h_pin[k]) cudaFreeHost(c->h_pin[k]);
         if (c->d_pack[k]) cudaFree(c->d_pack[k]);
     }
     if (c->flush_buf) cudaFree(c->flush_buf);
-    void *ptrs[] = {c->xyzq, c->vel, c->force, c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->face_v,
+    void *ptrs[] = {c->xyzq, c->vel, c->force, c->fmesh, c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->face_v,
                     c->edge_rec, c->l0, c->degree, c->ring, c->bslot_ref, c->ring_l0, c->bslot, c->pair_partial,
                     c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_warp, c->th_cur, c->th_mid, c->part_mesh,
                     c->part_vert, c->tickets, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units,
-                    c->sym_unit_id, c->sym_rowpart, c->sym_colpart, c->sym_fv};
+                    c->sym_rowpart, c->sym_colpart, c->sym_fv, c->xflags, c->xstate, c->xtickets,
+                    c->d_peer_xyzq, c->d_peer_fv, c->d_peer_ke, c->d_peer_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -833,6 +955,8 @@ int npsl_set_thermostat(npsl_ctx *c, const npsl_bath_link *mesh_bath, const npsl
         if (ions_bath) th.ions[j] = {ions_bath[j].Q, ions_bath[j].T, ions_bath[j].dof, ions_bath[j].xi, ions_bath[j].eta};
     }
     CU(cudaMemcpyAsync(c->th_cur, &th, sizeof th, cudaMemcpyHostToDevice, c->s_main));
+    k_thermo_prepare<<<1, 32, 0, c->s_main>>>(c->th_cur, c->th_mid, c->scal, c->mp);  // reverse half-chain of the next step
+    c->launches++;
     CU(cudaStreamSynchronize(c->s_main));
     return NPSL_OK;
 }
@@ -1090,6 +1214,40 @@ int npsl_step_timing(npsl_ctx *c, int n_steps, int flush_l2, double *total_ms) {
     return NPSL_OK;
 }
 
+int npsl_step_profile(npsl_ctx *c, int n_steps, char *out, int out_len) {
+    if (!c || !out || out_len < 64) return fail(c, NPSL_ERR_ARG, "bad argument");
+    if (!c->forces_valid) return fail(c, NPSL_ERR_STATE, "npsl_step_profile before npsl_force_init");
+    std::vector<double> sum;
+    std::vector<const char *> names;
+    for (int k = 0; k < n_steps; k++) {
+        c->prof = true;
+        c->prof_used = 0;
+        int n = issue(c, true, false, false, false);
+        c->prof = false;
+        if (n < 0) return n;
+        c->launches += n;
+        CU(cudaStreamSynchronize(c->s_main));
+        if (sum.empty()) { sum.assign(c->prof_used, 0.0); names.assign(c->prof_names.begin(), c->prof_names.begin() + c->prof_used); }
+        for (size_t j = 1; j < c->prof_used && j < sum.size(); j++) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, c->prof_ev[j - 1], c->prof_ev[j]));
+            sum[j] += ms;
+        }
+    }
+    std::string txt;
+    char line[160];
+    double tot = 0;
+    for (size_t j = 1; j < sum.size(); j++) {
+        snprintf(line, sizeof line, "%-34s %9.2f us\n", names[j], 1e3 * sum[j] / n_steps);
+        txt += line;
+        tot += sum[j];
+    }
+    snprintf(line, sizeof line, "%-34s %9.2f us (direct launches, not the graph)\n", "step", 1e3 * tot / n_steps);
+    txt += line;
+    snprintf(out, out_len, "%s", txt.c_str());
+    return NPSL_OK;
+}
+
 int npsl_set_pair_plan(npsl_ctx *c, int rows_per_thread, int col_splits) {
     if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
     if (!(rows_per_thread == 0 || rows_per_thread == 1 || rows_per_thread == 2 || rows_per_thread == 4) || col_splits < 0)
@@ -1129,6 +1287,8 @@ int npsl_set_pair_mode(npsl_ctx *c, int mode) {
 }
 
 int npsl_pair_mode(const npsl_ctx *c) { return c ? (c->use_sym ? 2 : 1) : NPSL_ERR_ARG; }
+
+int npsl_exchange_mode(const npsl_ctx *c) { return c ? (c->world == 1 ? 0 : (c->p2p ? 2 : 1)) : NPSL_ERR_ARG; }
 
 int npsl_owned_rows(const npsl_ctx *c, int32_t *lo, int32_t *hi) {
     if (!c) return NPSL_ERR_ARG;

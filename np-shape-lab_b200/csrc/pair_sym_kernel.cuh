@@ -11,8 +11,8 @@
 // the column accumulators need no atomics and receive their contributions in a fixed order.
 //   row partials    rowpart[c][k][i]   sum over the columns of chunk c        (k = x,y,z)
 //   column partials colpart[I][k][j]   minus the sum over the rows of block I
-// k_pair_reduce then adds, per vertex, the partials of each of 8 "virtual ranks" (unit id mod 8) in a
-// fixed order, and k_vertex adds the 8 results: the value does not depend on which GPU computed which
+// k_pair_reduce then adds, per vertex, the partials of each of 8 "virtual ranks" (a fixed function of the
+// row block) in a fixed order, and k_vertex adds the 8 results: the value does not depend on which GPU computed which
 // unit, so trajectories are bit-identical on 1, 2, 4 and 8 GPUs.
 //
 // FP64-pipe work per unordered pair: 32.75 instructions (20 for r, 1/r, exp; 4 for the geometry factor;
@@ -20,6 +20,7 @@
 // = 16.4 per ordered pair, against 28 in k_pair (tools/sass_count.py).
 #pragma once
 #include "pair_kernel.cuh"
+#include "xchg.cuh"
 
 namespace npsl {
 
@@ -220,35 +221,85 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
     if (min_r2_hi <= P.lj_cut_hi) *lj_hit = 1;  // benign race: every writer stores the same value
 }
 
-// Per vertex x and virtual rank v: the partials of v's units that contain x, in a fixed order (row partials
-// by ascending chunk, then column partials by ascending row block).  grid = (vertex blocks, local virtual
-// ranks); unit_id[I * n_chunks + c] is the unit's index in the global enumeration (-1: no such unit).
-__global__ void __launch_bounds__(128)
-k_pair_reduce(const double *__restrict__ rowpart, const double *__restrict__ colpart, const int *__restrict__ unit_id,
-              double *__restrict__ fv, int v_first, const SymParams P) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = v_first + blockIdx.y;
-    if (x >= P.n) return;
-    const int Ix = x / P.rb, cx = x / (P.chunk_tiles * kSymCT);
-    double fx = 0.0, fy = 0.0, fz = 0.0;
-    for (int c = cx; c < P.n_chunks; c++) {
-        const int id = __ldg(unit_id + Ix * P.n_chunks + c);
-        if (id >= 0 && (id % kSymV) == v) {
+// Virtual rank of a row block: 0..7, 7..0, 0..7, ... so that the triangular work (row block I meets
+// n_chunks - chunk(I) chunks) spreads evenly. All units of a row block belong to its virtual rank.
+__host__ __device__ __forceinline__ int sym_vrank(int I) {
+    const int m = I & 15;
+    return m < 8 ? m : 15 - m;
+}
+
+// Sums the partials per vertex x and virtual rank v in a fixed order:
+//   fv[v][x] = (v == vrank(block of x) ? sum of the row partials of x over its chunks : 0)
+//              + sum over the row blocks I <= block(x) with vrank(I) == v of colpart[I][x]   (ascending I).
+// block = (32 vertices, 8): thread (x, k) adds the column partials of virtual rank k and the row partials of
+// the chunks congruent to k mod 8; the eight row segments are then added in order 0..7.
+// Only the virtual ranks [v_first, v_first + v_count) are computed (the others live on other GPUs).
+__global__ void __launch_bounds__(256)
+k_pair_reduce(const double *__restrict__ rowpart, const double *__restrict__ colpart, double *__restrict__ fv,
+              int v_first, int v_count, double *const *__restrict__ peer_fv, int rows_per_rank, const Xchg X,
+              const SymParams P) {
+    __shared__ double seg[3][8][32];
+    const int tx = threadIdx.x, k = threadIdx.y;
+    const int x = blockIdx.x * 32 + tx;
+    const bool live = x < P.n;
+    const int Ix = live ? x / P.rb : 0;
+    const int vx = sym_vrank(Ix);
+    const bool rows_here = live && vx >= v_first && vx < v_first + v_count;
+    const bool cols_here = live && k >= v_first && k < v_first + v_count;
+    double rx = 0.0, ry = 0.0, rz = 0.0;
+    if (rows_here) {
+        const int cmin = (Ix * P.rb) / (P.chunk_tiles * kSymCT);
+#pragma unroll 4
+        for (int c = cmin + ((k - cmin) & 7); c < P.n_chunks; c += 8) {  // chunks congruent to k mod 8, ascending
             const double *rp = rowpart + (size_t) c * 3 * P.npad + x;
-            fx += __ldcg(rp); fy += __ldcg(rp + P.npad); fz += __ldcg(rp + 2 * (size_t) P.npad);
+            rx += __ldcg(rp); ry += __ldcg(rp + P.npad); rz += __ldcg(rp + 2 * (size_t) P.npad);
         }
     }
-    for (int I = 0; I <= Ix; I++) {
-        const int id = __ldg(unit_id + I * P.n_chunks + cx);
-        if (id >= 0 && (id % kSymV) == v) {
-            const double *cp = colpart + (size_t) I * 3 * P.npad + x;
-            fx += __ldcg(cp); fy += __ldcg(cp + P.npad); fz += __ldcg(cp + 2 * (size_t) P.npad);
+    seg[0][k][tx] = rx; seg[1][k][tx] = ry; seg[2][k][tx] = rz;
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    if (cols_here) {
+#pragma unroll 2
+        for (int b = 0; b <= Ix; b += 16) {  // row blocks of virtual rank k: 16j + k and 16j + 15 - k
+            const int I1 = b + k, I2 = b + 15 - k;
+            if (I1 <= Ix) {
+                const double *cp = colpart + (size_t) I1 * 3 * P.npad + x;
+                fx += __ldcg(cp); fy += __ldcg(cp + P.npad); fz += __ldcg(cp + 2 * (size_t) P.npad);
+            }
+            if (I2 <= Ix) {
+                const double *cp = colpart + (size_t) I2 * 3 * P.npad + x;
+                fx += __ldcg(cp); fy += __ldcg(cp + P.npad); fz += __ldcg(cp + 2 * (size_t) P.npad);
+            }
         }
     }
-    double *o = fv + (size_t) v * 3 * P.npad + x;
-    o[0] = fx;
-    o[P.npad] = fy;
-    o[2 * (size_t) P.npad] = fz;
+    __syncthreads();
+    if (cols_here) {
+        if (k == vx) {
+            double sx = 0.0, sy = 0.0, sz = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { sx += seg[0][j][tx]; sy += seg[1][j][tx]; sz += seg[2][j][tx]; }
+            fx = sx + fx; fy = sy + fy; fz = sz + fz;
+        }
+        // sharded over peer memory: the sum goes to the rank that owns vertex x, nobody else needs it
+        double *o = (X.on ? peer_fv[x / rows_per_rank] : fv) + (size_t) k * 3 * P.npad + x;
+        o[0] = fx;
+        o[P.npad] = fy;
+        o[2 * (size_t) P.npad] = fz;
+    }
+    if (X.on) {  // xchg_signal expects a 1-D block: fold the 2-D index
+        __syncthreads();
+        if (tx == 0 && k == 0) {
+            __threadfence_system();
+            const unsigned int t = atomicAdd(X.tickets + XK_FV, 1u);
+            if (t == gridDim.x - 1) {
+                X.tickets[XK_FV] = 0;
+                __threadfence();
+                const unsigned long long e = X.state[XK_FV] + 1;
+                X.state[XK_FV] = e;
+                __threadfence_system();
+                for (int r = 0; r < X.world; r++) st_release_sys(X.peer_flags[r] + XK_FV * kMaxRanks + X.rank, e);
+            }
+        }
+    }
 }
 
 }  // namespace npsl

@@ -38,7 +38,7 @@ st = ctx.download_state()
 th = ctx.get_thermostat()
 comp = ctx.download_force_components()
 lo, hi = ctx.owned_rows()
-print("rank %d owns rows [%d,%d) plan %s" % (rank, lo, hi, ctx.pair_geometry()), flush=True)
+print("rank %d owns rows [%d,%d) pair mode %d exchange mode %d" % (rank, lo, hi, ctx.pair_mode(), ctx.exchange_mode()), flush=True)
 ctx.close()
 ok = True
 if rank == 0:
