@@ -140,6 +140,9 @@ struct npsl_ctx {
     double *sym_rowpart = nullptr, *sym_colpart = nullptr, *sym_fv = nullptr;
     int sym_n_units = 0, sym_n_units_total = 0, sym_v_first = 0, sym_v_count = kSymV;
     int n_sm = 148;
+    // caller buffers of the host-buffer entry points that were page-locked with cudaHostRegister (so that the
+    // copies go straight from / to the caller's arrays); anything that cannot be registered is staged
+    std::vector<std::pair<void *, size_t>> pinned_user;
     // npsl_step_profile: events recorded between the launches of a step
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -533,6 +536,22 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
     return n;
 }
 
+// true when [p, p+bytes) is page-locked: either registered by an earlier call or registered now
+bool user_pinned(npsl_ctx *c, void *p, size_t bytes) {
+    for (auto &e : c->pinned_user)
+        if (e.first == p && e.second >= bytes) return true;
+    if (c->pinned_user.size() >= 16) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost) return true;  // caller pinned it
+    cudaGetLastError();
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    c->pinned_user.emplace_back(p, bytes);
+    return true;
+}
+
 int ensure_graph(npsl_ctx *c) {
     if (c->step_graph) return 0;
     cudaGraph_t g = nullptr;
@@ -839,6 +858,7 @@ void npsl_destroy(npsl_ctx *c) {
     if (c->s_side) cudaStreamSynchronize(c->s_side);
     if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
+    for (auto &e : c->pinned_user) cudaHostUnregister(e.first);
     for (int k = 0; k < 4; k++)
         for (int r = 0; r < kMaxRanks; r++)
             if (c->peer_map[k][r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_map[k][r]);
@@ -1103,9 +1123,15 @@ int npsl_md_step_host(npsl_ctx *c, double *pos, double *vel, double *force, int 
     double *in[3] = {pos, vel, force};
     double4 *dev[3] = {c->xyzq, c->vel, c->force};
     CU(cudaStreamSynchronize(c->s_main));
+    bool direct[3];
     for (int k = 0; k < 3; k++) {
-        memcpy(c->h_pin[k], in[k], bytes);
-        CU(cudaMemcpyAsync(c->d_pack[k], c->h_pin[k], bytes, cudaMemcpyHostToDevice, c->s_main));
+        direct[k] = user_pinned(c, in[k], bytes);
+        const double *src = in[k];
+        if (!direct[k]) {
+            memcpy(c->h_pin[k], in[k], bytes);
+            src = c->h_pin[k];
+        }
+        CU(cudaMemcpyAsync(c->d_pack[k], src, bytes, cudaMemcpyHostToDevice, c->s_main));
         k_scatter3<<<nb, 256, 0, c->s_main>>>(dev[k], c->d_pack[k], c->nv, k == 0 ? 1 : 0);
     }
     c->launches += 3;
@@ -1118,13 +1144,14 @@ int npsl_md_step_host(npsl_ctx *c, double *pos, double *vel, double *force, int 
             if (r) return r;
         }
         k_gather3<<<nb, 256, 0, c->s_main>>>(dev[k], c->d_pack[k], c->nv);
-        CU(cudaMemcpyAsync(c->h_pin[k], c->d_pack[k], bytes, cudaMemcpyDeviceToHost, c->s_main));
+        CU(cudaMemcpyAsync(direct[k] ? in[k] : c->h_pin[k], c->d_pack[k], bytes, cudaMemcpyDeviceToHost, c->s_main));
     }
     c->launches += 3;
     double ke = 0;
     CU(cudaMemcpyAsync(&ke, c->scal + SC_KE, sizeof(double), cudaMemcpyDeviceToHost, c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
-    for (int k = 0; k < 3; k++) memcpy(in[k], c->h_pin[k], bytes);
+    for (int k = 0; k < 3; k++)
+        if (!direct[k]) memcpy(in[k], c->h_pin[k], bytes);
     if (kinetic_out) *kinetic_out = ke;
     CU(cudaGetLastError());
     return NPSL_OK;
