@@ -180,6 +180,14 @@ int npsl_md_run(npsl_ctx *ctx, const double *pos, const double *vel, const doubl
  * previous call). The thermostat chains stay on the device (npsl_get/set_thermostat). */
 int npsl_md_step_host(npsl_ctx *ctx, double *pos, double *vel, double *force, int n_steps, double *kinetic_out);
 
+/* Rigid volume constraint of md_interface with geomConstraint 'V', linear form (src/functions.h:33-171): SHAKE
+ * after the drift (src/newmd.cpp:126), RATTLE after the second half-kick (:152), both inside npsl_step.
+ * npsl_constraint_init is the SHAKE + RATTLE pass before the first step (src/newmd.cpp:33-38); call it after
+ * npsl_force_init. Single-GPU contexts only. The multipliers of the last pass are available for diagnostics. */
+int npsl_set_volume_constraint(npsl_ctx *ctx, int on);
+int npsl_constraint_init(npsl_ctx *ctx);
+int npsl_constraint_multipliers(npsl_ctx *ctx, double *shake_lambda, double *rattle_mu);
+
 /* ---- introspection (measurement only) --------------------------------------------------- */
 
 /* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */

@@ -26,7 +26,8 @@ SYMBOLS = [
     "npsl_force", "npsl_step", "npsl_energy", "npsl_sync", "npsl_launch_count", "npsl_pair_timing",
     "npsl_pair_timing_read", "npsl_owned_rows", "npsl_pair_geometry", "npsl_fp64_peak", "npsl_md_run",
     "npsl_step_timing", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_md_step_host", "npsl_set_pair_mode",
-    "npsl_pair_mode", "npsl_exchange_mode", "npsl_step_profile",
+    "npsl_pair_mode", "npsl_exchange_mode", "npsl_step_profile", "npsl_set_volume_constraint", "npsl_constraint_init",
+    "npsl_constraint_multipliers",
 ]
 
 
@@ -114,6 +115,9 @@ def load() -> C.CDLL:
     L.npsl_set_pair_mode.argtypes = [vp, C.c_int]
     L.npsl_pair_mode.argtypes = [vp]
     L.npsl_exchange_mode.argtypes = [vp]
+    L.npsl_set_volume_constraint.argtypes = [vp, C.c_int]
+    L.npsl_constraint_init.argtypes = [vp]
+    L.npsl_constraint_multipliers.argtypes = [vp, dp, dp]
     L.npsl_step_profile.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
     if L.npsl_abi_version() != ABI_VERSION:
         raise NpslError(-1, "libnpsl.so ABI version %d, binding expects %d" % (L.npsl_abi_version(), ABI_VERSION))
@@ -351,6 +355,19 @@ class Context:
         buf = C.create_string_buffer(4096)
         self._ck(self.L.npsl_step_profile(self.h, int(n_steps), buf, 4096))
         return buf.value.decode()
+
+    def set_volume_constraint(self, on: bool = True) -> None:
+        """Rigid volume constraint (-G V): SHAKE / RATTLE inside every step."""
+        self._ck(self.L.npsl_set_volume_constraint(self.h, 1 if on else 0))
+
+    def constraint_init(self) -> None:
+        """SHAKE + RATTLE before the first step (src/newmd.cpp:33-38)."""
+        self._ck(self.L.npsl_constraint_init(self.h))
+
+    def constraint_multipliers(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.L.npsl_constraint_multipliers(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def exchange_mode(self) -> int:
         """0 single GPU, 1 NCCL all-gathers, 2 stores into peer memory over NVLink."""

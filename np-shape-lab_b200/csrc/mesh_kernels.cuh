@@ -49,6 +49,8 @@ enum {
     SC_LJ,        // LJ energy of the owned rows
     SC_EXPFAC,    // exp(-dt/2 xi_0) of the current step
     SC_KICK,      // dt/2 sqrt(expfac)
+    SC_LAMBDA,    // SHAKE multiplier of the last step (volume constraint)
+    SC_MU,        // RATTLE multiplier of the last step
     SC_COUNT = 16
 };
 
@@ -62,6 +64,7 @@ struct MeshParams {
     int use_pair;              // 0 when every charge is zero (pair partials are not read)
     int pair_sym;              // 1: pair forces come from the 8 virtual-rank sums of k_pair_reduce
     int npad;                  // plane length of those sums
+    int constraint;            // 1: rigid volume constraint (SHAKE / RATTLE, -G V)
     double dt;
     double pair_coef;  // scalefactor / em
     double bkappa, sconstant, sigma_a, sigma_v, ref_volume, avg_edge;
@@ -349,7 +352,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kMeshThreads)
 k_vertex_mesh(const double4 *__restrict__ xyzq, const double4 *__restrict__ bslot, const VertexTables T,
               const ForceComponents C, const double *__restrict__ scal, double4 *__restrict__ fmesh,
-              const MeshParams P) {
+              double4 *__restrict__ ngv /* VERTEX::neg_GradVi, only with the volume constraint */, const MeshParams P) {
     const int i = P.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.row_hi) return;
     const int nv = P.nv;
@@ -400,12 +403,74 @@ k_vertex_mesh(const double4 *__restrict__ xyzq, const double4 *__restrict__ bslo
     const V3 ft = mk(P.sigma_a * gA.x, P.sigma_a * gA.y, P.sigma_a * gA.z);
     const V3 fv = mk(kv * gV.x, kv * gV.y, kv * gV.z);
     fmesh[i] = make_double4(fb.x + fs.x + ft.x + fv.x, fb.y + fs.y + ft.y + fv.y, fb.z + fs.z + ft.z + fv.z, 0.0);
+    if (P.constraint) ngv[i] = make_double4(gV.x, gV.y, gV.z, 0.0);
     if (MODE == VMODE_FORCE) {
         C.bend[i] = make_double4(fb.x, fb.y, fb.z, 0.0);
         C.stretch[i] = make_double4(fs.x, fs.y, fs.z, 0.0);
         C.tension[i] = make_double4(ft.x, ft.y, ft.z, 0.0);
         C.voltension[i] = make_double4(fv.x, fv.y, fv.z, 0.0);
     }
+}
+
+// Tail shared by k_vertex and k_rattle_apply: per-warp kinetic-energy partials, (FORCE) pair-energy sums,
+// exchange signal, and in the last block the total kinetic energy and the thermostat.
+template <bool ENERGIES, bool STEP>
+__device__ __forceinline__ void vertex_tail(double (&acc)[3], double *__restrict__ partials, unsigned int *__restrict__ ticket,
+                                            double *__restrict__ scal, double *__restrict__ ke_warp, int n_ke_warps,
+                                            Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur,
+                                            double *const *__restrict__ peer_ke, const Xchg &X, const MeshParams &P,
+                                            double *red /* [3*32] */, bool *s_last_p) {
+    bool &s_last = *s_last_p;
+    const int nblocks = gridDim.x;
+    // kinetic energy: one partial per warp at its global warp index (see canonical_sum)
+    {
+        double ke = acc[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ke += __shfl_down_sync(0xffffffffu, ke, o);
+        const int i0 = P.row_lo + blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+        if ((threadIdx.x & 31) == 0 && i0 < P.row_hi) {
+            if (X.on) {
+                for (int r = 0; r < X.world; r++) peer_ke[r][i0 >> 5] = ke;
+            } else {
+                ke_warp[i0 >> 5] = ke;
+            }
+        }
+    }
+    if (ENERGIES) {  // pair energies of the owned rows (summed over ranks by the host, rank order)
+        double e2[2] = {acc[1], acc[2]};
+        block_sum<2>(e2, red);
+        if (threadIdx.x == 0) {
+            partials[blockIdx.x] = e2[0];
+            partials[nblocks + blockIdx.x] = e2[1];
+        }
+    }
+    if (X.on) xchg_signal(X, XK_KE, nblocks);
+    __syncthreads();  // every warp's ke_warp store precedes thread 0's fence + ticket
+    if (threadIdx.x == 0) s_last = take_last_ticket(ticket, nblocks);
+    __syncthreads();
+    if (!s_last) return;
+    if (ENERGIES) {
+        double tot[2] = {0, 0};
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+            tot[0] += __ldcg(partials + b);
+            tot[1] += __ldcg(partials + nblocks + b);
+        }
+        __syncthreads();
+        block_sum<2>(tot, red);
+        if (threadIdx.x == 0) {
+            scal[SC_ES] = tot[0];
+            scal[SC_LJ] = tot[1];
+        }
+        __syncthreads();
+    }
+    if (P.n_ranks > 1) return;  // sharded: k_ke_post finishes after the exchange of ke_warp
+    const double ke = canonical_sum(ke_warp, n_ke_warps, red);
+    if (threadIdx.x == 0) {
+        scal[SC_KE] = ke;
+        red[0] = ke;
+    }
+    __syncthreads();
+    thermo_finish(th_mid, th_cur, scal, red[0], STEP, P);
 }
 
 template <int MODE>
@@ -468,56 +533,9 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
         }
         acc[0] = 0.5 * (v.x * v.x + v.y * v.y + v.z * v.z);
     }
-    // kinetic energy: one partial per warp at its global warp index (see canonical_sum)
-    {
-        double ke = acc[0];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ke += __shfl_down_sync(0xffffffffu, ke, o);
-        const int i0 = P.row_lo + blockIdx.x * blockDim.x + (threadIdx.x & ~31);
-        if ((threadIdx.x & 31) == 0 && i0 < P.row_hi) {
-            if (X.on) {
-                for (int r = 0; r < X.world; r++) peer_ke[r][i0 >> 5] = ke;
-            } else {
-                ke_warp[i0 >> 5] = ke;
-            }
-        }
-    }
-    if (MODE == VMODE_FORCE) {  // pair energies of the owned rows (summed over ranks by the host, rank order)
-        double e2[2] = {acc[1], acc[2]};
-        block_sum<2>(e2, red);
-        if (threadIdx.x == 0) {
-            partials[blockIdx.x] = e2[0];
-            partials[nblocks + blockIdx.x] = e2[1];
-        }
-    }
-    if (X.on) xchg_signal(X, XK_KE, nblocks);
-    __syncthreads();  // every warp's ke_warp store precedes thread 0's fence + ticket
-    if (threadIdx.x == 0) s_last = take_last_ticket(ticket, nblocks);
-    __syncthreads();
-    if (!s_last) return;
-    if (MODE == VMODE_FORCE) {
-        double tot[2] = {0, 0};
-        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
-            tot[0] += __ldcg(partials + b);
-            tot[1] += __ldcg(partials + nblocks + b);
-        }
-        __syncthreads();
-        block_sum<2>(tot, red);
-        if (threadIdx.x == 0) {
-            scal[SC_ES] = tot[0];
-            scal[SC_LJ] = tot[1];
-        }
-        __syncthreads();
-    }
-    if (P.n_ranks > 1) return;  // sharded: k_ke_post finishes after the exchange of ke_warp
-    __shared__ double s_ke;
-    const double ke = canonical_sum(ke_warp, n_ke_warps, red);
-    if (threadIdx.x == 0) {
-        scal[SC_KE] = ke;
-        s_ke = ke;
-    }
-    __syncthreads();
-    thermo_finish(th_mid, th_cur, scal, s_ke, MODE == VMODE_STEP, P);
+    if (MODE == VMODE_STEP && P.constraint) return;  // RATTLE follows: k_rattle_apply finishes the step
+    vertex_tail<MODE == VMODE_FORCE, MODE == VMODE_STEP>(acc, partials, ticket, scal, ke_warp, n_ke_warps, th_mid, th_cur,
+                                                         peer_ke, X, P, red, &s_last);
 }
 
 // Sharded runs: after the all-gather of every rank's warp partials, one block sums them in the
@@ -538,6 +556,142 @@ k_ke_post(const double *__restrict__ ke_warp, int n_ke_warps, double *__restrict
     }
     __syncthreads();
     thermo_finish(th_mid, th_cur, scal, s_ke, step != 0, P);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rigid volume constraint (-G V, linear form): SHAKE after the drift, RATTLE after the second half-kick
+// (src/functions.h:33-171, called from src/newmd.cpp:33-38,126,152). g_i = VERTEX::neg_GradVi of the most
+// recent force evaluation (k_vertex_mesh leaves it in ngv); masses are 1 as in the reference.
+//
+// Smallest real root of x^3 + a x^2 + b x + c = 0 the way GSL's gsl_poly_solve_cubic reports it in x0
+// (trigonometric / Cardano solution, Numerical Recipes 5.6; three real roots are sorted ascending).
+__device__ __forceinline__ double cubic_x0(const double a, const double b, const double c) {
+    const double q = a * a - 3 * b;
+    const double r = 2 * a * a * a - 9 * a * b + 27 * c;
+    const double Q = q / 9, R = r / 54;
+    const double Q3 = Q * Q * Q, R2 = R * R;
+    const double CR2 = 729 * r * r, CQ3 = 2916 * q * q * q;
+    if (R == 0 && Q == 0) return -a / 3;
+    if (CR2 == CQ3) {
+        const double sqrtQ = sqrt(Q);
+        return (R > 0 ? -2 * sqrtQ : -sqrtQ) - a / 3;
+    }
+    if (R2 < Q3) {
+        const double sgnR = R >= 0 ? 1 : -1;
+        const double theta = acos(sgnR * sqrt(R2 / Q3));
+        const double norm = -2 * sqrt(Q);
+        const double pi = 3.14159265358979323846;
+        const double r0 = norm * cos(theta / 3) - a / 3;
+        const double r1 = norm * cos((theta + 2.0 * pi) / 3) - a / 3;
+        const double r2 = norm * cos((theta - 2.0 * pi) / 3) - a / 3;
+        return fmin(r0, fmin(r1, r2));
+    }
+    const double sgnR = R >= 0 ? 1 : -1;
+    const double A = -sgnR * pow(fabs(R) + sqrt(R2 - Q3), 1.0 / 3.0);
+    return A + Q / A - a / 3;
+}
+
+__device__ __forceinline__ double triple(V3 a, V3 b, V3 c) { return dot(a, cross(b, c)); }
+
+// Face sums of SHAKE (which == 0; 8 triple products, then the cubic for the multiplier) or RATTLE
+// (which == 1; d/dt of the volume and its derivative along g). One thread per face, ordered reduction,
+// the last block leaves the multiplier in scal[SC_LAMBDA] / scal[SC_MU].
+template <int WHICH>
+__global__ void __launch_bounds__(kMeshThreads)
+k_constraint_sums(const double4 *__restrict__ xyzq, const double4 *__restrict__ vel, const double4 *__restrict__ ngv,
+                  const int4 *__restrict__ face_v, double *__restrict__ partials /* [8][nblocks] */,
+                  unsigned int *__restrict__ ticket, double *__restrict__ scal, const MeshParams P) {
+    __shared__ double red[8 * 32];
+    __shared__ bool s_last;
+    const int nblocks = gridDim.x;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (f < P.nf) {
+        const int4 fv = __ldg(face_v + f);
+        const V3 p0 = ld3(xyzq, fv.x), p1 = ld3(xyzq, fv.y), p2 = ld3(xyzq, fv.z);
+        const double4 a0 = ldcg4(ngv + fv.x), a1 = ldcg4(ngv + fv.y), a2 = ldcg4(ngv + fv.z);
+        const V3 g0 = mk(a0.x, a0.y, a0.z), g1 = mk(a1.x, a1.y, a1.z), g2 = mk(a2.x, a2.y, a2.z);
+        if (WHICH == 0) {
+            acc[0] = triple(g0, g1, g2);
+            acc[1] = triple(g0, p1, g2);
+            acc[2] = triple(g0, g1, p2);
+            acc[3] = triple(p0, g1, g2);
+            acc[4] = triple(g0, p1, p2);
+            acc[5] = triple(p0, p1, g2);
+            acc[6] = triple(p0, g1, p2);
+            acc[7] = triple(p0, p1, p2);
+        } else {
+            const double4 b0 = ldcg4(vel + fv.x), b1 = ldcg4(vel + fv.y), b2 = ldcg4(vel + fv.z);
+            const V3 v0 = mk(b0.x, b0.y, b0.z), v1 = mk(b1.x, b1.y, b1.z), v2 = mk(b2.x, b2.y, b2.z);
+            acc[0] = triple(v0, p1, p2) + triple(p0, p1, v2) + triple(p0, v1, p2);
+            acc[1] = triple(g0, p1, p2) + triple(p0, p1, g2) + triple(p0, g1, p2);
+        }
+    }
+    block_sum<8>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) partials[k * nblocks + blockIdx.x] = acc[k];
+        s_last = take_last_ticket(ticket, nblocks);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) tot[k] += __ldcg(partials + k * nblocks + b);
+    }
+    __syncthreads();
+    block_sum<8>(tot, red);
+    if (threadIdx.x == 0) {
+        if (WHICH == 0) {
+            const double f0 = tot[0], idt = 1.0 / P.dt;
+            const double a = idt * (tot[1] + tot[2] + tot[3]) / f0;
+            const double b = idt * idt * (tot[4] + tot[5] + tot[6]) / f0;
+            const double c = idt * idt * idt * (tot[7] - 6 * P.ref_volume) / f0;
+            scal[SC_LAMBDA] = (c == 0 || f0 == 0) ? 0.0 : cubic_x0(a, b, c);  // already satisfied: bypass
+        } else {
+            scal[SC_MU] = (tot[0] == 0 || tot[1] == 0) ? 0.0 : -(tot[0] / tot[1]);
+        }
+    }
+}
+
+// SHAKE update: v += lambda g, x += lambda dt g.
+__global__ void __launch_bounds__(kMeshThreads)
+k_shake_apply(double4 *__restrict__ xyzq, double4 *__restrict__ vel, const double4 *__restrict__ ngv,
+              const double *__restrict__ scal, const MeshParams P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nv) return;
+    const double lam = __ldcg(scal + SC_LAMBDA);
+    if (lam == 0.0) return;
+    const double4 g = ngv[i];
+    double4 v = vel[i], x = xyzq[i];
+    v.x = v.x + lam * g.x; v.y = v.y + lam * g.y; v.z = v.z + lam * g.z;
+    const double ld = lam * P.dt;
+    x.x = x.x + ld * g.x; x.y = x.y + ld * g.y; x.z = x.z + ld * g.z;
+    vel[i] = v;
+    xyzq[i] = x;
+}
+
+// RATTLE update v += mu g, then what k_vertex does after the second half-kick: kinetic energy and thermostat
+// (INIT: the constraint pass before the first step, src/newmd.cpp:33-38 -- no forward half-chain).
+template <bool INIT>
+__global__ void __launch_bounds__(kMeshThreads)
+k_rattle_apply(double4 *__restrict__ vel, const double4 *__restrict__ ngv, double *__restrict__ partials,
+               unsigned int *__restrict__ ticket, double *__restrict__ scal, double *__restrict__ ke_warp, int n_ke_warps,
+               Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur, const Xchg X, const MeshParams P) {
+    __shared__ double red[3 * 32];
+    __shared__ bool s_last;
+    const int i = P.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[3] = {0, 0, 0};
+    if (i < P.row_hi) {
+        const double mu = __ldcg(scal + SC_MU);
+        const double4 g = ngv[i];
+        double4 v = vel[i];
+        v.x = v.x + mu * g.x; v.y = v.y + mu * g.y; v.z = v.z + mu * g.z;
+        vel[i] = v;
+        acc[0] = 0.5 * (v.x * v.x + v.y * v.y + v.z * v.z);
+    }
+    vertex_tail<false, !INIT>(acc, partials, ticket, scal, ke_warp, n_ke_warps, th_mid, th_cur, nullptr, X, P, red, &s_last);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -83,7 +83,8 @@ struct npsl_ctx {
     bool forces_valid = false;
 
     // state, one 32-byte record per vertex (coalesced 16-byte accesses everywhere)
-    double4 *xyzq = nullptr, *vel = nullptr, *force = nullptr, *fmesh = nullptr;
+    double4 *xyzq = nullptr, *vel = nullptr, *force = nullptr, *fmesh = nullptr, *ngv = nullptr;
+    double *part_con = nullptr;  // [8][face blocks] partials of the SHAKE / RATTLE face sums
     double4 *comp[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // pair, bend, stretch, tension, voltension
     // topology
     int4 *face_v = nullptr, *edge_rec = nullptr;
@@ -425,6 +426,14 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
                                 c->comm, c->s_main));
         }
         if (c->world > 1) mark("exchange positions");
+        if (c->mp.constraint) {  // SHAKE, src/newmd.cpp:126
+            k_constraint_sums<0><<<c->n_face_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv, c->face_v,
+                                                                                  c->part_con, c->tickets + 2, c->scal, c->mp);
+            k_shake_apply<<<(c->nv + kMeshThreads - 1) / kMeshThreads, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv,
+                                                                                                   c->scal, c->mp);
+            n += 2;
+            mark("SHAKE");
+        }
     } else {
         CU(cudaMemsetAsync(c->lj_hit, 0, sizeof(int), c->s_main));
     }
@@ -446,10 +455,10 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
         n++;
         if (step)
             k_vertex_mesh<VMODE_STEP><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_side>>>(c->xyzq, c->bslot, vt, fc, c->scal,
-                                                                                       c->fmesh, c->mp);
+                                                                                       c->fmesh, c->ngv, c->mp);
         else
             k_vertex_mesh<VMODE_FORCE><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_side>>>(c->xyzq, c->bslot, vt, fc, c->scal,
-                                                                                        c->fmesh, c->mp);
+                                                                                        c->fmesh, c->ngv, c->mp);
         n++;
     }
     CU(cudaEventRecord(c->ev_join, c->s_side));
@@ -522,6 +531,15 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
         n++;
     }
     mark("k_vertex");
+    if (step && c->mp.constraint) {  // RATTLE, src/newmd.cpp:152, then the kinetic energy and the thermostat
+        k_constraint_sums<1><<<c->n_face_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv, c->face_v,
+                                                                              c->part_con, c->tickets + 2, c->scal, c->mp);
+        k_rattle_apply<false><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(c->vel, c->ngv, c->part_vert, c->tickets + 1,
+                                                                                  c->scal, c->ke_warp, c->n_ke_warps,
+                                                                                  c->th_mid, c->th_cur, c->xg, c->mp);
+        n += 2;
+        mark("RATTLE");
+    }
     if (c->world > 1) {
         const size_t per_rank = (size_t) c->range / 32;
         if (!c->p2p)
@@ -742,7 +760,7 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     }
     c->prm = *prm;
     const size_t nrec = (size_t) c->range * world;
-    CUB(dalloc(&c->xyzq, nrec)); CUB(dalloc(&c->vel, nrec)); CUB(dalloc(&c->force, nrec)); CUB(dalloc(&c->fmesh, nrec));
+    CUB(dalloc(&c->xyzq, nrec)); CUB(dalloc(&c->vel, nrec)); CUB(dalloc(&c->force, nrec)); CUB(dalloc(&c->fmesh, nrec)); CUB(dalloc(&c->ngv, nrec));
     for (int k = 0; k < 5; k++) CUB(dalloc(&c->comp[k], nrec));
     CUB(dalloc(&c->face_v, c->nf)); CUB(dalloc(&c->edge_rec, c->ne)); CUB(dalloc(&c->l0, c->ne));
     CUB(dalloc(&c->degree, c->nv)); CUB(dalloc(&c->ring, (size_t) kMaxDeg * c->nv));
@@ -776,6 +794,7 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     c->n_vertex_blocks = (c->row_hi - c->row_lo + kMeshThreads - 1) / kMeshThreads;
     CUB(dalloc(&c->part_mesh, (size_t) 4 * (c->n_face_blocks + c->n_edge_blocks)));
     CUB(dalloc(&c->part_vert, (size_t) 3 * c->n_vertex_blocks));
+    CUB(dalloc(&c->part_con, (size_t) 8 * c->n_face_blocks));
 
     const double lam = prm->inv_kappa_out;
     c->pp.c2s = -1.4426950408889634074 / lam * (double) kExpTab;
@@ -790,6 +809,7 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     mp.nv = c->nv; mp.ne = c->ne; mp.nf = c->nf; mp.row_lo = c->row_lo; mp.row_hi = c->row_hi;
     mp.n_ranks = world; mp.chain = prm->chain; mp.buckling = prm->buckling ? 1 : 0;
     mp.use_pair = 0;
+    mp.constraint = 0;
     apply_pair_plan(c);
     mp.dt = prm->dt; mp.pair_coef = prm->scalefactor / prm->em;
     mp.bkappa = prm->bkappa; mp.sconstant = prm->sconstant; mp.sigma_a = prm->sigma_a; mp.sigma_v = prm->sigma_v;
@@ -870,7 +890,7 @@ void npsl_destroy(npsl_ctx *c) {
         if (c->d_pack[k]) cudaFree(c->d_pack[k]);
     }
     if (c->flush_buf) cudaFree(c->flush_buf);
-    void *ptrs[] = {c->xyzq, c->vel, c->force, c->fmesh, c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->face_v,
+    void *ptrs[] = {c->xyzq, c->vel, c->force, c->fmesh, c->ngv, c->part_con, c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->face_v,
                     c->edge_rec, c->l0, c->degree, c->ring, c->bslot_ref, c->ring_l0, c->bslot, c->pair_partial,
                     c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_warp, c->th_cur, c->th_mid, c->part_mesh,
                     c->part_vert, c->tickets, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units,
@@ -1297,6 +1317,44 @@ int npsl_set_pair_plan(npsl_ctx *c, int rows_per_thread, int col_splits) {
     apply_pair_plan(c);
     drop_graph(c);
     c->forces_valid = false;
+    return NPSL_OK;
+}
+
+int npsl_set_volume_constraint(npsl_ctx *c, int on) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    if (on && c->world > 1) return fail(c, NPSL_ERR_ARG, "the rigid volume constraint is not available on sharded contexts");
+    CU(cudaStreamSynchronize(c->s_main));
+    c->mp.constraint = on ? 1 : 0;
+    drop_graph(c);
+    c->forces_valid = false;  // neg_GradVi has to be (re)computed by a force evaluation
+    return NPSL_OK;
+}
+
+int npsl_constraint_init(npsl_ctx *c) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    if (!c->mp.constraint) return fail(c, NPSL_ERR_STATE, "npsl_constraint_init without npsl_set_volume_constraint");
+    if (!c->forces_valid) return fail(c, NPSL_ERR_STATE, "npsl_constraint_init before npsl_force_init");
+    k_constraint_sums<0><<<c->n_face_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv, c->face_v, c->part_con,
+                                                                          c->tickets + 2, c->scal, c->mp);
+    k_shake_apply<<<(c->nv + kMeshThreads - 1) / kMeshThreads, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv, c->scal,
+                                                                                           c->mp);
+    k_constraint_sums<1><<<c->n_face_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv, c->face_v, c->part_con,
+                                                                          c->tickets + 2, c->scal, c->mp);
+    k_rattle_apply<true><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(c->vel, c->ngv, c->part_vert, c->tickets + 1,
+                                                                             c->scal, c->ke_warp, c->n_ke_warps, c->th_mid,
+                                                                             c->th_cur, c->xg, c->mp);
+    c->launches += 4;
+    CU(cudaGetLastError());
+    return NPSL_OK;
+}
+
+int npsl_constraint_multipliers(npsl_ctx *c, double *shake_lambda, double *rattle_mu) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    double v[2];
+    CU(cudaMemcpyAsync(v, c->scal + SC_LAMBDA, sizeof v, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    if (shake_lambda) *shake_lambda = v[0];
+    if (rattle_mu) *rattle_mu = v[1];
     return NPSL_OK;
 }
 

@@ -252,13 +252,17 @@ def md_interface(boundary: INTERFACE, counterions: list, mesh_bath: List[THERMOS
     annealing. Series files are written to ``outdir`` in the reference's formats."""
     if counterions:
         raise NotImplementedError("explicit counterions are a 'next' row (SURVEY 8f rank 1)")
-    if geomConstraint != "N":
-        raise NotImplementedError("SHAKE/RATTLE constraints are a 'next' row (SURVEY 8f rank 2)")
+    if geomConstraint not in ("N", "V") or (geomConstraint == "V" and constraintForm != "L"):
+        raise NotImplementedError("only the rigid volume constraint in its linear form (-G V) is on the device path")
     boundary.dt = mdremote.timestep
     boundary.velvec = np.zeros_like(boundary.posvec)  # initialize_velocities_to_zero, src/newmd.cpp:16
     boundary._ctx = None
     ctx = boundary.context(scalefactor, bucklingFlag, mesh_bath, ions_bath)
+    if geomConstraint == "V":
+        ctx.set_volume_constraint(True)
     ctx.force_init()  # src/newmd.cpp:19
+    if geomConstraint == "V":
+        ctx.constraint_init()  # SHAKE + RATTLE prior to MD, src/newmd.cpp:33-38
     n3 = 3.0 * boundary.number_of_vertices
 
     def write_row(num: int) -> dict:

@@ -329,15 +329,20 @@ void initialize_velocities_to_zero(vector<VERTEX> &V, vector<PARTICLE> &ions) {
 // when the reference writes (num < 3 or num % writedata == 0), anneals, or at the end.
 void md_interface(INTERFACE &boundary, vector<PARTICLE> &counterions, vector<THERMOSTAT> &mesh_bath,
                   vector<THERMOSTAT> &ions_bath, CONTROL &mdremote, char geomConstraint, char bucklingFlag,
-                  char /*constraintForm*/, const double scalefactor, double /*box_radius*/) {
+                  char constraintForm, const double scalefactor, double /*box_radius*/) {
     require_no_ions(counterions);
-    if (geomConstraint != 'N') throw npsl_error(NPSL_ERR_ARG, "SHAKE/RATTLE constraints are not on the device path yet");
+    if (geomConstraint == 'V' && constraintForm == 'Q')
+        throw npsl_error(NPSL_ERR_ARG, "the quadratic constraint form is not on the device path");
+    if (geomConstraint != 'N' && geomConstraint != 'V')
+        throw npsl_error(NPSL_ERR_ARG, "only the rigid volume constraint (-G V, linear form) is on the device path");
     if (mesh_bath.size() != ions_bath.size() || mesh_bath.empty() || mesh_bath.size() > NPSL_MAX_CHAIN)
         throw npsl_error(NPSL_ERR_ARG, "thermostat chains must have equal length in [1, NPSL_MAX_CHAIN]");
     initialize_velocities_to_zero(boundary.V, counterions);
     boundary.drop_context();
     npsl_ctx *c = boundary.context(scalefactor, bucklingFlag, &mesh_bath, &ions_bath, mdremote.timestep);
+    if (geomConstraint == 'V') check(c, npsl_set_volume_constraint(c, 1), "npsl_set_volume_constraint");
     check(c, npsl_force_init(c), "npsl_force_init");
+    if (geomConstraint == 'V') check(c, npsl_constraint_init(c), "npsl_constraint_init");  // src/newmd.cpp:33-38
     npsl_bath_link mb[NPSL_MAX_CHAIN], ib[NPSL_MAX_CHAIN];
     const string &dir = boundary.outdir;
 

@@ -48,6 +48,9 @@ CONFIGS = {
     "janus_D8": ("ref:3_8", 8, JANUS, [0, 1], [250, 500, 750, 1000]),
     "buckling_D8": ("ref:3_8", 8, BUCKLING_CTRL, [0, 1], [500, 1000]),
     "disc_ico6": ("ico:6", 6, DISC, [0, 1], []),  # synthetic class-I icosphere, 362 vertices
+    # rigid volume constraint (SHAKE / RATTLE, src/functions.h:33-171); the cubic comes from oracle/shim/gsl/gsl_poly.h
+    "disc_D4_GV": ("ref:3_4", 4, DISC + ["-G", "V"], [0, 1, 2], [250, 500, 1000]),
+    "janus_D8_GV": ("ref:3_8", 8, JANUS + ["-G", "V"], [0, 1], [500, 1000]),
 }
 
 FULL_KEYS = ["pos", "vel", "force", "bforce", "sforce", "tforce", "vforce", "pforce", "itsS", "face_area",

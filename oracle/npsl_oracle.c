@@ -11,6 +11,7 @@
  * (src/vector3d.h:23), most scalars are truncated to double where the reference does so.
  * All citations are file:line in /root/reference.
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -57,6 +58,7 @@ typedef struct {
     ld vertex_ke;
     int chain;
     bath_t mesh_bath[16], ions_bath[16];
+    int constraint; /* 1: rigid volume constraint, geomConstraint 'V', linear form */
 } npo_t;
 
 /* ---------------------------------------------------------------- construction */
@@ -454,7 +456,75 @@ void npo_refresh_ke(void *hh) {
     h->vertex_ke = kinetic_energy(h);
 }
 
-/* One iteration of the loop of md_interface, src/newmd.cpp:96-170 (no constraints, no ions) */
+/* gsl_poly_solve_cubic as the reference calls it (src/functions.h:102): GSL is a third-party dependency that is
+ * not vendored in the reference tree (README.md:21 asks for GSL >= 2.x, unpinned); this restates the algorithm
+ * its manual documents (Cardano / trigonometric solution, Numerical Recipes 5.6). x0 = smallest real root. */
+static double cubic_x0(double a, double b, double c) {
+    double q = a * a - 3 * b, r = 2 * a * a * a - 9 * a * b + 27 * c;
+    double Q = q / 9, R = r / 54, Q3 = Q * Q * Q, R2 = R * R;
+    double CR2 = 729 * r * r, CQ3 = 2916 * q * q * q;
+    if (R == 0 && Q == 0) return -a / 3;
+    if (CR2 == CQ3) { double sq = sqrt(Q); return (R > 0 ? -2 * sq : -sq) - a / 3; }
+    if (R2 < Q3) {
+        double sgnR = R >= 0 ? 1 : -1, theta = acos(sgnR * sqrt(R2 / Q3)), norm = -2 * sqrt(Q);
+        double r0 = norm * cos(theta / 3) - a / 3, r1 = norm * cos((theta + 2.0 * M_PI) / 3) - a / 3,
+               r2 = norm * cos((theta - 2.0 * M_PI) / 3) - a / 3;
+        return fmin(r0, fmin(r1, r2));
+    }
+    double sgnR = R >= 0 ? 1 : -1, A = -sgnR * pow(fabs(R) + sqrt(R2 - Q3), 1.0 / 3.0);
+    return A + Q / A - a / 3;
+}
+
+static ld triple(vec3 a, vec3 b, vec3 c) { return vdot(a, vcross(b, c)); }
+
+/* SHAKE, src/functions.h:33-117 (linear form: neg_GradConi = neg_GradVi of the last force evaluation) */
+static void shake(npo_t *h) {
+    double f0 = 0, fa1 = 0, fa2 = 0, fa3 = 0, fb1 = 0, fb2 = 0, fb3 = 0, fc = 0;
+    for (int f = 0; f < h->nf; f++) {
+        const int *fv = h->face_v + 3 * f;
+        vec3 p0 = h->pos[fv[0]], p1 = h->pos[fv[1]], p2 = h->pos[fv[2]];
+        vec3 g0 = h->negGradV[fv[0]], g1 = h->negGradV[fv[1]], g2 = h->negGradV[fv[2]];
+        f0 = f0 + triple(g0, g1, g2);
+        fa1 = fa1 + triple(g0, p1, g2); fa2 = fa2 + triple(g0, g1, p2); fa3 = fa3 + triple(p0, g1, g2);
+        fb1 = fb1 + triple(g0, p1, p2); fb2 = fb2 + triple(p0, p1, g2); fb3 = fb3 + triple(p0, g1, p2);
+        fc = fc + triple(p0, p1, p2);
+    }
+    double idt = 1.0 / h->dt;
+    double a = idt * (fa1 + fa2 + fa3) / f0, b = idt * idt * (fb1 + fb2 + fb3) / f0;
+    double c = idt * idt * idt * (fc - 6 * h->ref_volume) / f0;
+    if (c == 0 || f0 == 0) return;
+    double x0 = cubic_x0(a, b, c);
+    for (int v = 0; v < h->nv; v++) h->vel[v] = vadd(h->vel[v], vscale(h->negGradV[v], x0));
+    for (int v = 0; v < h->nv; v++) h->pos[v] = vadd(h->pos[v], vscale(h->negGradV[v], x0 * h->dt));
+}
+
+/* RATTLE, src/functions.h:120-171 */
+static void rattle(npo_t *h) {
+    double num = 0, den = 0;
+    for (int f = 0; f < h->nf; f++) {
+        const int *fv = h->face_v + 3 * f;
+        vec3 p0 = h->pos[fv[0]], p1 = h->pos[fv[1]], p2 = h->pos[fv[2]];
+        vec3 v0 = h->vel[fv[0]], v1 = h->vel[fv[1]], v2 = h->vel[fv[2]];
+        vec3 g0 = h->negGradV[fv[0]], g1 = h->negGradV[fv[1]], g2 = h->negGradV[fv[2]];
+        num = num + triple(v0, p1, p2) + triple(p0, p1, v2) + triple(p0, v1, p2);
+        den = den + triple(g0, p1, p2) + triple(p0, p1, g2) + triple(p0, g1, p2);
+    }
+    if (num == 0 || den == 0) return;
+    double mu = -(num / den);
+    for (int v = 0; v < h->nv; v++) h->vel[v] = vadd(h->vel[v], vscale(h->negGradV[v], mu));
+}
+
+void npo_set_constraint(void *hh, int on) { ((npo_t *) hh)->constraint = on; }
+
+/* SHAKE + RATTLE prior to MD, src/newmd.cpp:33-38; call after npo_md_init */
+void npo_constraint_init(void *hh) {
+    npo_t *h = (npo_t *) hh;
+    shake(h);
+    rattle(h);
+    h->vertex_ke = kinetic_energy(h);
+}
+
+/* One iteration of the loop of md_interface, src/newmd.cpp:96-170 (no ions; volume constraint optional) */
 void npo_md_step(void *hh) {
     npo_t *h = (npo_t *) hh;
     const double dt = h->dt;
@@ -469,9 +539,11 @@ void npo_md_step(void *hh) {
     ld kick = 0.5 * dt * sqrtl(ef); /* VERTEX::update_real_velocity, src/vertex.h:105-108 */
     for (int v = 0; v < h->nv; v++) h->vel[v] = vadd(vscale(h->vel[v], ef), vscale(h->forvec[v], kick));
     for (int v = 0; v < h->nv; v++) h->pos[v] = vadd(h->pos[v], vscale(h->vel[v], dt));
+    if (h->constraint) shake(h); /* src/newmd.cpp:126 */
     npo_dressup(h);
     npo_force(h, 0, h->nv - 1);
     for (int v = 0; v < h->nv; v++) h->vel[v] = vadd(vscale(h->vel[v], ef), vscale(h->forvec[v], kick));
+    if (h->constraint) rattle(h); /* src/newmd.cpp:152 */
     h->vertex_ke = kinetic_energy(h);
     for (int j = 0; j < C; j++) update_eta(&h->mesh_bath[j], dt);
     for (int j = 0; j < C; j++) update_eta(&h->ions_bath[j], dt);

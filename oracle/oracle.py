@@ -39,6 +39,8 @@ def lib():
         L.npo_force.argtypes = [vp, C.c_int, C.c_int]
         L.npo_energy.argtypes = [vp, C.c_int, C.c_int, dp]
         L.npo_md_init.argtypes = [vp]
+        L.npo_set_constraint.argtypes = [vp, C.c_int]
+        L.npo_constraint_init.argtypes = [vp]
         L.npo_refresh_ke.argtypes = [vp]
         L.npo_md_step.argtypes = [vp]
         L.npo_md_steps.argtypes = [vp, C.c_int]
@@ -114,6 +116,13 @@ class Oracle:
 
     def md_init(self):
         self.L.npo_md_init(self.h)
+
+    def set_constraint(self, on: bool = True):
+        """Rigid volume constraint (-G V, linear form): SHAKE / RATTLE inside md_steps."""
+        self.L.npo_set_constraint(self.h, 1 if on else 0)
+
+    def constraint_init(self):
+        self.L.npo_constraint_init(self.h)
 
     def refresh_ke(self):
         self.L.npo_refresh_ke(self.h)

@@ -11,6 +11,7 @@ if ROOT not in sys.path:
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 GOLDEN_NAMES = ["disc_D4", "rod_D4", "janus_D4", "buckled_D4", "janus_D8", "buckling_D8", "disc_ico6"]
+CONSTRAINED_NAMES = ["disc_D4_GV", "janus_D8_GV"]  # rigid volume constraint (-G V)
 
 
 def pytest_configure(config):

@@ -132,6 +132,36 @@ def test_trajectory_matches_reference_over_1000_steps(name):
         assert relerr(pos, g["k%d_pos" % g.traj_steps[-1]]) < 1e-6
 
 
+@pytest.mark.parametrize("name", ["disc_D4_GV", "janus_D8_GV"])
+def test_volume_constraint_matches_reference(name):
+    """-G V: SHAKE after the drift and RATTLE after the second kick (src/functions.h:33-171) against the
+    reference's own constrained runs -- first steps to 1e-10, A/U/E to 1e-6 over 1000 steps, and the enclosed
+    volume pinned to its initial value."""
+    g = golden(name)
+    with make_ctx(g) as ctx:
+        ctx.set_volume_constraint(True)
+        ctx.force_init()
+        ctx.constraint_init()
+        v0 = g.params["ref_volume"]
+        done = 0
+        for k in g.full_steps:
+            ctx.step(k - done)
+            done = k
+            check_against_fixture(ctx, g, k)
+        lam, mu = ctx.constraint_multipliers()
+        assert lam != 0.0 and mu != 0.0  # both corrections are live after a step
+        for k in g.traj_steps:
+            ctx.step(k - done)
+            done = k
+            e, s = ctx.energy(), g.scalars(k)
+            assert abs(e["total_area"] - s["total_area"]) <= 1e-6 * s["total_area"], (name, k)
+            assert abs(e["potential"] - s["penergy"]) <= 1e-6 * abs(s["penergy"]), (name, k)
+            assert abs(e["energy"] - s["energy"]) <= 1e-6 * abs(s["energy"]), (name, k)
+            assert abs(e["total_volume"] - v0) <= 1e-10 * v0, (name, k, e["total_volume"], v0)
+        pos = ctx.download_state()["pos"]
+        assert relerr(pos, g["k%d_pos" % g.traj_steps[-1]]) < 1e-6
+
+
 def perturbed(g, seed, amp):
     rng = np.random.default_rng(seed)
     pos = g["pos0"] * (1.0 + 0.05 * rng.standard_normal()) + amp * rng.standard_normal(g["pos0"].shape)

@@ -48,6 +48,7 @@ RECIPES = {
     "disc_D4": ["-q", "600", "-c", "0.005"],
     "janus_D8": ["-q", "600", "-c", "0.005", "-N", "2", "-p", "0.5"],
     "buckled_D4": ["-q", "0", "-c", "0.005", "-t", "0", "-v", "0", "-b", "1", "-s", "1000", "-B", "y"],
+    "disc_D4_GV": ["-q", "600", "-c", "0.005", "-G", "V"],
 }
 
 

@@ -72,6 +72,30 @@ def test_oracle_trajectory_matches_reference(name):
     assert relerr(o.vec("pos"), g["k%d_pos" % g.traj_steps[-1]]) < 1e-8
 
 
+@pytest.mark.parametrize("name", ["disc_D4_GV", "janus_D8_GV"])
+def test_oracle_volume_constraint_matches_reference(name):
+    """SHAKE / RATTLE (-G V, src/functions.h:33-171) and the restated cubic against the reference's own
+    constrained runs: first steps in full, then A/U/E and the pinned volume along the trajectory."""
+    g = golden(name)
+    o = make_oracle(g)
+    o.set_constraint(True)
+    o.md_init()
+    o.constraint_init()
+    done = 0
+    for k in g.full_steps:
+        o.md_steps(k - done)
+        done = k
+        check_step(o, g, k)
+    for k in g.traj_steps[:1]:
+        o.md_steps(k - done)
+        done = k
+        e, s = o.energy(), g.scalars(k)
+        sc = o.scalars()
+        assert abs(sc["total_area"] - s["total_area"]) < 1e-9 * s["total_area"]
+        assert abs(e["penergy"] - s["penergy"]) < 1e-9 * abs(s["penergy"])
+        assert abs(sc["total_volume"] - g.params["ref_volume"]) < 1e-12 * g.params["ref_volume"]
+
+
 def test_golden_fixtures_reproduce_shipped_example_series():
     """The fixtures (compiled reference, %.17g) agree with the series files the reference ships in
     examples/*_Control at their printed 6 significant digits, rows 0,1,2 (and 500/1000 where the
