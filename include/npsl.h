@@ -216,7 +216,14 @@ int npsl_pair_mode(const npsl_ctx *ctx);
  * 0 single GPU, 1 NCCL all-gathers, 2 direct stores into peer memory over NVLink (CUDA IPC; default when the
  * buffers can be mapped; NPSL_EXCHANGE=nccl in the environment forces 1). */
 int npsl_exchange_mode(const npsl_ctx *ctx);
-/* Owned row range of this context, half-open. */
+/* Sharding plan of a multi-GPU context: 0 single GPU; 1 rows -- vertices are owned in slices like the reference's
+ * MPI ranks (src/main.cpp:448-455), three exchanges per step; 2 replicated integrator -- only the pair term is
+ * split and every rank integrates all vertices, as the reference does after its all_gather of forces
+ * (src/newforces.cpp:268-271), one exchange per step. Automatic: 2 for charged meshes up to 100 000 vertices when
+ * peer memory is available; NPSL_SHARD=rows|replicated in the environment overrides. Trajectories are bit-identical
+ * under both plans and on any GPU count. */
+int npsl_shard_plan(const npsl_ctx *ctx);
+/* Vertex range this context integrates, half-open (all vertices under the replicated plan). */
 int npsl_owned_rows(const npsl_ctx *ctx, int32_t *lo, int32_t *hi);
 /* Launch geometry of the pair kernel: rows per thread, row tiles x column splits, columns per CTA. */
 int npsl_pair_geometry(const npsl_ctx *ctx, int32_t *rows_per_thread, int32_t *row_tiles, int32_t *col_splits,

@@ -26,7 +26,7 @@ SYMBOLS = [
     "npsl_force", "npsl_step", "npsl_energy", "npsl_sync", "npsl_launch_count", "npsl_pair_timing",
     "npsl_pair_timing_read", "npsl_owned_rows", "npsl_pair_geometry", "npsl_fp64_peak", "npsl_md_run",
     "npsl_step_timing", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_md_step_host", "npsl_set_pair_mode",
-    "npsl_pair_mode", "npsl_exchange_mode", "npsl_step_profile", "npsl_set_volume_constraint", "npsl_constraint_init",
+    "npsl_pair_mode", "npsl_exchange_mode", "npsl_shard_plan", "npsl_step_profile", "npsl_set_volume_constraint", "npsl_constraint_init",
     "npsl_constraint_multipliers",
 ]
 
@@ -115,6 +115,7 @@ def load() -> C.CDLL:
     L.npsl_set_pair_mode.argtypes = [vp, C.c_int]
     L.npsl_pair_mode.argtypes = [vp]
     L.npsl_exchange_mode.argtypes = [vp]
+    L.npsl_shard_plan.argtypes = [vp]
     L.npsl_set_volume_constraint.argtypes = [vp, C.c_int]
     L.npsl_constraint_init.argtypes = [vp]
     L.npsl_constraint_multipliers.argtypes = [vp, dp, dp]
@@ -368,6 +369,10 @@ class Context:
         a, b = C.c_double(), C.c_double()
         self._ck(self.L.npsl_constraint_multipliers(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def shard_plan(self) -> int:
+        """0 single GPU, 1 rows (owned vertex slices), 2 replicated integrator (only the pair term is split)."""
+        return int(self.L.npsl_shard_plan(self.h))
 
     def exchange_mode(self) -> int:
         """0 single GPU, 1 NCCL all-gathers, 2 stores into peer memory over NVLink."""

@@ -216,13 +216,13 @@ k_kick_drift(double4 *__restrict__ xyzq, double4 *__restrict__ vel, const double
         x.y = fma(v.y, dt, x.y);
         x.z = fma(v.z, dt, x.z);
         vel[i] = v;
-        if (X.on) {  // the new position goes straight into every rank's copy (NVLink peer stores)
+        if (xchg_has(X, XK_POS)) {  // the new position goes straight into every rank's copy (NVLink peer stores)
             for (int r = 0; r < X.world; r++) peer_xyzq[r][i] = x;
         } else {
             xyzq[i] = x;
         }
     }
-    if (X.on) xchg_signal(X, XK_POS, gridDim.x);
+    if (xchg_has(X, XK_POS)) xchg_signal(X, XK_POS, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -429,7 +429,7 @@ __device__ __forceinline__ void vertex_tail(double (&acc)[3], double *__restrict
         for (int o = 16; o > 0; o >>= 1) ke += __shfl_down_sync(0xffffffffu, ke, o);
         const int i0 = P.row_lo + blockIdx.x * blockDim.x + (threadIdx.x & ~31);
         if ((threadIdx.x & 31) == 0 && i0 < P.row_hi) {
-            if (X.on) {
+            if (xchg_has(X, XK_KE)) {
                 for (int r = 0; r < X.world; r++) peer_ke[r][i0 >> 5] = ke;
             } else {
                 ke_warp[i0 >> 5] = ke;
@@ -444,7 +444,7 @@ __device__ __forceinline__ void vertex_tail(double (&acc)[3], double *__restrict
             partials[nblocks + blockIdx.x] = e2[1];
         }
     }
-    if (X.on) xchg_signal(X, XK_KE, nblocks);
+    if (xchg_has(X, XK_KE)) xchg_signal(X, XK_KE, nblocks);
     __syncthreads();  // every warp's ke_warp store precedes thread 0's fence + ticket
     if (threadIdx.x == 0) s_last = take_last_ticket(ticket, nblocks);
     __syncthreads();
@@ -484,9 +484,20 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
          const Xchg X, const MeshParams P) {
     __shared__ double red[3 * 32];
     __shared__ bool s_last;
+    __shared__ size_t s_fv_off;
     const int nblocks = gridDim.x;
     const int i = P.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
     double acc[3] = {0, 0, 0};  // ke, es energy, lj energy
+    // Sums of the virtual ranks that arrive over peer memory: wait here (one warp per CTA polls the arrival
+    // flags of this force evaluation's exchange) instead of in a kernel of its own.
+    if (P.use_pair && P.pair_sym && xchg_has(X, XK_FV)) {
+        if (threadIdx.x < 32) {
+            const unsigned long long e = xchg_wait_own_epoch(X, XK_FV);
+            if (threadIdx.x == 0) s_fv_off = (size_t) ((e - 1) & 1ull) * (8 * 3) * P.npad;
+        }
+        __syncthreads();
+        pair_fv += s_fv_off;
+    }
     if (i < P.row_hi) {
         // ---- pair term: fixed-order sum of the partial results
         V3 fp = mk(0, 0, 0);
@@ -544,7 +555,7 @@ __global__ void __launch_bounds__(kMeshThreads)
 k_ke_post(const double *__restrict__ ke_warp, int n_ke_warps, double *__restrict__ scal,
           Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur, int step, const Xchg X, const MeshParams P) {
     __shared__ double red[32];
-    if (X.on) {
+    if (xchg_has(X, XK_KE)) {
         if (threadIdx.x < 32) xchg_wait_warp(X, XK_KE);
         __syncthreads();
     }

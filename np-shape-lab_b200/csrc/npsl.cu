@@ -110,8 +110,8 @@ struct npsl_ctx {
     LjParams ljp;
     MeshParams mp;
 
-    cudaStream_t s_main = nullptr, s_side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t s_main = nullptr, s_side = nullptr, s_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_lj_fork = nullptr, ev_lj_join = nullptr;
     cudaGraphExec_t step_graph = nullptr;
     ncclComm_t comm = nullptr;
 
@@ -140,6 +140,10 @@ struct npsl_ctx {
     int2 *sym_units = nullptr;   // this rank's units, heaviest first
     double *sym_rowpart = nullptr, *sym_colpart = nullptr, *sym_fv = nullptr;
     int sym_n_units = 0, sym_n_units_total = 0, sym_v_first = 0, sym_v_count = kSymV;
+    int *red_groups = nullptr;  // k_pair_reduce: vertex groups of the CTAs (rows + columns first, then columns only)
+    int red_n_a = 0, red_n_b_groups = 0, red_n_b_ctas = 0;
+    unsigned long long *sym_trace = nullptr;  // NPSL_SYM_TRACE
+    std::vector<int2> sym_trace_units;
     int n_sm = 148;
     // caller buffers of the host-buffer entry points that were page-locked with cudaHostRegister (so that the
     // copies go straight from / to the caller's arrays); anything that cannot be registered is staged
@@ -151,6 +155,10 @@ struct npsl_ctx {
     size_t prof_used = 0;
     // exchanges over NVLink peer memory (xchg.cuh); NCCL all-gathers are the fallback
     bool p2p = false;
+    // sharding plan of a multi-GPU context: rows (owned vertex ranges, three exchanges per step) or replicated
+    // integrator (every rank integrates all vertices, only the pair term is split, one exchange per step)
+    bool replicated = false;
+    int shard_pref = 0;                           // 0 automatic, 1 rows, 2 replicated (NPSL_SHARD)
     Xchg xg;                                      // kernel parameter block
     unsigned long long *xflags = nullptr;         // [XK_KINDS][kMaxRanks], written by the peers
     unsigned long long *xstate = nullptr;         // epochs
@@ -345,8 +353,19 @@ int plan_sym(npsl_ctx *c) {
     sp.rb = c->sym_rows * c->sym_threads;
     // 256 columns per unit up to 32768 vertices, at most 256 chunks beyond: fine-grained enough to fill 8 GPUs
     sp.chunk_tiles = std::max(2, (nv + 256 * kSymCT - 1) / (256 * kSymCT));
+    if (const char *e = getenv("NPSL_SYM_CHUNK_TILES"))  // measurement knob; changes the grouping of the row sums
+        if (atoi(e) > 0) sp.chunk_tiles = atoi(e);
     const int n_tiles = (nv + kSymCT - 1) / kSymCT;
-    sp.n_chunks = (n_tiles + sp.chunk_tiles - 1) / sp.chunk_tiles;
+    // The last quarter of the column range is cut into half-width chunks. Units are launched heaviest first, so
+    // these run last and halve the raggedness at the end of the launch (each rank of an 8-GPU job has fewer than
+    // two waves of full units at S64). A function of the vertex count only, like everything else here.
+    int fine_pct = 25;
+    if (const char *e = getenv("NPSL_SYM_FINE_PCT")) fine_pct = std::max(0, std::min(100, atoi(e)));  // measurement knob
+    sp.fine_tiles = std::max(1, sp.chunk_tiles / 2);
+    const int coarse_tiles = n_tiles - (int) ((long) n_tiles * fine_pct / 100);
+    sp.n_coarse = fine_pct >= 100 ? 0 : (coarse_tiles + sp.chunk_tiles - 1) / sp.chunk_tiles;
+    const int rest = std::max(0, n_tiles - sp.n_coarse * sp.chunk_tiles);
+    sp.n_chunks = sp.n_coarse + (rest + sp.fine_tiles - 1) / sp.fine_tiles;
     sp.c2s = c->pp.c2s; sp.inv_lambda = c->pp.inv_lambda; sp.lj_cut_hi = c->pp.lj_cut_hi;
     const int n_rb = (nv + sp.rb - 1) / sp.rb;
     const bool want = c->pair_mode == 2 || (c->pair_mode == 0 && nv >= 4096);
@@ -356,14 +375,23 @@ int plan_sym(npsl_ctx *c) {
     if (!c->use_sym) return 0;
     c->sym_v_count = kSymV / c->world;
     c->sym_v_first = c->rank * c->sym_v_count;
+    // Measurement only: NPSL_EMULATE_SHARD="r/w" makes a single-GPU context do just the pair work of rank r of w
+    // (incomplete forces), so that a rank's kernels can be profiled under ncu without a multi-rank job.
+    if (const char *e = getenv("NPSL_EMULATE_SHARD")) {
+        int er = 0, ew = 1;
+        if (c->world == 1 && sscanf(e, "%d/%d", &er, &ew) == 2 && ew > 0 && kSymV % ew == 0 && er >= 0 && er < ew) {
+            c->sym_v_count = kSymV / ew;
+            c->sym_v_first = er * c->sym_v_count;
+        }
+    }
     struct U { int I, cc, work; };
     std::vector<U> mine;
     int total = 0;
     for (int I = 0; I < n_rb; I++) {
         const int v = sym_vrank(I);
         for (int cc = 0; cc < sp.n_chunks; cc++) {
-            const int tile_end = std::min((cc + 1) * sp.chunk_tiles, n_tiles);
-            const int tile_begin = std::max(cc * sp.chunk_tiles, I * sp.rb / kSymCT);
+            const int tile_end = std::min(sym_chunk_tile0(sp, cc + 1), n_tiles);
+            const int tile_begin = std::max(sym_chunk_tile0(sp, cc), I * sp.rb / kSymCT);
             if (tile_end <= tile_begin) continue;
             total++;
             if (v >= c->sym_v_first && v < c->sym_v_first + c->sym_v_count) mine.push_back({I, cc, tile_end - tile_begin});
@@ -381,8 +409,33 @@ int plan_sym(npsl_ctx *c) {
     CU(dalloc(&c->sym_units, units.size()));
     CU(dalloc(&c->sym_rowpart, (size_t) sp.n_chunks * 3 * sp.npad));
     CU(dalloc(&c->sym_colpart, (size_t) n_rb * 3 * sp.npad));
-    if (!c->sym_fv) CU(dalloc(&c->sym_fv, (size_t) kSymV * 3 * sp.npad));  // fixed size: peers map it
+    if (!c->sym_fv) CU(dalloc(&c->sym_fv, (size_t) 2 * kSymV * 3 * sp.npad));  // fixed size: peers map it; two epochs
     CU(cudaMemcpy(c->sym_units, units.data(), sizeof(int2) * units.size(), cudaMemcpyHostToDevice));
+    {  // k_pair_reduce: groups of 32 vertices whose row block is computed here come first (they also add row partials)
+        std::vector<int> ga, gb;
+        const int n_groups = (nv + 31) / 32;
+        for (int g = 0; g < n_groups; g++) {
+            const int v = sym_vrank(g * 32 / sp.rb);
+            (v >= c->sym_v_first && v < c->sym_v_first + c->sym_v_count ? ga : gb).push_back(g);
+        }
+        c->red_n_a = (int) ga.size();
+        c->red_n_b_groups = (int) gb.size();
+        const int per_cta = kSymV / c->sym_v_count;
+        c->red_n_b_ctas = (c->red_n_b_groups + per_cta - 1) / per_cta;
+        ga.insert(ga.end(), gb.begin(), gb.end());
+        if (c->red_groups) cudaFree(c->red_groups);
+        c->red_groups = nullptr;
+        CU(dalloc(&c->red_groups, ga.size()));
+        CU(cudaMemcpy(c->red_groups, ga.data(), sizeof(int) * ga.size(), cudaMemcpyHostToDevice));
+    }
+    if (c->sym_trace) cudaFree(c->sym_trace);
+    c->sym_trace = nullptr;
+    sp.trace = nullptr;
+    if (getenv("NPSL_SYM_TRACE")) {  // measurement only: per-CTA timeline of the last k_pair_sym launch
+        CU(dalloc(&c->sym_trace, 3 * units.size() + 3));
+        sp.trace = c->sym_trace;
+        c->sym_trace_units = units;
+    }
     return 0;
 }
 
@@ -418,14 +471,14 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
                                                                         c->d_peer_xyzq, c->xg, c->mp);
         n++;
         mark("k_kick_drift");
-        if (c->p2p) {
+        if (c->xg.on & (1 << XK_POS)) {
             k_xchg_wait<<<1, 32, 0, c->s_main>>>(c->xg, XK_POS);
             n++;
-        } else if (c->world > 1) {
+        } else if (c->world > 1 && !c->replicated) {
             NC(g_nccl.AllGather(c->xyzq + (size_t) c->rank * c->range, c->xyzq, (size_t) c->range * 4, ncclFloat64_,
                                 c->comm, c->s_main));
         }
-        if (c->world > 1) mark("exchange positions");
+        if (c->world > 1 && !c->replicated) mark("exchange positions");
         if (c->mp.constraint) {  // SHAKE, src/newmd.cpp:126
             k_constraint_sums<0><<<c->n_face_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv, c->face_v,
                                                                                   c->part_con, c->tickets + 2, c->scal, c->mp);
@@ -437,8 +490,11 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
     } else {
         CU(cudaMemsetAsync(c->lj_hit, 0, sizeof(int), c->s_main));
     }
-    // mesh terms on the side stream, concurrent with the pair term
+    // Mesh terms on the low-priority side stream. They are issued after the pair kernel: its CTAs fill every SM
+    // (three per SM take all registers), so the mesh CTAs run in the ragged end of the pair launch instead of
+    // delaying its start. Uncharged meshes have no pair kernel; there the order does not matter.
     CU(cudaEventRecord(c->ev_fork, c->s_main));
+    auto issue_mesh = [&]() -> int {
     CU(cudaStreamWaitEvent(c->s_side, c->ev_fork, 0));
     {
         const int grid = c->n_face_blocks + c->n_edge_blocks;
@@ -462,6 +518,10 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
         n++;
     }
     CU(cudaEventRecord(c->ev_join, c->s_side));
+        return 0;
+    };
+    bool mesh_issued = false;
+    cudaStream_t lj_stream = c->s_main;
     if (!c->all_q_zero) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (time_pair && c->t_used + 2 <= c->t_ev.size()) {
@@ -488,7 +548,14 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
             n++;
             if (e1) CU(cudaEventRecord(e1, c->s_main));
             mark("k_pair_sym");
-            k_pair_reduce<<<(c->nv + 31) / 32, dim3(32, 8), 0, c->s_main>>>(c->sym_rowpart, c->sym_colpart, c->sym_fv,
+            { int r = issue_mesh(); if (r < 0) return r; mesh_issued = true; }
+            if (!ordered) {  // the exact LJ pass only needs the collision detector: it runs beside k_pair_reduce
+                CU(cudaEventRecord(c->ev_lj_fork, c->s_main));
+                CU(cudaStreamWaitEvent(c->s_aux, c->ev_lj_fork, 0));
+                lj_stream = c->s_aux;
+            }
+            k_pair_reduce<<<c->red_n_a + c->red_n_b_ctas, dim3(32, 8), 0, c->s_main>>>(c->sym_rowpart, c->sym_colpart, c->sym_fv,
+                                                                            c->red_groups, c->red_n_a, c->red_n_b_groups,
                                                                             c->sym_v_first, c->sym_v_count,
                                                                             c->d_peer_fv, c->range, c->xg, c->sp);
             n++;
@@ -509,16 +576,17 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
             if (e1 && !c->use_sym) CU(cudaEventRecord(e1, c->s_main));
         }
     }
-    k_lj<<<(c->row_hi - c->row_lo + 127) / 128, 128, 0, c->s_main>>>(c->xyzq, c->lj_out, c->lj_hit,
-                                                                      c->all_q_zero ? 1 : 0, c->ljp);
+    if (!mesh_issued) { int r = issue_mesh(); if (r < 0) return r; }
+    k_lj<<<(c->row_hi - c->row_lo + 127) / 128, 128, 0, lj_stream>>>(c->xyzq, c->lj_out, c->lj_hit,
+                                                                     c->all_q_zero ? 1 : 0, c->ljp);
     n++;
+    if (lj_stream != c->s_main) {
+        CU(cudaEventRecord(c->ev_lj_join, lj_stream));
+        CU(cudaStreamWaitEvent(c->s_main, c->ev_lj_join, 0));
+    }
     mark("k_pair (ordered) + k_lj");
     CU(cudaStreamWaitEvent(c->s_main, c->ev_join, 0));
-    if (c->p2p && c->use_sym && !c->all_q_zero) {  // the virtual-rank sums for the owned vertices have arrived
-        k_xchg_wait<<<1, 32, 0, c->s_main>>>(c->xg, XK_FV);
-        n++;
-    }
-    mark("join k_mesh + wait pair sums");
+    mark("join k_mesh");
     if (step) {
         k_vertex<VMODE_STEP><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(
             c->xyzq, c->vel, c->force, c->fmesh, c->pair_partial, c->sym_fv, c->lj_out, c->lj_hit, fc, c->part_vert,
@@ -540,7 +608,7 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
         n += 2;
         mark("RATTLE");
     }
-    if (c->world > 1) {
+    if (c->world > 1 && !c->replicated) {
         const size_t per_rank = (size_t) c->range / 32;
         if (!c->p2p)
             NC(g_nccl.AllGather(c->ke_warp + (size_t) c->rank * per_rank, c->ke_warp, per_rank, ncclFloat64_, c->comm,
@@ -582,7 +650,7 @@ int ensure_graph(npsl_ctx *c) {
     }
     if (e != cudaSuccess) return fail(c, NPSL_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e));
     c->launches_per_step = n;
-    e = cudaGraphInstantiate(&c->step_graph, g, 0);
+    e = cudaGraphInstantiateWithFlags(&c->step_graph, g, cudaGraphInstantiateFlagUseNodePriority);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) return fail(c, NPSL_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
     return 0;
@@ -603,7 +671,7 @@ int collect_timing(npsl_ctx *c) {
 
 // in-place all-gather of a per-vertex record array laid out as world*range records
 int gather_records(npsl_ctx *c, double4 *buf) {
-    if (c->world == 1) return 0;
+    if (c->world == 1 || c->replicated) return 0;  // replicated integrator: every rank holds every vertex
     NC(g_nccl.AllGather(buf + (size_t) c->rank * c->range, buf, (size_t) c->range * 4, ncclFloat64_, c->comm,
                         c->s_main));
     return 0;
@@ -648,7 +716,7 @@ void drop_graph(npsl_ctx *c) {
 // flags) into this process with CUDA IPC. The handles travel through one NCCL all-gather. Any failure leaves
 // the context on the NCCL exchanges.
 int setup_p2p(npsl_ctx *c) {
-    c->xg.world = c->world; c->xg.rank = c->rank; c->xg.on = 0;
+    c->xg.world = c->world; c->xg.rank = c->rank; c->xg.on = 0; c->xg.fv_bcast = 0; c->xg.cta_fence_sys = 0;
     c->xg.peer_flags = nullptr; c->xg.state = nullptr; c->xg.tickets = nullptr;
     if (c->world == 1) return 0;
     const char *env = getenv("NPSL_EXCHANGE");
@@ -704,7 +772,48 @@ int setup_p2p(npsl_ctx *c) {
     CU(cudaMemcpy(c->d_peer_flags, c->peer_map[3], sizeof(void *) * c->world, cudaMemcpyHostToDevice));
     c->xg.peer_flags = c->d_peer_flags; c->xg.state = c->xstate; c->xg.tickets = c->xtickets;
     c->p2p = true;
-    c->xg.on = 1;
+    c->xg.on = (1 << XK_KINDS) - 1;
+    return 0;
+}
+
+// Chooses between the two sharding plans of a multi-GPU context and sets the owned ranges, launch geometry and
+// exchange mask accordingly. Every rank takes the same decision (it depends on the vertex count, the charges,
+// the environment and on whether peer mapping succeeded, which the ranks agreed on in setup_p2p).
+//   rows        vertices are owned in slices (src/main.cpp:448-455); positions, pair-force sums and kinetic-energy
+//               partials are exchanged every step. Less redundant O(N) work, three exchange latencies per step.
+//   replicated  only the pair term is split (the reference's own scheme: it all-gathers forces and lets every rank
+//               integrate, src/newforces.cpp:268-271); one exchange per step. Wins while the O(N) kernels are
+//               latency-bound, i.e. for meshes up to about 1e5 vertices.
+constexpr int kReplicateUpTo = 100000;
+int apply_shard_plan(npsl_ctx *c) {
+    const bool can = c->world > 1 && c->p2p && c->use_sym && !c->all_q_zero;
+    const bool want = c->shard_pref == 2 || (c->shard_pref == 0 && c->nv <= kReplicateUpTo);
+    c->replicated = can && want;
+    if (c->mp.constraint && c->world > 1 && !c->replicated)
+        return fail(c, NPSL_ERR_ARG, "the rigid volume constraint needs a single-GPU context or the replicated sharding plan");
+    if (c->replicated) {
+        c->row_lo = 0;
+        c->row_hi = c->nv;
+    } else {
+        c->row_lo = std::min(c->rank * c->range, c->nv);
+        c->row_hi = std::min((c->rank + 1) * c->range, c->nv);
+    }
+    c->n_vertex_blocks = (c->row_hi - c->row_lo + kMeshThreads - 1) / kMeshThreads;
+    c->pp.row_lo = c->ljp.row_lo = c->mp.row_lo = c->row_lo;
+    c->pp.row_hi = c->ljp.row_hi = c->mp.row_hi = c->row_hi;
+    c->mp.n_ranks = c->replicated ? 1 : c->world;
+    c->xg.on = !c->p2p ? 0 : (c->replicated ? (1 << XK_FV) : (1 << XK_KINDS) - 1);
+    c->xg.fv_bcast = c->replicated ? 1 : 0;
+    c->xg.cta_fence_sys = 0;
+    if (const char *e = getenv("NPSL_CTA_FENCE_SYS")) c->xg.cta_fence_sys = atoi(e) ? 1 : 0;  // measurement knob
+    CU(cudaStreamSynchronize(c->s_main));
+    plan_pair(c, c->n_sm);
+    if (c->pair_partial) cudaFree(c->pair_partial);
+    c->pair_partial = nullptr;
+    CU(dalloc(&c->pair_partial, (size_t) c->pair_splits * c->pair_row_stride));
+    apply_pair_plan(c);
+    drop_graph(c);
+    c->forces_valid = false;
     return 0;
 }
 
@@ -766,7 +875,7 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     CUB(dalloc(&c->degree, c->nv)); CUB(dalloc(&c->ring, (size_t) kMaxDeg * c->nv));
     CUB(dalloc(&c->ring_l0, (size_t) kMaxDeg * c->nv)); CUB(dalloc(&c->bslot_ref, (size_t) 2 * kMaxDeg * c->nv));
     CUB(dalloc(&c->bslot, (size_t) 4 * c->ne));
-    CUB(dalloc(&c->lj_out, c->range)); CUB(dalloc(&c->lj_hit, 1));
+    CUB(dalloc(&c->lj_out, nrec)); CUB(dalloc(&c->lj_hit, 1));
     CUB(dalloc(&c->scal, SC_COUNT)); CUB(dalloc(&c->scal_all, (size_t) SC_COUNT * world));
     c->n_ke_warps = (int) (nrec / 32);
     CUB(dalloc(&c->ke_warp, c->n_ke_warps));
@@ -793,7 +902,7 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     c->n_edge_blocks = (c->ne + kMeshThreads - 1) / kMeshThreads;
     c->n_vertex_blocks = (c->row_hi - c->row_lo + kMeshThreads - 1) / kMeshThreads;
     CUB(dalloc(&c->part_mesh, (size_t) 4 * (c->n_face_blocks + c->n_edge_blocks)));
-    CUB(dalloc(&c->part_vert, (size_t) 3 * c->n_vertex_blocks));
+    CUB(dalloc(&c->part_vert, (size_t) 3 * ((nrec + kMeshThreads - 1) / kMeshThreads)));
     CUB(dalloc(&c->part_con, (size_t) 8 * c->n_face_blocks));
 
     const double lam = prm->inv_kappa_out;
@@ -821,11 +930,18 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     CUB(cudaMemcpy(c->th_mid, &th, sizeof th, cudaMemcpyHostToDevice));
 
     if (plan_sym(c)) return bail(NPSL_ERR_CUDA);
-    if (!c->sym_fv) CUB(dalloc(&c->sym_fv, (size_t) kSymV * 3 * c->sp.npad));
-    CUB(cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
-    CUB(cudaStreamCreateWithFlags(&c->s_side, cudaStreamNonBlocking));
+    if (!c->sym_fv) CUB(dalloc(&c->sym_fv, (size_t) 2 * kSymV * 3 * c->sp.npad));
+    {
+        int prio_least = 0, prio_greatest = 0;
+        CUB(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        CUB(cudaStreamCreateWithPriority(&c->s_main, cudaStreamNonBlocking, prio_greatest));
+        CUB(cudaStreamCreateWithPriority(&c->s_side, cudaStreamNonBlocking, prio_least));
+        CUB(cudaStreamCreateWithPriority(&c->s_aux, cudaStreamNonBlocking, prio_least));
+    }
     CUB(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_lj_fork, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_lj_join, cudaEventDisableTiming));
 #undef CUB
     if (world > 1) {
         std::string e;
@@ -838,6 +954,9 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     {
         int r = setup_p2p(c);
         if (r) return bail(r);
+        const char *env = getenv("NPSL_SHARD");
+        c->shard_pref = env && strcmp(env, "rows") == 0 ? 1 : (env && strcmp(env, "replicated") == 0 ? 2 : 0);
+        if ((r = apply_shard_plan(c))) return bail(r);
     }
     *out = c;
     return NPSL_OK;
@@ -875,7 +994,20 @@ int npsl_nccl_unique_id(void *out_id) {
 void npsl_destroy(npsl_ctx *c) {
     if (!c) return;
     if (c->s_main) cudaStreamSynchronize(c->s_main);
+    if (c->sym_trace && getenv("NPSL_SYM_TRACE")) {  // "block I chunk sm start_ns end_ns" of the last launch
+        std::vector<unsigned long long> tr(3 * c->sym_trace_units.size());
+        if (cudaMemcpy(tr.data(), c->sym_trace, tr.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            if (FILE *f = fopen(getenv("NPSL_SYM_TRACE"), "w")) {
+                for (size_t k = 0; k < c->sym_trace_units.size(); k++)
+                    fprintf(f, "%zu %d %d %llu %llu %llu\n", k, c->sym_trace_units[k].x, c->sym_trace_units[k].y, tr[3 * k],
+                            tr[3 * k + 1], tr[3 * k + 2]);
+                fclose(f);
+            }
+        }
+        cudaFree(c->sym_trace);
+    }
     if (c->s_side) cudaStreamSynchronize(c->s_side);
+    if (c->s_aux) cudaStreamSynchronize(c->s_aux);
     if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
     for (auto &e : c->pinned_user) cudaHostUnregister(e.first);
@@ -893,15 +1025,18 @@ void npsl_destroy(npsl_ctx *c) {
     void *ptrs[] = {c->xyzq, c->vel, c->force, c->fmesh, c->ngv, c->part_con, c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->face_v,
                     c->edge_rec, c->l0, c->degree, c->ring, c->bslot_ref, c->ring_l0, c->bslot, c->pair_partial,
                     c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_warp, c->th_cur, c->th_mid, c->part_mesh,
-                    c->part_vert, c->tickets, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units,
+                    c->part_vert, c->tickets, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units, c->red_groups,
                     c->sym_rowpart, c->sym_colpart, c->sym_fv, c->xflags, c->xstate, c->xtickets,
                     c->d_peer_xyzq, c->d_peer_fv, c->d_peer_ke, c->d_peer_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_lj_fork) cudaEventDestroy(c->ev_lj_fork);
+    if (c->ev_lj_join) cudaEventDestroy(c->ev_lj_join);
     if (c->s_main) cudaStreamDestroy(c->s_main);
     if (c->s_side) cudaStreamDestroy(c->s_side);
+    if (c->s_aux) cudaStreamDestroy(c->s_aux);
     delete c;
 }
 
@@ -927,6 +1062,10 @@ int npsl_upload_state(npsl_ctx *c, const double *pos, const double *vel, const d
         if (use != c->mp.use_pair) {
             c->mp.use_pair = use;
             drop_graph(c);
+            if (c->world > 1) {  // uncharged meshes have no pair term to split: rows plan
+                int r2 = apply_shard_plan(c);
+                if (r2) return r2;
+            }
         }
         c->forces_valid = false;
     }
@@ -1067,7 +1206,8 @@ int npsl_energy(npsl_ctx *c, npsl_energies *out) {
     int r = force_pass(c);
     if (r) return r;
     std::vector<double> all((size_t) SC_COUNT * c->world);
-    if (c->world > 1) {
+    const int n_parts = c->replicated ? 1 : c->world;  // replicated integrator: this rank walked all rows itself
+    if (n_parts > 1) {
         NC(g_nccl.AllGather(c->scal, c->scal_all, SC_COUNT, ncclFloat64_, c->comm, c->s_main));
         CU(cudaMemcpyAsync(all.data(), c->scal_all, sizeof(double) * all.size(), cudaMemcpyDeviceToHost, c->s_main));
     } else {
@@ -1077,11 +1217,11 @@ int npsl_energy(npsl_ctx *c, npsl_energies *out) {
     CU(cudaMemcpyAsync(&th, c->th_cur, sizeof th, cudaMemcpyDeviceToHost, c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
     double ke = 0, es = 0, lj = 0;
-    for (int k = 0; k < c->world; k++) {  // fixed rank order
+    for (int k = 0; k < n_parts; k++) {  // fixed rank order
         es += all[(size_t) k * SC_COUNT + SC_ES];
         lj += all[(size_t) k * SC_COUNT + SC_LJ];
     }
-    const double *s = all.data() + (size_t) c->rank * SC_COUNT;
+    const double *s = all.data() + (size_t) (n_parts > 1 ? c->rank : 0) * SC_COUNT;
     const npsl_params &p = c->prm;
     ke = s[SC_KE];  // already the sum over all ranks (canonical order, mesh_kernels.cuh)
     out->kinetic = ke;
@@ -1322,7 +1462,8 @@ int npsl_set_pair_plan(npsl_ctx *c, int rows_per_thread, int col_splits) {
 
 int npsl_set_volume_constraint(npsl_ctx *c, int on) {
     if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
-    if (on && c->world > 1) return fail(c, NPSL_ERR_ARG, "the rigid volume constraint is not available on sharded contexts");
+    if (on && c->world > 1 && !c->replicated)
+        return fail(c, NPSL_ERR_ARG, "the rigid volume constraint is not available on row-sharded contexts");
     CU(cudaStreamSynchronize(c->s_main));
     c->mp.constraint = on ? 1 : 0;
     drop_graph(c);
@@ -1366,6 +1507,7 @@ int npsl_set_pair_mode(npsl_ctx *c, int mode) {
     int r = plan_sym(c);
     if (r) return r;
     if (mode == 2 && !c->use_sym) return fail(c, NPSL_ERR_ARG, "symmetric pair kernel needs a rank count that divides 8");
+    if (c->world > 1 && (r = apply_shard_plan(c))) return r;
     drop_graph(c);
     c->forces_valid = false;
     return NPSL_OK;
@@ -1374,6 +1516,8 @@ int npsl_set_pair_mode(npsl_ctx *c, int mode) {
 int npsl_pair_mode(const npsl_ctx *c) { return c ? (c->use_sym ? 2 : 1) : NPSL_ERR_ARG; }
 
 int npsl_exchange_mode(const npsl_ctx *c) { return c ? (c->world == 1 ? 0 : (c->p2p ? 2 : 1)) : NPSL_ERR_ARG; }
+
+int npsl_shard_plan(const npsl_ctx *c) { return c ? (c->world == 1 ? 0 : (c->replicated ? 2 : 1)) : NPSL_ERR_ARG; }
 
 int npsl_owned_rows(const npsl_ctx *c, int32_t *lo, int32_t *hi) {
     if (!c) return NPSL_ERR_ARG;

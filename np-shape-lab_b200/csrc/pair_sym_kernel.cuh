@@ -32,11 +32,23 @@ struct SymParams {
     int n;            // vertices
     int npad;         // plane length of the partial buffers (>= n, multiple of kSymPad)
     int rb;           // rows per row block = threads per CTA x rows per thread
-    int chunk_tiles;  // 128-column tiles per column chunk
+    int chunk_tiles;  // 128-column tiles per column chunk (the first n_coarse chunks)
+    int n_coarse;     // chunks [n_coarse, n_chunks) at the high end of the column range are fine_tiles wide: smaller
+    int fine_tiles;   //   units that are scheduled last and even out the tail of the launch
     int n_chunks;
     int lj_cut_hi;
+    unsigned long long *trace;  // measurement only (NPSL_SYM_TRACE): per CTA {SM id, start ns, end ns}, else null
 };
 constexpr int kSymCT = 128;   // granularity of the column chunks (the kernels' column tile is THREADS wide)
+// first tile of chunk c (c == n_chunks: one past the last tile, before clamping to the vertex count)
+__host__ __device__ __forceinline__ int sym_chunk_tile0(const SymParams &P, const int c) {
+    return c <= P.n_coarse ? c * P.chunk_tiles : P.n_coarse * P.chunk_tiles + (c - P.n_coarse) * P.fine_tiles;
+}
+// chunk that holds tile t
+__host__ __device__ __forceinline__ int sym_chunk_of_tile(const SymParams &P, const int t) {
+    const int tc = P.n_coarse * P.chunk_tiles;
+    return t < tc ? t / P.chunk_tiles : P.n_coarse + (t - tc) / P.fine_tiles;
+}
 
 // e^{-r/lambda} (1/r^3 + 1/(lambda r^2)) of one pair; d = x_i - x_j
 __device__ __forceinline__ double pair_geom(double dx, double dy, double dz, const double c2s, const double inv_lambda,
@@ -156,6 +168,8 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
     __shared__ double sax[THREADS], say[THREADS], saz[THREADS];
     __shared__ double tab[kExpTab];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    unsigned long long t_begin = 0;
+    if (P.trace && t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
     for (int k = t; k < kExpTab; k += THREADS) tab[k] = c_exp2_tab[k];
     const int2 unit = units[blockIdx.x];
     const int I = unit.x, c = unit.y;
@@ -174,8 +188,8 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
     const double c2s = P.c2s, inv_lambda = P.inv_lambda;
     int min_r2_hi = 0x7fffffff;
     // columns of this unit: the chunk, from the start of the row block on (what lies below belongs to other units)
-    const int col_begin = max(c * P.chunk_tiles * kSymCT, row0);
-    const int col_end = min((c + 1) * P.chunk_tiles * kSymCT, P.n);
+    const int col_begin = max(sym_chunk_tile0(P, c) * kSymCT, row0);
+    const int col_end = min(sym_chunk_tile0(P, c + 1) * kSymCT, P.n);
 
     for (int j0 = col_begin; j0 < col_end; j0 += THREADS) {
         const int j = j0 + t;
@@ -219,6 +233,18 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
         }
     }
     if (min_r2_hi <= P.lj_cut_hi) *lj_hit = 1;  // benign race: every writer stores the same value
+    if (P.trace) {
+        __syncthreads();
+        if (t == 0) {
+            unsigned long long t_end;
+            unsigned int smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            P.trace[3 * blockIdx.x] = smid;
+            P.trace[3 * blockIdx.x + 1] = t_begin;
+            P.trace[3 * blockIdx.x + 2] = t_end;
+        }
+    }
 }
 
 // Virtual rank of a row block: 0..7, 7..0, 0..7, ... so that the triangular work (row block I meets
@@ -231,74 +257,116 @@ __host__ __device__ __forceinline__ int sym_vrank(int I) {
 // Sums the partials per vertex x and virtual rank v in a fixed order:
 //   fv[v][x] = (v == vrank(block of x) ? sum of the row partials of x over its chunks : 0)
 //              + sum over the row blocks I <= block(x) with vrank(I) == v of colpart[I][x]   (ascending I).
-// block = (32 vertices, 8): thread (x, k) adds the column partials of virtual rank k and the row partials of
-// the chunks congruent to k mod 8; the eight row segments are then added in order 0..7.
 // Only the virtual ranks [v_first, v_first + v_count) are computed (the others live on other GPUs).
+// A CTA has 8 slots of 32 lanes (lane = vertex of a group of 32 consecutive vertices):
+//   CTAs [0, n_a): one group whose row block belongs to this rank -- slot k adds the row partials of the chunks
+//     congruent to k mod 8 (the eight segments are then added in order 0..7) and, if virtual rank k is computed
+//     here, the column partials of virtual rank k;
+//   the others: 8 / v_count groups that only receive column partials -- slot s works on group s / v_count for
+//     virtual rank v_first + s % v_count.
+// groups[] lists the group of every (CTA, slot / v_count); the loads of a thread are issued in batches of 8 chunks /
+// all row blocks so that a CTA needs only a few memory round trips (the kernel is latency-bound on a shard).
 __global__ void __launch_bounds__(256)
 k_pair_reduce(const double *__restrict__ rowpart, const double *__restrict__ colpart, double *__restrict__ fv,
-              int v_first, int v_count, double *const *__restrict__ peer_fv, int rows_per_rank, const Xchg X,
-              const SymParams P) {
+              const int *__restrict__ groups, int n_a, int n_b_groups, int v_first, int v_count,
+              double *const *__restrict__ peer_fv, int rows_per_rank, const Xchg X, const SymParams P) {
     __shared__ double seg[3][8][32];
-    const int tx = threadIdx.x, k = threadIdx.y;
-    const int x = blockIdx.x * 32 + tx;
-    const bool live = x < P.n;
+    const int tx = threadIdx.x, slot = threadIdx.y;
+    const bool remote = xchg_has(X, XK_FV);
+    // receive buffers are double-buffered on the parity of the exchange epoch (read before this CTA's ticket,
+    // i.e. before the last CTA can bump it)
+    const size_t fv_off = remote ? (size_t) (X.state[XK_FV] & 1ull) * (kSymV * 3) * P.npad : 0;
+    const bool part_a = (int) blockIdx.x < n_a;
+    int g = -1, k = slot;
+    if (part_a) {
+        g = __ldg(groups + blockIdx.x);
+    } else {
+        const int per_cta = 8 / v_count;
+        const int idx = ((int) blockIdx.x - n_a) * per_cta + slot / v_count;
+        if (idx < n_b_groups) g = __ldg(groups + n_a + idx);
+        k = v_first + slot % v_count;
+    }
+    const int x = g * 32 + tx;
+    const bool live = g >= 0 && x < P.n;
     const int Ix = live ? x / P.rb : 0;
     const int vx = sym_vrank(Ix);
-    const bool rows_here = live && vx >= v_first && vx < v_first + v_count;
     const bool cols_here = live && k >= v_first && k < v_first + v_count;
-    double rx = 0.0, ry = 0.0, rz = 0.0;
-    if (rows_here) {
-        const int cmin = (Ix * P.rb) / (P.chunk_tiles * kSymCT);
-#pragma unroll 4
-        for (int c = cmin + ((k - cmin) & 7); c < P.n_chunks; c += 8) {  // chunks congruent to k mod 8, ascending
-            const double *rp = rowpart + (size_t) c * 3 * P.npad + x;
-            rx += __ldcg(rp); ry += __ldcg(rp + P.npad); rz += __ldcg(rp + 2 * (size_t) P.npad);
-        }
-    }
-    seg[0][k][tx] = rx; seg[1][k][tx] = ry; seg[2][k][tx] = rz;
+    const size_t plane = P.npad;
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    if (cols_here) {
-#pragma unroll 2
-        for (int b = 0; b <= Ix; b += 16) {  // row blocks of virtual rank k: 16j + k and 16j + 15 - k
-            const int I1 = b + k, I2 = b + 15 - k;
-            if (I1 <= Ix) {
-                const double *cp = colpart + (size_t) I1 * 3 * P.npad + x;
-                fx += __ldcg(cp); fy += __ldcg(cp + P.npad); fz += __ldcg(cp + 2 * (size_t) P.npad);
+    if (cols_here) {  // row blocks of virtual rank k: 16j + k and 16j + 15 - k, ascending
+        constexpr int UB = 4;
+        for (int b0 = 0; b0 <= Ix; b0 += 16 * UB) {
+            double v[UB][2][3];
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                const int I1 = b0 + 16 * u + k, I2 = b0 + 16 * u + 15 - k;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int I = h ? I2 : I1;
+                    const bool on = I <= Ix;
+                    const double *cp = colpart + (size_t) (on ? I : 0) * 3 * plane + x;
+                    v[u][h][0] = on ? __ldcg(cp) : 0.0;
+                    v[u][h][1] = on ? __ldcg(cp + plane) : 0.0;
+                    v[u][h][2] = on ? __ldcg(cp + 2 * plane) : 0.0;
+                }
             }
-            if (I2 <= Ix) {
-                const double *cp = colpart + (size_t) I2 * 3 * P.npad + x;
-                fx += __ldcg(cp); fy += __ldcg(cp + P.npad); fz += __ldcg(cp + 2 * (size_t) P.npad);
-            }
+#pragma unroll
+            for (int u = 0; u < UB; u++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int I = h ? b0 + 16 * u + 15 - k : b0 + 16 * u + k;
+                    if (I <= Ix) { fx += v[u][h][0]; fy += v[u][h][1]; fz += v[u][h][2]; }
+                }
         }
     }
-    __syncthreads();
-    if (cols_here) {
-        if (k == vx) {
+    if (part_a) {
+        double rx = 0.0, ry = 0.0, rz = 0.0;
+        if (live) {  // chunks congruent to k mod 8, ascending
+            constexpr int UR = 8;
+            const int cmin = sym_chunk_of_tile(P, (Ix * P.rb) / kSymCT);
+            for (int c0 = cmin + ((k - cmin) & 7); c0 < P.n_chunks; c0 += 8 * UR) {
+                double v[UR][3];
+#pragma unroll
+                for (int u = 0; u < UR; u++) {
+                    const int c = c0 + 8 * u;
+                    const bool on = c < P.n_chunks;
+                    const double *rp = rowpart + (size_t) (on ? c : 0) * 3 * plane + x;
+                    v[u][0] = on ? __ldcg(rp) : 0.0;
+                    v[u][1] = on ? __ldcg(rp + plane) : 0.0;
+                    v[u][2] = on ? __ldcg(rp + 2 * plane) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < UR; u++)
+                    if (c0 + 8 * u < P.n_chunks) { rx += v[u][0]; ry += v[u][1]; rz += v[u][2]; }
+            }
+        }
+        seg[0][k][tx] = rx; seg[1][k][tx] = ry; seg[2][k][tx] = rz;
+        __syncthreads();
+        if (cols_here && k == vx) {
             double sx = 0.0, sy = 0.0, sz = 0.0;
 #pragma unroll
             for (int j = 0; j < 8; j++) { sx += seg[0][j][tx]; sy += seg[1][j][tx]; sz += seg[2][j][tx]; }
             fx = sx + fx; fy = sy + fy; fz = sz + fz;
         }
-        // sharded over peer memory: the sum goes to the rank that owns vertex x, nobody else needs it
-        double *o = (X.on ? peer_fv[x / rows_per_rank] : fv) + (size_t) k * 3 * P.npad + x;
-        o[0] = fx;
-        o[P.npad] = fy;
-        o[2 * (size_t) P.npad] = fz;
     }
-    if (X.on) {  // xchg_signal expects a 1-D block: fold the 2-D index
-        __syncthreads();
-        if (tx == 0 && k == 0) {
-            __threadfence_system();
-            const unsigned int t = atomicAdd(X.tickets + XK_FV, 1u);
-            if (t == gridDim.x - 1) {
-                X.tickets[XK_FV] = 0;
-                __threadfence();
-                const unsigned long long e = X.state[XK_FV] + 1;
-                X.state[XK_FV] = e;
-                __threadfence_system();
-                for (int r = 0; r < X.world; r++) st_release_sys(X.peer_flags[r] + XK_FV * kMaxRanks + X.rank, e);
+    if (cols_here) {
+        const size_t off = fv_off + (size_t) k * 3 * plane + x;
+        if (!remote) {
+            double *o = fv + off;
+            o[0] = fx; o[plane] = fy; o[2 * plane] = fz;
+        } else if (!X.fv_bcast) {  // row-sharded plan: the sum goes to the rank that owns vertex x, nobody else needs it
+            double *o = peer_fv[x / rows_per_rank] + off;
+            o[0] = fx; o[plane] = fy; o[2 * plane] = fz;
+        } else {  // replicated integrator: every rank adds up all 8 sums of every vertex
+            for (int r = 0; r < X.world; r++) {
+                double *o = peer_fv[r] + off;
+                o[0] = fx; o[plane] = fy; o[2 * plane] = fz;
             }
         }
+    }
+    if (remote) {  // xchg_signal expects a 1-D block: fold the 2-D index
+        __syncthreads();
+        if (tx == 0 && slot == 0) xchg_signal_cta(X, XK_FV, gridDim.x);
     }
 }
 

@@ -9,10 +9,15 @@
 //             into flags[kind][my rank] of every rank;
 //   consumer: one warp spins (acquire loads) until flags[kind][r] has reached the next epoch for every r.
 // Epochs only grow and both sides count exchanges from zero, so nothing is reset between steps and the
-// kernels can be replayed from a CUDA graph unchanged. Three kinds per MD step: positions (k_kick_drift
-// -> everyone), pair-force sums of the virtual ranks (k_pair_reduce -> owner of the vertex), per-warp
-// kinetic energies (k_vertex -> everyone). A rank cannot run ahead by more than one exchange, which is
-// what makes the buffers safe to overwrite (Multi-GPU).
+// kernels can be replayed from a CUDA graph unchanged.
+//   Row-sharded plan, three kinds per MD step: positions (k_kick_drift -> everyone), pair-force sums of the
+//   virtual ranks (k_pair_reduce -> owner of the vertex), per-warp kinetic energies (k_vertex -> everyone).
+//   A rank cannot run ahead by more than one exchange, which makes the buffers safe to overwrite.
+//   Replicated-integrator plan, one kind per step: every rank broadcasts the sums of its virtual ranks
+//   (k_pair_reduce -> everyone) and integrates all vertices itself. The receive buffer is double-buffered
+//   on the parity of the epoch: a rank can be at most one exchange ahead of the slowest reader.
+// Every rank produces each exchange exactly once per force evaluation, so a consumer's next epoch is its
+// own producer epoch (Multi-GPU).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -23,11 +28,15 @@ enum { XK_POS = 0, XK_FV = 1, XK_KE = 2, XK_KINDS = 3 };
 
 struct Xchg {
     int world, rank;
-    int on;                                   // 0: single GPU or NCCL exchanges
+    int on;                                   // bit k set: exchange kind k goes over peer memory (0: single GPU or NCCL)
+    int fv_bcast;                             // 1: every rank receives every virtual-rank sum (replicated integrator)
+    int cta_fence_sys;                        // 1: every CTA fences at system scope before its ticket (see xchg_signal_cta)
     unsigned long long *const *peer_flags;    // [world] -> each rank's flags[XK_KINDS][kMaxRanks]
     unsigned long long *state;                // local: [kind] producer epoch, [XK_KINDS + kind] consumer epoch
     unsigned int *tickets;                    // local: [kind]
 };
+
+__device__ __forceinline__ bool xchg_has(const Xchg &X, const int kind) { return (X.on >> kind) & 1; }
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -38,21 +47,31 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
-// Called by every thread of every CTA of the producing kernel, after its remote stores.
-__device__ __forceinline__ void xchg_signal(const Xchg &X, const int kind, const unsigned int nblocks) {
-    __syncthreads();  // the CTA's remote stores happen-before thread 0's system-scope fence (fences are cumulative)
-    if (threadIdx.x == 0) {
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// One thread per CTA of the producing kernel, after a CTA barrier that follows the CTA's remote stores.
+// The CTA's stores are ordered before its ticket by a device-scope fence (fences are cumulative over the barrier);
+// the CTA that draws the last ticket has thereby observed every CTA's stores, fences once at system scope and
+// then publishes the new epoch to every rank with relaxed stores (fence + store = release pattern; causality order
+// is transitive across the two scopes). X.cta_fence_sys = 1 restores a system-scope fence in every CTA.
+__device__ __forceinline__ void xchg_signal_cta(const Xchg &X, const int kind, const unsigned int nblocks) {
+    if (X.cta_fence_sys) __threadfence_system(); else __threadfence();
+    const unsigned int t = atomicAdd(X.tickets + kind, 1u);
+    if (t == nblocks - 1) {
+        X.tickets[kind] = 0;
+        const unsigned long long e = X.state[kind] + 1;
+        X.state[kind] = e;
         __threadfence_system();
-        const unsigned int t = atomicAdd(X.tickets + kind, 1u);
-        if (t == nblocks - 1) {
-            X.tickets[kind] = 0;
-            __threadfence();
-            const unsigned long long e = X.state[kind] + 1;
-            X.state[kind] = e;
-            __threadfence_system();
-            for (int r = 0; r < X.world; r++) st_release_sys(X.peer_flags[r] + kind * kMaxRanks + X.rank, e);
-        }
+        for (int r = 0; r < X.world; r++) st_relaxed_sys(X.peer_flags[r] + kind * kMaxRanks + X.rank, e);
     }
+}
+
+// Called by every thread of every CTA (1-D block) of the producing kernel, after its remote stores.
+__device__ __forceinline__ void xchg_signal(const Xchg &X, const int kind, const unsigned int nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) xchg_signal_cta(X, kind, nblocks);
 }
 
 // One warp: waits until every rank's signal of the next epoch of `kind` has arrived. Returns to all lanes.
@@ -66,6 +85,22 @@ __device__ __forceinline__ void xchg_wait_warp(const Xchg &X, const int kind) {
     __syncwarp();
     if (lane == 0) X.state[XK_KINDS + kind] = e;
     __threadfence();
+}
+
+// One warp of any CTA of the consuming kernel: waits for every rank's signal of the exchange this rank itself
+// produced last (its own producer epoch; valid because every rank produces each exchange exactly once per force
+// evaluation and this rank's producer precedes the consumer in stream order). No state is written, so any
+// number of CTAs may call it. Returns the epoch to all lanes.
+__device__ __forceinline__ unsigned long long xchg_wait_own_epoch(const Xchg &X, const int kind) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long e = X.state[kind];
+    if (lane < X.world) {
+        const unsigned long long *f = X.peer_flags[X.rank] + kind * kMaxRanks + lane;
+        while (ld_acquire_sys(f) < e) __nanosleep(32);
+    }
+    __syncwarp();
+    __threadfence();
+    return e;
 }
 
 __global__ void k_xchg_wait(const Xchg X, const int kind) {

@@ -14,5 +14,9 @@ with capi.Context(w.mesh.edges, w.mesh.faces, w.params["l0"], P, n_vertices=w.n_
         ctx.set_pair_plan(int(sys.argv[3]), int(sys.argv[4]))
     ctx.force_init()
     ctx.step(steps)
+    if os.environ.get("NPSL_PROFILE_SEGMENTS"):
+        print(ctx.step_profile(20))
+        ctx.sync()
+        print("graph ms/step", ctx.step_timing(200, flush_l2=True) / 200)
     e = ctx.energy()
     print("ok", name, steps, "steps, E =", e["energy"], ctx.pair_geometry())
