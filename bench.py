@@ -282,13 +282,19 @@ def run_b200(args) -> None:
     dfma_peak = max_over_ranks(dfma_peak) if world > 1 else dfma_peak
     pairs_per_launch = (hi - lo) * (n - 1)
     mode = ctx.pair_mode()
-    ctx_pair_mode, ctx_xchg_mode = mode, ctx.exchange_mode()
+    ctx_pair_mode, ctx_xchg_mode, ctx_shard_plan = mode, ctx.exchange_mode(), ctx.shard_plan()
     # the symmetric kernel's launch covers this rank's share (1/world) of all unordered pairs
     pairs_per_launch = n * (n - 1) // world if mode == 2 else pairs_per_launch
     achieved_dfma = pairs_per_launch * DFMA_PER_PAIR[mode] / (pair_ms * 1e-3) if pair_ms > 0 else 0.0
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    traffic = None
+    try:  # per-launch DRAM bytes of the dominant kernel from the committed ncu capture of this workload, if any
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("%s:%d" % (args.workload, world), {}).get("bytes")
     except Exception:
         pass
 
@@ -308,8 +314,11 @@ def run_b200(args) -> None:
         "config": {
             "workload": args.workload, "vertices": n, "edges": w.mesh.n_edges, "faces": w.mesh.n_faces,
             "ordered_pairs_per_step": n * (n - 1), "reference_cli": w.cli,
-            "sharding": "units of the pair term (8 virtual ranks) and owned vertices split over %d GPU(s); positions, "
-                        "pair-force sums and kinetic-energy partials exchanged each step" % world if world > 1 else "single GPU",
+            "sharding": {0: "single GPU",
+                         1: "rows: units of the pair term (8 virtual ranks) and owned vertices split over %d GPUs; positions, "
+                            "pair-force sums and kinetic-energy partials exchanged each step" % world,
+                         2: "replicated integrator: units of the pair term (8 virtual ranks) split over %d GPUs, every GPU "
+                            "integrates all vertices; one exchange (pair-force sums) per step" % world}[ctx_shard_plan],
             "l2": "flushed between timed steps (256 MiB memset outside each step's CUDA-event bracket); "
                   "ms_per_step = sum of the per-step brackets / K, max over ranks",
             "pair_plan": geo, "pair_kernel": {1: "ordered (k_pair)", 2: "symmetric (k_pair_sym)"}[ctx_pair_mode],
@@ -324,7 +333,7 @@ def run_b200(args) -> None:
                 "call": "npsl_md_step_host: posvec/velvec/forvec host->device, one step, device->host, wall clock"},
         "roofline": {
             "bound": "fp64", "achieved": 2e-12 * achieved_dfma, "peak": 2e-12 * dfma_peak, "unit": "TFLOP/s",
-            "frac": achieved_dfma / dfma_peak if dfma_peak else None, "traffic": None,
+            "frac": achieved_dfma / dfma_peak if dfma_peak else None, "traffic": traffic,
             "kernel": "k_pair_sym<4,128,3> (each unordered pair once, applied to both vertices)" if mode == 2
                       else "k_pair<%d,false>" % geo["rows_per_thread"],
             "kernel_ms": pair_ms, "kernel_launches_timed": pair_count,

@@ -162,31 +162,69 @@ __device__ __forceinline__ double canonical_sum(const double *__restrict__ p, in
     return v[0];
 }
 
-// End of a force evaluation, called by the first two lanes of the block that holds the total kinetic
-// energy: lane 0 advances the mesh chain, lane 1 the ion chain (they are independent, src/newmd.cpp:99-110).
+// One sweep of update_chain_xi over a chain held one link per lane (lanes [0,16) mesh chain, [16,32) ion chain;
+// link j in lane j of its half). The arithmetic is the reference's, operation for operation:
+//   xi_j <- xi_j exp(-dt/2 xi_{j+1}) + (dt/2 1/Q_j) drive_j exp(-dt/4 xi_{j+1}),
+//   drive_0 = 2 KE - dof_0 T_0,   drive_j = Q_{j-1} xi_{j-1}^2 - dof_j T_j          (src/functions.h:176-189)
+// FORWARD (j ascending, src/newmd.cpp:161-170): xi_{j+1} is still the old value, so both exponentials of every
+// link are evaluated in parallel before the sweep and only the drive is serial. Reverse (j descending,
+// src/newmd.cpp:99-110): xi_{j+1} has just been updated, so the exponentials are part of the serial chain.
+template <bool FORWARD>
+__device__ __forceinline__ void chain_sweep(BathLink &b, const int j, const int n, const double dt, const double ke) {
+    const unsigned int full = 0xffffffffu;
+    const bool real = j < n && b.Q != 0;
+    const double c = real ? 0.5 * dt * (1.0 / b.Q) : 0.0;
+    const double dofT = b.dof * b.T;
+    double e1 = 1.0, e2 = 1.0;
+    if (FORWARD) {
+        double xn = __shfl_down_sync(full, b.xi, 1, 16);
+        if (j + 1 >= n) xn = 0.0;
+        if (real) { e1 = exp(-0.5 * dt * xn); e2 = exp(-0.25 * dt * xn); }
+    }
+    for (int it = 0; it < n; it++) {
+        const int cur = FORWARD ? it : n - 1 - it;
+        const double xp = __shfl_up_sync(full, b.xi, 1, 16), Qp = __shfl_up_sync(full, b.Q, 1, 16);
+        double xn = __shfl_down_sync(full, b.xi, 1, 16);
+        if (j == cur && real) {
+            if (!FORWARD) {
+                if (j + 1 >= n) xn = 0.0;
+                e1 = exp(-0.5 * dt * xn);
+                e2 = exp(-0.25 * dt * xn);
+            }
+            const double drive = (j == 0) ? (2 * ke - dofT) : (Qp * xp * xp - dofT);
+            b.xi = b.xi * e1 + c * drive * e2;
+        }
+    }
+}
+
+// End of a force evaluation, called by warp 0 of the block that holds the total kinetic energy; lanes [0,16) carry
+// the mesh chain, lanes [16,32) the ion chain (they are independent, src/newmd.cpp:99-110), one link per lane.
 // Inside a step: forward half-chain, th_mid -> th_cur (src/newmd.cpp:161-170). Always: the reverse half-chain
 // of the step that may follow from th_cur into th_mid, with exp(-dt/2 xi_0) and dt/2 sqrt(.) left in the
 // scalar block, so that k_kick_drift is a pure streaming kernel.
 __device__ __forceinline__ void thermo_finish(Thermo *th_mid, Thermo *th_cur, double *scal, const double ke_mesh,
                                               const bool step, const MeshParams &P) {
-    const int who = threadIdx.x;  // 0: mesh chain, 1: ion chain
-    if (who > 1) return;
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x, who = lane >> 4, j = lane & 15;  // who 0: mesh chain, 1: ion chain
     BathLink *mid = who == 0 ? th_mid->mesh : th_mid->ions;
     BathLink *cur = who == 0 ? th_cur->mesh : th_cur->ions;
     const double ke = who == 0 ? ke_mesh : 0.0;
     const int n = P.chain;
+    const double dt = P.dt;
+    BathLink b = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (j < n) b = step ? mid[j] : cur[j];
     if (step) {  // th_mid -> (eta, then xi forward) -> th_cur
-        for (int j = 0; j < n; j++) cur[j] = mid[j];
-        chain_eta(cur, n, P.dt);
-        for (int j = 0; j < n; j++) chain_xi(cur, j, n, P.dt, ke);
+        if (j < n && b.Q != 0) b.eta = b.eta + 0.5 * dt * b.xi;
+        chain_sweep<true>(b, j, n, dt, ke);
+        if (j < n) cur[j] = b;
     }
-    for (int j = 0; j < n; j++) mid[j] = cur[j];
-    for (int j = n - 1; j > -1; j--) chain_xi(mid, j, n, P.dt, ke);
-    chain_eta(mid, n, P.dt);
-    if (who == 0) {
-        const double ef = exp(-0.5 * P.dt * mid[0].xi);
+    chain_sweep<false>(b, j, n, dt, ke);
+    if (j < n && b.Q != 0) b.eta = b.eta + 0.5 * dt * b.xi;
+    if (j < n) mid[j] = b;
+    if (lane == 0) {
+        const double ef = exp(-0.5 * dt * b.xi);
         scal[SC_EXPFAC] = ef;
-        scal[SC_KICK] = 0.5 * P.dt * sqrt(ef);
+        scal[SC_KICK] = 0.5 * dt * sqrt(ef);
     }
 }
 
@@ -415,7 +453,7 @@ k_vertex_mesh(const double4 *__restrict__ xyzq, const double4 *__restrict__ bslo
 // Tail shared by k_vertex and k_rattle_apply: per-warp kinetic-energy partials, (FORCE) pair-energy sums,
 // exchange signal, and in the last block the total kinetic energy and the thermostat.
 template <bool ENERGIES, bool STEP>
-__device__ __forceinline__ void vertex_tail(double (&acc)[3], double *__restrict__ partials, unsigned int *__restrict__ ticket,
+__device__ __forceinline__ bool vertex_tail(double (&acc)[3], double *__restrict__ partials, unsigned int *__restrict__ ticket,
                                             double *__restrict__ scal, double *__restrict__ ke_warp, int n_ke_warps,
                                             Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur,
                                             double *const *__restrict__ peer_ke, const Xchg &X, const MeshParams &P,
@@ -448,7 +486,7 @@ __device__ __forceinline__ void vertex_tail(double (&acc)[3], double *__restrict
     __syncthreads();  // every warp's ke_warp store precedes thread 0's fence + ticket
     if (threadIdx.x == 0) s_last = take_last_ticket(ticket, nblocks);
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) return false;
     if (ENERGIES) {
         double tot[2] = {0, 0};
         for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
@@ -463,7 +501,7 @@ __device__ __forceinline__ void vertex_tail(double (&acc)[3], double *__restrict
         }
         __syncthreads();
     }
-    if (P.n_ranks > 1) return;  // sharded: k_ke_post finishes after the exchange of ke_warp
+    if (P.n_ranks > 1) return false;  // sharded: k_ke_post finishes after the exchange of ke_warp
     const double ke = canonical_sum(ke_warp, n_ke_warps, red);
     if (threadIdx.x == 0) {
         scal[SC_KE] = ke;
@@ -471,6 +509,7 @@ __device__ __forceinline__ void vertex_tail(double (&acc)[3], double *__restrict
     }
     __syncthreads();
     thermo_finish(th_mid, th_cur, scal, red[0], STEP, P);
+    return true;
 }
 
 template <int MODE>
@@ -485,7 +524,6 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
     __shared__ double red[3 * 32];
     __shared__ bool s_last;
     __shared__ size_t s_fv_off;
-    const int nblocks = gridDim.x;
     const int i = P.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
     double acc[3] = {0, 0, 0};  // ke, es energy, lj energy
     // Sums of the virtual ranks that arrive over peer memory: wait here (one warp per CTA polls the arrival
@@ -518,7 +556,7 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
                     fp.x += a.x; fp.y += a.y; fp.z += a.z; ue += a.w;
                 }
             }
-            const double cq = P.pair_coef * __ldg(&xyzq[i].w);
+            const double cq = P.pair_coef * __ldcg(&xyzq[i].w);
             fp.x *= cq; fp.y *= cq; fp.z *= cq;
             ue *= 0.5 * cq;
         }
