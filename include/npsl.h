@@ -192,6 +192,21 @@ int npsl_constraint_multipliers(npsl_ctx *ctx, double *shake_lambda, double *rat
 
 /* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
 int64_t npsl_launch_count(const npsl_ctx *ctx);
+/* ---- data feeds of the reference's writers ----------------------------------------------------------------
+ * Vertex areas (1/3 of the incident face areas) and unit normals (area-weighted face normals), i.e.
+ * VERTEX::compute_area_normal for every vertex (src/vertex.cpp:7-18; src/interface.cpp:39-41, src/newmd.cpp:232-235)
+ * at the positions on the device: area[n], normal[n][3]; either may be NULL. interface_movie prints the area and
+ * charge / area per vertex (src/functions.cpp:50-84). */
+int npsl_vertex_geometry(npsl_ctx *ctx, double *area, double *normal);
+/* Per-face energy maps of INTERFACE::compute_local_energies and compute_local_energies_by_component
+ * (src/interface.cpp:1140-1337) at the positions on the device, one value per face (the g channel of the
+ * reference's local_*_E.off files): electrostatic = sum over the face's vertices of their pair energy with every other
+ * vertex; bending / stretching = sum over the face's three edges (stretching in its l0 form, as the reference does
+ * here whatever -B says); elastic = stretching + bending. Any output may be NULL. Needs a force evaluation at the
+ * current positions (npsl_force_init / npsl_force / npsl_energy); runs the energy-enabled pass itself when the last
+ * evaluation did not keep the per-vertex energies. */
+int npsl_local_energies(npsl_ctx *ctx, double *electrostatic, double *elastic, double *bending, double *stretching);
+
 /* Average device time of the pair kernel over the launches since the last reset, measured with
  * CUDA events on the context's stream when timing is enabled. */
 int npsl_pair_timing(npsl_ctx *ctx, int enable);

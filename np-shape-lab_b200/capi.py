@@ -26,7 +26,7 @@ SYMBOLS = [
     "npsl_force", "npsl_step", "npsl_energy", "npsl_sync", "npsl_launch_count", "npsl_pair_timing",
     "npsl_pair_timing_read", "npsl_owned_rows", "npsl_pair_geometry", "npsl_fp64_peak", "npsl_md_run",
     "npsl_step_timing", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_md_step_host", "npsl_set_pair_mode",
-    "npsl_pair_mode", "npsl_exchange_mode", "npsl_shard_plan", "npsl_step_profile", "npsl_set_volume_constraint", "npsl_constraint_init",
+    "npsl_pair_mode", "npsl_exchange_mode", "npsl_shard_plan", "npsl_vertex_geometry", "npsl_local_energies", "npsl_step_profile", "npsl_set_volume_constraint", "npsl_constraint_init",
     "npsl_constraint_multipliers",
 ]
 
@@ -116,6 +116,8 @@ def load() -> C.CDLL:
     L.npsl_pair_mode.argtypes = [vp]
     L.npsl_exchange_mode.argtypes = [vp]
     L.npsl_shard_plan.argtypes = [vp]
+    L.npsl_vertex_geometry.argtypes = [vp, dp, dp]
+    L.npsl_local_energies.argtypes = [vp, dp, dp, dp, dp]
     L.npsl_set_volume_constraint.argtypes = [vp, C.c_int]
     L.npsl_constraint_init.argtypes = [vp]
     L.npsl_constraint_multipliers.argtypes = [vp, dp, dp]
@@ -369,6 +371,18 @@ class Context:
         a, b = C.c_double(), C.c_double()
         self._ck(self.L.npsl_constraint_multipliers(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def vertex_geometry(self) -> dict:
+        """VERTEX::itsarea / itsnormal of every vertex at the positions on the device (src/vertex.cpp:7-18)."""
+        area, normal = np.zeros(self.nv), np.zeros((self.nv, 3))
+        self._ck(self.L.npsl_vertex_geometry(self.h, _dp(area), _dp(normal)))
+        return {"area": area, "normal": normal}
+
+    def local_energies(self) -> dict:
+        """Per-face energy maps of INTERFACE::compute_local_energies(_by_component), src/interface.cpp:1140-1337."""
+        out = {k: np.zeros(self.nf) for k in ("electrostatic", "elastic", "bending", "stretching")}
+        self._ck(self.L.npsl_local_energies(self.h, *[_dp(out[k]) for k in ("electrostatic", "elastic", "bending", "stretching")]))
+        return out
 
     def shard_plan(self) -> int:
         """0 single GPU, 1 rows (owned vertex slices), 2 replicated integrator (only the pair term is split)."""

@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(kMeshThreads)
 k_mesh(const double4 *__restrict__ xyzq, const int4 *__restrict__ face_v, const int4 *__restrict__ edge_rec,
        const double *__restrict__ l0, double4 *__restrict__ bslot, double *__restrict__ partials /* [4][nblocks] */,
        unsigned int *__restrict__ ticket, double *__restrict__ scal, double4 *__restrict__ face_dir_area,
-       double *__restrict__ face_vol, double *__restrict__ edge_S, int n_face_blocks, const MeshParams P) {
+       double *__restrict__ face_vol, double *__restrict__ edge_S, double2 *__restrict__ edge_E, int n_face_blocks,
+       const MeshParams P) {
     __shared__ double red[4 * 32];
     __shared__ bool s_last;
     const int nblocks = gridDim.x;
@@ -324,7 +325,14 @@ k_mesh(const double4 *__restrict__ xyzq, const int4 *__restrict__ face_v, const 
             bslot[P.ne + e] = make_double4(kb * (t10.x + t11.x), kb * (t10.y + t11.y), kb * (t10.z + t11.z), 0.0);
             bslot[2 * P.ne + e] = make_double4(kb * ta.x, kb * ta.y, kb * ta.z, 0.0);
             bslot[3 * P.ne + e] = make_double4(kb * tb.x, kb * tb.y, kb * tb.z, 0.0);
-            if (STORE) edge_S[e] = S;
+            if (STORE) {
+                edge_S[e] = S;
+                // per-edge energies of the local maps (INTERFACE::compute_local_energies, src/interface.cpp:1198-1209):
+                // bending, and stretching always in its l0 form whatever -B says
+                const double le = __ldg(l0 + e), st = sqrt(dot(e01, e01)) - le;
+                edge_E[e] = make_double2(P.bkappa * (1.0 - S * inv_n0n1),
+                                         (0.5 * P.sconstant * st * st / (le * le)) * (P.avg_edge * P.avg_edge));
+            }
             if (ENERGY) {
                 acc[2] = P.bkappa * (1.0 - S * inv_n0n1);
                 const double l = sqrt(dot(e01, e01));
@@ -384,6 +392,7 @@ struct VertexTables {
 
 struct ForceComponents {  // FORCE mode only
     double4 *pair, *bend, *stretch, *tension, *voltension;
+    double2 *vertex_e;  // (electrostatic, LJ) energy of the vertex: half its sum over all partners
 };
 
 template <int MODE>
@@ -577,6 +586,7 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
             vel[i] = v;
         } else {
             C.pair[i] = make_double4(fp.x, fp.y, fp.z, 0.0);
+            C.vertex_e[i] = make_double2(ue, ulj);
             acc[1] = ue;
             acc[2] = ulj;
         }
@@ -741,6 +751,57 @@ k_rattle_apply(double4 *__restrict__ vel, const double4 *__restrict__ ngv, doubl
         acc[0] = 0.5 * (v.x * v.x + v.y * v.y + v.z * v.z);
     }
     vertex_tail<false, !INIT>(acc, partials, ticket, scal, ke_warp, n_ke_warps, th_mid, th_cur, nullptr, X, P, red, &s_last);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Data feeds of the reference's writers.
+//
+// k_vertex_geometry: VERTEX::compute_area_normal (src/vertex.cpp:7-18) -- area = 1/3 of the incident face areas,
+// normal = normalised sum of area-weighted face normals (normal_F * A_F = direction_F / 2, src/face.cpp:16-26) --
+// gathered over the one-ring; consumed by interface_movie (Va and Vq/a columns of p.lammpstrj, src/functions.cpp:50-84).
+__global__ void __launch_bounds__(kMeshThreads)
+k_vertex_geometry(const double4 *__restrict__ xyzq, const VertexTables T, double4 *__restrict__ out /* nx ny nz area */,
+                  const MeshParams P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nv) return;
+    const int nv = P.nv;
+    const V3 p = ld3(xyzq, i);
+    const int deg = __ldg(T.degree + i);
+    const V3 pfirst = ld3(xyzq, __ldg(T.ring + i));
+    V3 pn = pfirst, ns = mk(0, 0, 0);
+    double area = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxDeg; k++) {
+        if (k >= deg) break;
+        const V3 pnn = (k + 1 < deg) ? ld3(xyzq, __ldg(T.ring + (k + 1) * nv + i)) : pfirst;
+        const V3 dir = cross(sub(pn, p), sub(pnn, pn));  // face (p, pn, pnn) in its stored orientation
+        ns.x += 0.5 * dir.x; ns.y += 0.5 * dir.y; ns.z += 0.5 * dir.z;
+        area += 0.5 * sqrt(dot(dir, dir));
+        pn = pnn;
+    }
+    const double inv = 1.0 / sqrt(dot(ns, ns));
+    out[i] = make_double4(ns.x * inv, ns.y * inv, ns.z * inv, area * (1. / 3.));
+}
+
+// k_local_faces: the per-face energy maps of INTERFACE::compute_local_energies / _by_component
+// (src/interface.cpp:1140-1337). The reference adds every unordered pair energy to the faces of both vertices and
+// every edge energy to the edge's two faces; gathered by face that is
+//   es[F] = sum_{v in F} sum_{j != v} E_es(v, j) = sum_{v in F} 2 * (vertex_e of the energy pass),
+//   bending[F] / stretching[F] = sum over the three edges of F,   elastic = stretching + bending.
+// face_e holds the three edge indices of a face in ascending order (the order in which the reference's edge loop
+// reaches the face).
+__global__ void __launch_bounds__(kMeshThreads)
+k_local_faces(const int4 *__restrict__ face_v, const int4 *__restrict__ face_e, const double2 *__restrict__ vertex_e,
+              const double2 *__restrict__ edge_E, double4 *__restrict__ out /* es elastic bending stretching */,
+              const MeshParams P) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= P.nf) return;
+    const int4 v = __ldg(face_v + f), e = __ldg(face_e + f);
+    const double es = 2.0 * vertex_e[v.x].x + 2.0 * vertex_e[v.y].x + 2.0 * vertex_e[v.z].x;
+    const double2 a = edge_E[e.x], b = edge_E[e.y], c = edge_E[e.z];
+    double el = 0;
+    el += a.y; el += a.x; el += b.y; el += b.x; el += c.y; el += c.x;  // stretching then bending, edge by edge
+    out[f] = make_double4(es, el, a.x + b.x + c.x, a.y + b.y + c.y);
 }
 
 // ------------------------------------------------------------------------------------------------

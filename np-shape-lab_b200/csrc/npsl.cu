@@ -101,6 +101,11 @@ struct npsl_ctx {
     unsigned int *tickets = nullptr;
     double4 *face_dir_area = nullptr;
     double *face_vol = nullptr, *edge_S = nullptr;
+    // data feeds of the writers (local energy maps, vertex areas / normals)
+    double2 *edge_E = nullptr, *vertex_e = nullptr;
+    int4 *face_e = nullptr;
+    double4 *face_local = nullptr, *vertex_geo = nullptr;
+    bool local_valid = false;  // vertex_e / edge_E hold the energy pass at the current positions
     double *peak_out = nullptr;
 
     // launch geometry
@@ -208,7 +213,7 @@ inline uint64_t dkey(int a, int b) { return ((uint64_t) (uint32_t) a << 32) | (u
 
 // Static topology tables consumed by k_mesh / k_vertex (layout described in mesh_kernels.cuh).
 struct Tables {
-    std::vector<int4> face_v, edge_rec;
+    std::vector<int4> face_v, edge_rec, face_e;
     std::vector<int> degree, ring, bslot_ref;
     std::vector<double> ring_l0;
 };
@@ -254,6 +259,18 @@ int build_tables(const npsl_mesh_desc *m, Tables &t, std::string &why) {
         ecnt[v1]++;
     }
     if ((size_t) ne * 2 != third.size()) { why = "edge / face counts inconsistent"; return -1; }
+    // the three edges of every face, ascending edge index
+    t.face_e.resize(nf);
+    for (int f = 0; f < nf; f++) {
+        const int32_t *fv = m->face_v + 3 * f;
+        int es[3];
+        for (int k = 0; k < 3; k++) {
+            const int a = fv[k], b = fv[(k + 1) % 3];
+            es[k] = edge_of.at(dkey(std::min(a, b), std::max(a, b)));
+        }
+        std::sort(es, es + 3);
+        t.face_e[f] = make_int4(es[0], es[1], es[2], 0);
+    }
     // one-rings, counter-clockwise, starting at the first incident face in file order
     t.degree.assign(nv, 0);
     t.ring.assign((size_t) kMaxDeg * nv, -1);
@@ -452,8 +469,9 @@ void launch_pair(npsl_ctx *c, bool energy, cudaStream_t s) {
 // context's streams. Used both for direct execution and under stream capture.
 int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
     const VertexTables vt = {c->degree, c->ring, c->ring_l0, c->bslot_ref};
-    const ForceComponents fc = {c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4]};
+    const ForceComponents fc = {c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->vertex_e};
     int n = 0;
+    if (!step) c->local_valid = energy && store;
     auto mark = [&](const char *name) {
         if (!c->prof) return;
         if (c->prof_used == c->prof_ev.size()) {
@@ -502,7 +520,7 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
 #define MESH(E, S)                                                                                              \
     k_mesh<E, S><<<grid, kMeshThreads, 0, c->s_side>>>(c->xyzq, c->face_v, c->edge_rec, c->l0, c->bslot,         \
                                                        c->part_mesh, tk, c->scal, c->face_dir_area, c->face_vol, \
-                                                       c->edge_S, c->n_face_blocks, c->mp)
+                                                       c->edge_S, c->edge_E, c->n_face_blocks, c->mp)
         if (energy && store) MESH(true, true);
         else if (energy) MESH(true, false);
         else if (store) MESH(false, true);
@@ -882,6 +900,9 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     CUB(dalloc(&c->th_cur, 1)); CUB(dalloc(&c->th_mid, 1));
     CUB(dalloc(&c->tickets, 4));
     CUB(dalloc(&c->face_dir_area, c->nf)); CUB(dalloc(&c->face_vol, c->nf)); CUB(dalloc(&c->edge_S, c->ne));
+    CUB(dalloc(&c->edge_E, c->ne)); CUB(dalloc(&c->vertex_e, nrec)); CUB(dalloc(&c->face_e, c->nf));
+    CUB(dalloc(&c->face_local, c->nf)); CUB(dalloc(&c->vertex_geo, c->nv));
+    CUB(cudaMemcpy(c->face_e, tb.face_e.data(), sizeof(int4) * c->nf, cudaMemcpyHostToDevice));
     CUB(dalloc(&c->peak_out, 1));
     CUB(cudaMemcpy(c->face_v, tb.face_v.data(), sizeof(int4) * c->nf, cudaMemcpyHostToDevice));
     CUB(cudaMemcpy(c->edge_rec, tb.edge_rec.data(), sizeof(int4) * c->ne, cudaMemcpyHostToDevice));
@@ -1025,7 +1046,7 @@ void npsl_destroy(npsl_ctx *c) {
     void *ptrs[] = {c->xyzq, c->vel, c->force, c->fmesh, c->ngv, c->part_con, c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->face_v,
                     c->edge_rec, c->l0, c->degree, c->ring, c->bslot_ref, c->ring_l0, c->bslot, c->pair_partial,
                     c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_warp, c->th_cur, c->th_mid, c->part_mesh,
-                    c->part_vert, c->tickets, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units, c->red_groups,
+                    c->part_vert, c->tickets, c->edge_E, c->vertex_e, c->face_e, c->face_local, c->vertex_geo, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units, c->red_groups,
                     c->sym_rowpart, c->sym_colpart, c->sym_fv, c->xflags, c->xstate, c->xtickets,
                     c->d_peer_xyzq, c->d_peer_fv, c->d_peer_ke, c->d_peer_flags};
     for (void *p : ptrs)
@@ -1047,7 +1068,7 @@ int npsl_upload_state(npsl_ctx *c, const double *pos, const double *vel, const d
     const int n = c->nv;
     int r;
     if ((r = upload_records(c, c->xyzq, pos, true, 0))) return r;
-    if (pos) c->forces_valid = false;
+    if (pos) c->forces_valid = c->local_valid = false;
     if ((r = upload_records(c, c->vel, vel, false, 1))) return r;
     if (q) {
         CU(cudaStreamSynchronize(c->s_main));
@@ -1056,6 +1077,7 @@ int npsl_upload_state(npsl_ctx *c, const double *pos, const double *vel, const d
         k_scatter_w<<<(n + 255) / 256, 256, 0, c->s_main>>>(c->xyzq, c->d_pack[0], n);
         c->launches++;
         c->all_q_zero = true;
+        c->local_valid = false;
         for (int i = 0; i < n; i++)
             if (q[i] != 0.0) { c->all_q_zero = false; break; }
         const int use = c->all_q_zero ? 0 : 1;
@@ -1146,7 +1168,7 @@ int npsl_dressup(npsl_ctx *c, double *total_area, double *total_volume) {
     if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
     k_mesh<false, true><<<c->n_face_blocks + c->n_edge_blocks, kMeshThreads, 0, c->s_main>>>(
         c->xyzq, c->face_v, c->edge_rec, c->l0, c->bslot, c->part_mesh, c->tickets, c->scal, c->face_dir_area,
-        c->face_vol, c->edge_S, c->n_face_blocks, c->mp);
+        c->face_vol, c->edge_S, c->edge_E, c->n_face_blocks, c->mp);
     c->launches++;
     double s[2];
     CU(cudaMemcpyAsync(s, c->scal + SC_AREA, sizeof s, cudaMemcpyDeviceToHost, c->s_main));
@@ -1178,6 +1200,7 @@ int npsl_step(npsl_ctx *c, int n_steps) {
     if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
     if (n_steps < 0) return fail(c, NPSL_ERR_ARG, "n_steps < 0");
     if (!c->forces_valid) return fail(c, NPSL_ERR_STATE, "npsl_step before npsl_force_init");
+    if (n_steps > 0) c->local_valid = false;
     if (c->timing) {
         for (int k = 0; k < n_steps; k++) {
             if (c->t_used + 2 > c->t_ev.size()) {
@@ -1296,6 +1319,7 @@ int npsl_md_step_host(npsl_ctx *c, double *pos, double *vel, double *force, int 
     }
     c->launches += 3;
     c->forces_valid = true;  // the caller's forvec is the force at the caller's posvec (src/newmd.cpp:114-117)
+    c->local_valid = false;
     for (int k = 0; k < n_steps; k++) CU(cudaGraphLaunch(c->step_graph, c->s_main));
     c->launches += (int64_t) c->launches_per_step * n_steps;
     for (int k = 0; k < 3; k++) {
@@ -1322,6 +1346,51 @@ int npsl_sync(npsl_ctx *c) {
     CU(cudaStreamSynchronize(c->s_main));
     CU(cudaGetLastError());
     return collect_timing(c);
+}
+
+// ---- data feeds of the writers -------------------------------------------------------
+
+int npsl_vertex_geometry(npsl_ctx *c, double *area, double *normal) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    const VertexTables vt = {c->degree, c->ring, c->ring_l0, c->bslot_ref};
+    k_vertex_geometry<<<(c->nv + kMeshThreads - 1) / kMeshThreads, kMeshThreads, 0, c->s_main>>>(c->xyzq, vt, c->vertex_geo, c->mp);
+    c->launches++;
+    std::vector<double4> tmp(c->nv);
+    CU(cudaMemcpyAsync(tmp.data(), c->vertex_geo, sizeof(double4) * c->nv, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    CU(cudaGetLastError());
+    for (int i = 0; i < c->nv; i++) {
+        if (area) area[i] = tmp[i].w;
+        if (normal) { normal[3 * i] = tmp[i].x; normal[3 * i + 1] = tmp[i].y; normal[3 * i + 2] = tmp[i].z; }
+    }
+    return NPSL_OK;
+}
+
+int npsl_local_energies(npsl_ctx *c, double *electrostatic, double *elastic, double *bending, double *stretching) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    if (!c->forces_valid) return fail(c, NPSL_ERR_STATE, "npsl_local_energies before npsl_force_init");
+    if (!c->local_valid) {  // an energy-enabled, storing force pass at the current positions
+        int r = force_pass(c);
+        if (r) return r;
+    }
+    if (c->world > 1 && !c->replicated) {  // row-sharded: the per-vertex energies of the other ranks' rows
+        NC(g_nccl.AllGather(c->vertex_e + (size_t) c->rank * c->range, c->vertex_e, (size_t) c->range * 2, ncclFloat64_, c->comm,
+                            c->s_main));
+    }
+    k_local_faces<<<c->n_face_blocks, kMeshThreads, 0, c->s_main>>>(c->face_v, c->face_e, c->vertex_e, c->edge_E, c->face_local,
+                                                                    c->mp);
+    c->launches++;
+    std::vector<double4> tmp(c->nf);
+    CU(cudaMemcpyAsync(tmp.data(), c->face_local, sizeof(double4) * c->nf, cudaMemcpyDeviceToHost, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
+    CU(cudaGetLastError());
+    for (int f = 0; f < c->nf; f++) {
+        if (electrostatic) electrostatic[f] = tmp[f].x;
+        if (elastic) elastic[f] = tmp[f].y;
+        if (bending) bending[f] = tmp[f].z;
+        if (stretching) stretching[f] = tmp[f].w;
+    }
+    return NPSL_OK;
 }
 
 // ---- introspection -----------------------------------------------------------------------------------
@@ -1355,6 +1424,7 @@ int npsl_step_timing(npsl_ctx *c, int n_steps, int flush_l2, double *total_ms) {
     if (!c || !total_ms) return fail(c, NPSL_ERR_ARG, "NULL argument");
     if (n_steps < 1) return fail(c, NPSL_ERR_ARG, "n_steps < 1");
     if (!c->forces_valid) return fail(c, NPSL_ERR_STATE, "npsl_step_timing before npsl_force_init");
+    c->local_valid = false;
     int r = ensure_graph(c);
     if (r) return r;
     if (c->s_ev.size() < 2) {
@@ -1404,6 +1474,7 @@ int npsl_step_timing(npsl_ctx *c, int n_steps, int flush_l2, double *total_ms) {
 int npsl_step_profile(npsl_ctx *c, int n_steps, char *out, int out_len) {
     if (!c || !out || out_len < 64) return fail(c, NPSL_ERR_ARG, "bad argument");
     if (!c->forces_valid) return fail(c, NPSL_ERR_STATE, "npsl_step_profile before npsl_force_init");
+    c->local_valid = false;
     std::vector<double> sum;
     std::vector<const char *> names;
     for (int k = 0; k < n_steps; k++) {

@@ -201,6 +201,39 @@ class INTERFACE:
                                                         e["lj"], e["electrostatic"], e["volume"]))
 
 
+    def compute_vertex_area_normals(self) -> None:
+        """VERTEX::compute_area_normal for every vertex (src/vertex.cpp:7-18; src/newmd.cpp:232-235)."""
+        if self._ctx is None:
+            raise capi.NpslError(-4, "compute_vertex_area_normals before the device context exists")
+        geo = self._ctx.vertex_geometry()
+        self.itsarea, self.itsnormal = geo["area"], geo["normal"]
+
+    def compute_local_energies(self, scalefactor: float, outdir: Optional[str] = None) -> dict:
+        """src/interface.cpp:1140-1232: per-face electrostatic and elastic energy maps; with ``outdir`` also the
+        reference's ``local_electrostatic_E.off`` / ``local_elastic_E.off`` (colormap = (0, E, 1 - E, 1))."""
+        return self._local_maps(("electrostatic", "elastic"), outdir)
+
+    def compute_local_energies_by_component(self, outdir: Optional[str] = None) -> dict:
+        """src/interface.cpp:1235-1337: the stretching and bending maps separately."""
+        return self._local_maps(("stretching", "bending"), outdir)
+
+    def _local_maps(self, keys, outdir) -> dict:
+        if self._ctx is None:
+            raise capi.NpslError(-4, "local energy maps before the first force call")
+        loc = self._ctx.local_energies()
+        pos = self._ctx.download_state(vel=False, force=False)["pos"]
+        for k in keys:
+            print("%s range\t%g\t%g" % (k, loc[k].min(), loc[k].max()))
+            if outdir is not None:
+                with open(os.path.join(outdir, "local_%s_E.off" % k), "w") as fh:
+                    fh.write("OFF\n%d %d %d\n" % (pos.shape[0], self.faces.shape[0], self.edges.shape[0]))
+                    for p in pos:
+                        fh.write("%g %g %g\n" % tuple(p))
+                    for f, e in zip(self.faces, loc[k]):
+                        fh.write("3 %d %d %d 0 %g %g 1\n" % (f[0], f[1], f[2], e, 1 - e))
+        return {k: loc[k] for k in keys}
+
+
 def force_calculation_init(boundary: INTERFACE, counterions: list, scalefactor: float, bucklingFlag: str) -> None:
     """src/newforces.cpp:4-135."""
     if counterions:

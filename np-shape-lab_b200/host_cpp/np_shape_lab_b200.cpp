@@ -86,9 +86,17 @@ int main(int argc, char **argv) {
         double qt = 0;
         for (size_t i = 0; i < boundary.V.size(); i++) qt += boundary.V[i].q;
         std::cout << qt << std::endl;
+        const double box_halflength = 1.0;  // src/main.cpp:194
+        output_directory() = outdir;
+        if (!outdir.empty()) {  // initial frame of the movie ("time step -1"), src/main.cpp:417
+            boundary.compute_vertex_area_normals();
+            interface_movie(0, boundary.V, counterions, box_halflength);
+        }
         const auto t0 = std::chrono::steady_clock::now();
-        md_interface(boundary, counterions, mesh_bath, ions_bath, mdremote, G, B, 'L', scalefactor, 1.0);
+        md_interface(boundary, counterions, mesh_bath, ions_bath, mdremote, G, B, 'L', scalefactor, box_halflength);
         const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        boundary.compute_local_energies(scalefactor);  // src/main.cpp:468-469
+        boundary.compute_local_energies_by_component();
         const npsl_energies &e = boundary.parts;
         const double E = boundary.energy + e.mesh_bath_ke + e.mesh_bath_pe + e.ions_bath_ke + e.ions_bath_pe;
         std::printf("{\"vertices\": %zu, \"steps\": %d, \"wall_s\": %.6f, \"A\": %.17g, \"U\": %.17g, \"E\": %.17g}\n",

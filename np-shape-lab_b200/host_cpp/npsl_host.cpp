@@ -283,6 +283,92 @@ void INTERFACE::compute_energy(int num, vector<PARTICLE> &counterions, const dou
     append_line(outdir, "energy_in_parts_kE_bE_sE_tE_ljE_esE.dat", row.str());
 }
 
+void INTERFACE::compute_vertex_area_normals() {
+    if (!ctx) throw npsl_error(NPSL_ERR_STATE, "compute_vertex_area_normals before the first dressup / force call");
+    vector<double> a(V.size()), n(3 * V.size());
+    check(ctx, npsl_vertex_geometry(ctx, a.data(), n.data()), "npsl_vertex_geometry");
+    for (size_t i = 0; i < V.size(); i++) {
+        V[i].itsarea = a[i];
+        V[i].itsnormal = VECTOR3D(n[3 * i], n[3 * i + 1], n[3 * i + 2]);
+    }
+}
+
+namespace {
+// One local_*_E.off file: header, vertex positions, then per face "3 i j k r g b a" with colormap(E) = (0, E, 1 - E, 1)
+// (src/interface.cpp:12-18, 1141-1190), everything in the stream's default format like the reference.
+void write_local_off(const INTERFACE &b, const string &file, const char *label, const vector<double> &e) {
+    double lo = 1e100, hi = -1e100;
+    for (size_t i = 0; i < e.size(); i++) { lo = std::min(lo, e[i]); hi = std::max(hi, e[i]); }
+    std::cout << label << " range" << "\t" << lo << "\t" << hi << std::endl;
+    if (b.outdir.empty()) return;
+    std::ofstream out((b.outdir + "/" + file).c_str(), std::ios::out);
+    out << "OFF\n" << b.V.size() << " " << b.F.size() << " " << b.E.size() << "\n";
+    for (size_t i = 0; i < b.V.size(); i++) out << b.V[i].posvec.x << " " << b.V[i].posvec.y << " " << b.V[i].posvec.z << "\n";
+    for (size_t i = 0; i < b.F.size(); i++)
+        out << "3 " << b.F[i].itsV[0]->index << " " << b.F[i].itsV[1]->index << " " << b.F[i].itsV[2]->index << " " << 0.0 << " "
+            << e[i] << " " << 1 - e[i] << " " << 1.0 << "\n";
+}
+}  // namespace
+
+void INTERFACE::compute_local_energies(const double scalefactor) {
+    if (!ctx) throw npsl_error(NPSL_ERR_STATE, "compute_local_energies before the first force call");
+    (void) scalefactor;  // part of the context since the first force call
+    vector<double> es(F.size()), el(F.size());
+    check(ctx, npsl_local_energies(ctx, es.data(), el.data(), nullptr, nullptr), "npsl_local_energies");
+    write_local_off(*this, "local_electrostatic_E.off", "electrostatic", es);
+    write_local_off(*this, "local_elastic_E.off", "elastic", el);
+}
+
+void INTERFACE::compute_local_energies_by_component() {
+    if (!ctx) throw npsl_error(NPSL_ERR_STATE, "compute_local_energies_by_component before the first force call");
+    vector<double> be(F.size()), st(F.size());
+    check(ctx, npsl_local_energies(ctx, nullptr, nullptr, be.data(), st.data()), "npsl_local_energies");
+    write_local_off(*this, "local_stretching_E.off", "stretching", st);
+    write_local_off(*this, "local_bending_E.off", "bending", be);
+}
+
+string &output_directory() {
+    static string dir = "outfiles";
+    return dir;
+}
+
+void interface_movie(int num, vector<VERTEX> &V, vector<PARTICLE> &counterions, double box_halflength) {
+    if (output_directory().empty()) return;
+    std::ofstream outdump((output_directory() + "/p.lammpstrj").c_str(), std::ios::app);
+    outdump << std::setprecision(12);
+    outdump << std::fixed;
+    outdump << "ITEM: TIMESTEP" << std::endl;
+    outdump << num - 1 << std::endl;
+    outdump << "ITEM: NUMBER OF ATOMS" << std::endl;
+    outdump << V.size() + counterions.size() << std::endl;
+    outdump << "ITEM: BOX BOUNDS" << std::endl;
+    for (int k = 0; k < 3; k++) outdump << -box_halflength << "\t" << box_halflength << std::endl;
+    outdump << "ITEM: ATOMS index type x y z Vq Va Vq/a" << std::endl;
+    for (size_t i = 0; i < V.size(); i++)
+        outdump << i << "\t" << (V[i].q > 0 ? "1" : "-1") << "\t" << V[i].posvec.x << "\t" << V[i].posvec.y << "\t" << V[i].posvec.z
+                << "\t" << V[i].q << "\t" << V[i].itsarea << "\t" << (V[i].q / V[i].itsarea) << std::endl;
+    for (size_t i = 0; i < counterions.size(); i++)
+        outdump << i + V.size() << "\t" << 2 << "\t" << counterions[i].posvec.x << "\t" << counterions[i].posvec.y << "\t"
+                << counterions[i].posvec.z << "\t" << counterions[i].q << "\t" << 0 << "\t" << 0 << std::endl;
+}
+
+void interface_off(int num, INTERFACE &dsphere) {
+    if (output_directory().empty()) return;
+    std::ostringstream ss;
+    ss << output_directory() << "/" << num << ".off";
+    std::ofstream outdump(ss.str().c_str(), std::ios::out);
+    outdump << "OFF\n" << dsphere.number_of_vertices << " " << dsphere.number_of_faces << " " << dsphere.number_of_edges << "\n";
+    for (size_t i = 0; i < dsphere.V.size(); i++)
+        outdump << dsphere.V[i].posvec.x << " " << dsphere.V[i].posvec.y << " " << dsphere.V[i].posvec.z << "\n";
+    for (size_t i = 0; i < dsphere.F.size(); i++) {
+        FACE &f = dsphere.F[i];
+        outdump << "3 " << f.itsV[0]->index << " " << f.itsV[1]->index << " " << f.itsV[2]->index << " ";
+        if (f.itsV[0]->q > 0 && f.itsV[1]->q > 0 && f.itsV[2]->q > 0) outdump << "255 0 0 1\n";
+        else if (f.itsV[2]->q < 0 && f.itsV[1]->q < 0 && f.itsV[0]->q < 0) outdump << "0 0 255 1\n";
+        else outdump << "0 0 0 0\n";
+    }
+}
+
 void force_calculation_init(INTERFACE &boundary, vector<PARTICLE> &counterions, const double scalefactor, char bucklingFlag) {
     require_no_ions(counterions);
     npsl_ctx *c = boundary.context(scalefactor, bucklingFlag);
@@ -329,7 +415,7 @@ void initialize_velocities_to_zero(vector<VERTEX> &V, vector<PARTICLE> &ions) {
 // when the reference writes (num < 3 or num % writedata == 0), anneals, or at the end.
 void md_interface(INTERFACE &boundary, vector<PARTICLE> &counterions, vector<THERMOSTAT> &mesh_bath,
                   vector<THERMOSTAT> &ions_bath, CONTROL &mdremote, char geomConstraint, char bucklingFlag,
-                  char constraintForm, const double scalefactor, double /*box_radius*/) {
+                  char constraintForm, const double scalefactor, double box_radius) {
     require_no_ions(counterions);
     if (geomConstraint == 'V' && constraintForm == 'Q')
         throw npsl_error(NPSL_ERR_ARG, "the quadratic constraint form is not on the device path");
@@ -387,6 +473,7 @@ void md_interface(INTERFACE &boundary, vector<PARTICLE> &counterions, vector<THE
         // run on the device up to the next step at which the host has something to do
         int nxt = mdremote.steps;
         nxt = std::min(nxt, num < 2 ? num + 1 : (num / mdremote.writedata + 1) * mdremote.writedata);
+        if (mdremote.moviefreq > 0) nxt = std::min(nxt, (num / mdremote.moviefreq + 1) * mdremote.moviefreq);
         if (mdremote.anneal == 'y') {
             if (anneal_step(num + 1)) nxt = std::min(nxt, num + 1);
             nxt = std::min(nxt, (num / mdremote.annealfreq + 1) * mdremote.annealfreq);
@@ -405,6 +492,13 @@ void md_interface(INTERFACE &boundary, vector<PARTICLE> &counterions, vector<THE
                 if (abortCounter == 10)
                     throw npsl_error(NPSL_ERR_NUMERIC, "aborting: >5% net energy drift downwards prior to annealing");
             }
+        }
+        if (mdremote.moviefreq > 0 && num % mdremote.moviefreq == 0 && !dir.empty()) {  // snapshots, src/newmd.cpp:230-240
+            boundary.pull_state();
+            boundary.compute_vertex_area_normals();
+            output_directory() = dir;
+            if (mdremote.offfreq > 0 && num % mdremote.offfreq == 0) interface_off(num, boundary);
+            interface_movie(num, boundary.V, counterions, box_radius);
         }
         if (anneal_step(num)) {  // gradual annealing, src/newmd.cpp:258-299
             sync_baths();

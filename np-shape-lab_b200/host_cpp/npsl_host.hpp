@@ -62,6 +62,7 @@ public:
     unsigned int index = 0;
     VECTOR3D posvec, velvec, forvec;
     VECTOR3D bforce, sforce, TForce, VolTForce;  // per-term forces, src/newforces.cpp:279-280
+    VECTOR3D itsnormal;                          // area-weighted unit normal, src/vertex.cpp:7-18
     double q = 0, m = 1, ke = 0, itsarea = 0;
     std::vector<EDGE *> itsE;
     std::vector<FACE *> itsF;
@@ -150,6 +151,13 @@ public:
                                 char functionFlag);
     void dressup(double lambda_a, double lambda_v);                      // src/interface.cpp:33-67
     void compute_energy(int num, std::vector<PARTICLE> &counterions, const double scalefactor, char bucklingFlag);
+    // local energy maps: <outdir>/local_electrostatic_E.off, local_elastic_E.off and local_bending_E.off,
+    // local_stretching_E.off in the reference's format, per-face sums from the device (src/interface.cpp:1140-1337)
+    void compute_local_energies(const double scalefactor);
+    void compute_local_energies_by_component();
+    // VERTEX::compute_area_normal for every vertex (src/vertex.cpp:7-18), as the movie writer refreshes them
+    // (src/newmd.cpp:232-235): V[i].itsarea, V[i].itsnormal <- device
+    void compute_vertex_area_normals();
 
     // ---- device plumbing (not in the reference) ----
     npsl_ctx *ctx = nullptr;
@@ -176,5 +184,10 @@ long double compute_kinetic_energy(std::vector<VERTEX> &V);              // src/
 double bath_kinetic_energy(std::vector<THERMOSTAT> &bath);               // src/newenergies.h:28-36
 double bath_potential_energy(std::vector<THERMOSTAT> &bath);             // src/newenergies.h:38-46
 void initialize_velocities_to_zero(std::vector<VERTEX> &V, std::vector<PARTICLE> &ions);  // src/functions.cpp:40-47
+// The reference's snapshot writers (host formatting only; areas come from compute_vertex_area_normals). They write
+// into output_directory() ("outfiles" unless changed), like the reference's hard-wired "outfiles/".
+void interface_movie(int num, std::vector<VERTEX> &V, std::vector<PARTICLE> &counterions, double box_halflength);  // src/functions.cpp:50-84  p.lammpstrj
+void interface_off(int num, INTERFACE &dsphere);                                                                   // src/functions.cpp:134-167  <num>.off
+std::string &output_directory();
 
 #endif

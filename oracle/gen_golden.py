@@ -145,6 +145,72 @@ def readme_series() -> None:
         json.dump(out, fh)
 
 
+LOCAL_CASES = {"disc_D4": 2, "janus_D8": 1, "buckled_D4": 1}  # config name -> step
+
+
+def local_maps() -> None:
+    """tests/golden/local_maps.npz: vertex areas / normals and the per-face local energy maps
+    (INTERFACE::compute_local_energies(_by_component), src/interface.cpp:1140-1337) of the compiled reference in full
+    precision (the driver repeats the reference's sums with the reference's own pair / edge functions) together with the
+    g channel of the reference's own local_*_E.off files (6 digits), which pin the repeated sums; plus the shipped
+    examples/*/local_*_E.off (positions and per-face energies after 25 000 steps, 6 digits)."""
+    out = {}
+    scratch = os.path.join("/tmp", "npsl_golden")
+    os.makedirs(scratch, exist_ok=True)
+    for name, step in LOCAL_CASES.items():
+        src, D, flags, _, _ = CONFIGS[name]
+        mesh_file = os.path.join(REF, "bin", "infiles", src[4:] + ".dat")
+        wd = refdump.make_workdir(mesh_file, D, root=scratch)
+        d = refdump.dump_at_step(wd, D, flags, step, local=True)
+        lf = d["local_faces"]
+        for k, key in enumerate(("electrostatic", "elastic", "bending", "stretching")):
+            off = d["off_" + key]
+            tol = 1e-5 * max(np.max(np.abs(off)), 1e-300)
+            assert np.max(np.abs(lf[:, k] - off)) <= tol, (name, key)
+            out["%s_off_%s" % (name, key)] = off
+        out[name + "_step"] = np.array(step)
+        out[name + "_pos"] = d["pos"]
+        out[name + "_vertex_area"] = d["vertex_area"]
+        out[name + "_vertex_normal"] = d["vertex_normal"]
+        out[name + "_local_faces"] = lf
+        print("local maps", name, "step", step, "es range %.6g..%.6g" % (lf[:, 0].min(), lf[:, 0].max()), flush=True)
+        shutil.rmtree(wd, ignore_errors=True)
+    ex = {"disc_D4": "HomogeneouslyCharged_Disc_Control", "rod_D4": "HomogeneouslyCharged_Rod_Control",
+          "janus_D4": "InhomogeneouslyCharged_Hemisphere_Control", "buckled_D4": "Uncharged_Buckled_Control"}
+    for name, d in ex.items():
+        pos = None
+        for key, fn in refdump.LOCAL_OFF.items():
+            p, e = refdump.parse_local_off(os.path.join(REF, "examples", d, fn))
+            assert pos is None or np.array_equal(pos, p)
+            pos = p
+            out["example_%s_%s" % (name, key)] = e
+        out["example_%s_pos" % name] = pos
+    np.savez_compressed(os.path.join(GOLD, "local_maps.npz"), **out)
+
+
+def writers() -> None:
+    """tests/golden/writers_disc_D4.npz: what the reference's snapshot writers leave behind in a 5000-step README disc
+    run -- p.lammpstrj frames (interface_movie, every 1000 steps; frames 1000 and 5000 are kept), 5000.off
+    (interface_off) and the four local_*_E.off maps of the final state."""
+    name, K = "disc_D4", 5000
+    src, D, flags, _, _ = CONFIGS[name]
+    scratch = os.path.join("/tmp", "npsl_golden")
+    os.makedirs(scratch, exist_ok=True)
+    wd = refdump.make_workdir(os.path.join(REF, "bin", "infiles", src[4:] + ".dat"), D, root=scratch)
+    d = refdump.dump_at_step(wd, D, flags, K, writedata=K, local=True)
+    steps, frames = refdump.parse_lammpstrj(os.path.join(wd, "outfiles", "p.lammpstrj"))
+    keep = [int(np.where(steps == s - 1)[0][0]) for s in (1000, K)]  # the writer labels step num as num - 1
+    pos, faces, colours = refdump.parse_shape_off(os.path.join(wd, "outfiles", "%d.off" % K))
+    out = {"steps": np.array(K), "movie_timesteps": steps[keep], "movie_frames": frames[keep], "movie_all_timesteps": steps,
+           "off_pos": pos, "off_faces": faces, "off_colours": colours}
+    for key in refdump.LOCAL_OFF:
+        out["local_" + key] = d["off_" + key]
+    out["local_full"] = d["local_faces"]
+    np.savez_compressed(os.path.join(GOLD, "writers_disc_D4.npz"), **out)
+    print("writers", name, "frames", steps.tolist(), flush=True)
+    shutil.rmtree(wd, ignore_errors=True)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -154,6 +220,10 @@ def main() -> None:
         raise SystemExit("build oracle/_ref first: make -C oracle ref")
     os.makedirs(GOLD, exist_ok=True)
     readme_series()
+    if a.only in (None, "local_maps"):
+        local_maps()
+    if a.only in (None, "writers"):
+        writers()
     for name in CONFIGS:
         if a.only and a.only != name:
             continue

@@ -419,6 +419,58 @@ void npo_energy(void *hh, int lo, int hi, double *out) {
     out[6] = h->volE; out[7] = h->penergy; out[8] = h->energy;
 }
 
+/* ---------------------------------------------------------------- data feeds of the writers */
+
+/* VERTEX::compute_area_normal, src/vertex.cpp:7-18, after FACE::compute_area_normal (src/face.cpp:16-26) as the movie
+ * writer refreshes them (src/newmd.cpp:232-235). area[nv], normal[nv][3]. Call after npo_dressup. */
+void npo_vertex_geometry(void *hh, double *area, double *normal) {
+    npo_t *h = (npo_t *) hh;
+    for (int v = 0; v < h->nv; v++) {
+        vec3 n = v3(0, 0, 0);
+        for (int k = 0; k < h->v_nf[v]; k++) {
+            int f = h->v_f[v * NPO_MAXDEG + k];
+            vec3 fn = vscale(h->f_dir[f], 0.5 / h->f_area[f]); /* FACE::itsnormal */
+            n = vadd(n, vscale(fn, h->f_area[f]));              /* area weighted */
+        }
+        n = vscale(n, 1 / vnorm(n));
+        double a = 0;
+        for (int k = 0; k < h->v_nf[v]; k++) a = a + h->f_area[h->v_f[v * NPO_MAXDEG + k]];
+        a = a * (1. / 3.);
+        area[v] = a;
+        normal[3 * v] = (double) n.x; normal[3 * v + 1] = (double) n.y; normal[3 * v + 2] = (double) n.z;
+    }
+}
+
+/* INTERFACE::compute_local_energies and compute_local_energies_by_component, src/interface.cpp:1140-1337: the
+ * per-face values handed to colormap(). out[nf][4] = electrostatic, elastic, bending, stretching. Uses EDGE::itsS and
+ * the face areas of the last npo_force / npo_dressup, like the reference. */
+void npo_local_energies(void *hh, double *out) {
+    npo_t *h = (npo_t *) hh;
+    const int n = h->nv;
+    double *es = (double *) calloc(h->nf, sizeof(double)), *el = (double *) calloc(h->nf, sizeof(double));
+    double *be = (double *) calloc(h->nf, sizeof(double)), *st = (double *) calloc(h->nf, sizeof(double));
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++) {
+            vec3 r_vec = vsub(h->pos[i], h->pos[j]);
+            double r = (double) vnorm(r_vec);
+            double cur_E = h->scalefactor * h->q[i] * h->q[j] * (exp(-(1.0 / h->inv_kappa_out) * r)) / (h->em * r);
+            for (int k = 0; k < h->v_nf[i]; k++) es[h->v_f[i * NPO_MAXDEG + k]] += cur_E;
+            for (int k = 0; k < h->v_nf[j]; k++) es[h->v_f[j * NPO_MAXDEG + k]] += cur_E;
+        }
+    for (int e = 0; e < h->ne; e++) {
+        double stretched = edge_length(h, e) - h->l0[e];
+        double senergy = 0.5 * h->sconstant * stretched * stretched / (h->l0[e] * h->l0[e]);
+        senergy *= h->avg_edge_length * h->avg_edge_length;
+        double benergy = h->bkappa * (1 - h->e_S[e] / (4 * h->f_area[h->edge_f[2 * e]] * h->f_area[h->edge_f[2 * e + 1]]));
+        for (int k = 0; k < 2; k++) { el[h->edge_f[2 * e + k]] += senergy; st[h->edge_f[2 * e + k]] += senergy; }
+        for (int k = 0; k < 2; k++) { el[h->edge_f[2 * e + k]] += benergy; be[h->edge_f[2 * e + k]] += benergy; }
+    }
+    for (int f = 0; f < h->nf; f++) {
+        out[4 * f] = es[f]; out[4 * f + 1] = el[f]; out[4 * f + 2] = be[f]; out[4 * f + 3] = st[f];
+    }
+    free(es); free(el); free(be); free(st);
+}
+
 /* ---------------------------------------------------------------- thermostat + integrator */
 
 /* update_chain_xi, src/functions.h:176-189 */

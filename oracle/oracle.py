@@ -48,6 +48,8 @@ def lib():
         L.npo_get_vec.argtypes = [vp, C.c_int, dp]
         L.npo_get_scalars.argtypes = [vp, dp]
         L.npo_get_edge_S.argtypes = [vp, dp]
+        L.npo_vertex_geometry.argtypes = [vp, dp, dp]
+        L.npo_local_energies.argtypes = [vp, dp]
         _lib = L
     return _lib
 
@@ -149,3 +151,16 @@ class Oracle:
         out = np.zeros(self.ne)
         self.L.npo_get_edge_S(self.h, _dp(out))
         return out
+
+    def vertex_geometry(self) -> dict:
+        """VERTEX::compute_area_normal for every vertex (after dressup)."""
+        area, normal = np.zeros(self.nv), np.zeros((self.nv, 3))
+        self.L.npo_vertex_geometry(self.h, _dp(area), _dp(normal))
+        return {"area": area, "normal": normal}
+
+    def local_energies(self) -> dict:
+        """Per-face maps of INTERFACE::compute_local_energies(_by_component) (after force)."""
+        out = np.zeros((self.nf, 4))
+        self.L.npo_local_energies(self.h, _dp(out))
+        return {"electrostatic": out[:, 0].copy(), "elastic": out[:, 1].copy(), "bending": out[:, 2].copy(),
+                "stretching": out[:, 3].copy()}

@@ -74,6 +74,7 @@ struct Options {
     long row_lo = 0, row_hi = -1;
     int reps = 1;
     int warm = 0;
+    int local = 0;  // 1: also dump vertex areas / normals and the per-face local energy maps
 };
 
 bool parse(int argc, char **argv, Options &o) {
@@ -113,6 +114,7 @@ bool parse(int argc, char **argv, Options &o) {
         else if (a == "--row-hi") o.row_hi = atol(need("--row-hi"));
         else if (a == "--reps") o.reps = atoi(need("--reps"));
         else if (a == "--warm") o.warm = atoi(need("--warm"));
+        else if (a == "--local") o.local = atoi(need("--local"));
         else {
             std::fprintf(stderr, "unknown option %s\n", a.c_str());
             return false;
@@ -363,6 +365,43 @@ int main(int argc, char **argv) {
         std::fprintf(f, "face %zu %u %u %u %.17g %.17g\n", i, boundary.F[i].itsV[0]->index,
                      boundary.F[i].itsV[1]->index, boundary.F[i].itsV[2]->index, boundary.F[i].itsarea,
                      boundary.F[i].subtends_volume);
+    if (o.local) {
+        // VERTEX::itsarea / itsnormal the way the movie writer refreshes them (src/newmd.cpp:232-235)
+        for (size_t i = 0; i < boundary.F.size(); i++) boundary.F[i].compute_area_normal();
+        for (size_t i = 0; i < N; i++) boundary.V[i].compute_area_normal();
+        for (size_t i = 0; i < N; i++)
+            std::fprintf(f, "varea %zu %.17g %.21Lg %.21Lg %.21Lg\n", i, boundary.V[i].itsarea, boundary.V[i].itsnormal.x,
+                         boundary.V[i].itsnormal.y, boundary.V[i].itsnormal.z);
+        // The reference's own local maps land in outfiles/local_*_E.off with 6 significant digits
+        // (src/interface.cpp:1140-1337); the same sums are repeated here with the reference's pair / edge functions so
+        // that they can be printed in full. oracle/gen_golden.py checks the two against each other.
+        boundary.compute_local_energies(scalefactor);
+        boundary.compute_local_energies_by_component();
+        std::vector<double> es(boundary.F.size(), 0), el(boundary.F.size(), 0), be(boundary.F.size(), 0), st(boundary.F.size(), 0);
+        for (size_t i = 0; i < N; i++)
+            for (size_t j = i + 1; j < N; j++) {
+                double cur_E = energy_es_pair(boundary.V[i], boundary.V[j], boundary.em, boundary.inv_kappa_out, scalefactor);
+                for (size_t k = 0; k < boundary.V[i].itsF.size(); k++) es[boundary.V[i].itsF[k]->index] += cur_E;
+                for (size_t k = 0; k < boundary.V[j].itsF.size(); k++) es[boundary.V[j].itsF[k]->index] += cur_E;
+            }
+        for (size_t i = 0; i < boundary.E.size(); i++) {
+            EDGE &E = boundary.E[i];
+            double stretched = (E.length() - E.l0);
+            double senergy = 0.5 * boundary.sconstant * stretched * stretched / (E.l0 * E.l0);
+            senergy *= boundary.avg_edge_length * boundary.avg_edge_length;
+            double benergy = boundary.bkappa * (1 - E.itsS / (4 * E.itsF[0]->itsarea * E.itsF[1]->itsarea));
+            for (size_t k = 0; k < E.itsF.size(); k++) {
+                el[E.itsF[k]->index] += senergy;
+                st[E.itsF[k]->index] += senergy;
+            }
+            for (size_t k = 0; k < E.itsF.size(); k++) {
+                el[E.itsF[k]->index] += benergy;
+                be[E.itsF[k]->index] += benergy;
+            }
+        }
+        for (size_t i = 0; i < boundary.F.size(); i++)
+            std::fprintf(f, "lface %zu %.17g %.17g %.17g %.17g\n", i, es[i], el[i], be[i], st[i]);
+    }
     std::fclose(f);
     std::fprintf(stderr, "dumped step %d to %s (md wall %.3f s)\n", o.steps, o.out.c_str(), t1 - t0);
     return 0;

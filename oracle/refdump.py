@@ -75,6 +75,7 @@ def parse_dump(path: str) -> dict:
     vec: dict = {}
     baths: dict = {"mesh_bath": [], "ions_bath": []}
     edges, faces = [], []
+    varea, lface = [], []
     q = None
     for line in lines:
         t = line.split()
@@ -94,6 +95,10 @@ def parse_dump(path: str) -> dict:
             edges.append([int(t[2]), int(t[3]), float(t[4]), float(t[5])])
         elif k == "face":
             faces.append([int(t[2]), int(t[3]), int(t[4]), float(t[5]), float(t[6])])
+        elif k == "varea":
+            varea.append([float(x) for x in t[2:6]])
+        elif k == "lface":
+            lface.append([float(x) for x in t[2:6]])
         elif len(t) == 2:
             d[k] = float(t[1])
     d.update(vec)
@@ -108,14 +113,68 @@ def parse_dump(path: str) -> dict:
     d["faces"] = fa[:, :3].astype(np.int32)
     d["face_area"] = fa[:, 3].copy()
     d["face_volume"] = fa[:, 4].copy()
+    if varea:  # --local 1
+        va = np.array(varea)
+        d["vertex_area"], d["vertex_normal"] = va[:, 0].copy(), va[:, 1:4].copy()
+        d["local_faces"] = np.array(lface)  # [F, 4]: electrostatic, elastic, bending, stretching
     d["scalars"] = np.array([d[s] for s in SCALARS])
     d["params"] = np.array([d[s] for s in PARAMS])
     assert d["edges"].shape[0] == e and d["faces"].shape[0] == f
     return d
 
 
-def dump_at_step(wd: str, D: int, flags: list[str], step: int, threads: int | None = None, writedata: int = 500) -> dict:
+def dump_at_step(wd: str, D: int, flags: list[str], step: int, threads: int | None = None, writedata: int = 500,
+                 local: bool = False) -> dict:
     reset_outfiles(wd)
     out = os.path.join(wd, "dump_%d.txt" % step)
-    run_ref(wd, ["--mode", "dump", "--out", out, "-D", D, "--steps", step, "-W", writedata] + flags, threads=threads)
-    return parse_dump(out)
+    run_ref(wd, ["--mode", "dump", "--out", out, "-D", D, "--steps", step, "-W", writedata] + (["--local", 1] if local else []) + flags,
+            threads=threads)
+    d = parse_dump(out)
+    if local:  # the reference's own files (6 significant digits)
+        for key, fn in LOCAL_OFF.items():
+            d["off_" + key] = parse_local_off(os.path.join(wd, "outfiles", fn))[1]
+    return d
+
+
+LOCAL_OFF = {"electrostatic": "local_electrostatic_E.off", "elastic": "local_elastic_E.off",
+             "bending": "local_bending_E.off", "stretching": "local_stretching_E.off"}
+
+
+def parse_local_off(path: str):
+    """local_*_E.off of INTERFACE::compute_local_energies (src/interface.cpp:1140-1337): vertex positions and, per
+    face, colormap(E) = (r, g, b, a) = (0, E, 1 - E, 1). Returns (positions [V,3], E per face [F])."""
+    with open(path) as fh:
+        t = fh.read().split()
+    assert t[0] == "OFF"
+    nv, nf = int(t[1]), int(t[2])
+    pos = np.array(t[4:4 + 3 * nv], dtype=np.float64).reshape(nv, 3)
+    rows = np.array(t[4 + 3 * nv:4 + 3 * nv + 8 * nf], dtype=np.float64).reshape(nf, 8)
+    return pos, rows[:, 5].copy()
+
+
+def parse_lammpstrj(path: str):
+    """p.lammpstrj of interface_movie (src/functions.cpp:50-84) -> (timesteps [T], rows [T, N, 8]:
+    index type x y z Vq Va Vq/a)."""
+    steps, frames = [], []
+    with open(path) as fh:
+        lines = fh.read().splitlines()
+    i = 0
+    while i < len(lines):
+        assert lines[i].startswith("ITEM: TIMESTEP"), lines[i]
+        steps.append(int(lines[i + 1]))
+        n = int(lines[i + 3])
+        rows = [[float(x) for x in lines[i + 9 + k].split()] for k in range(n)]
+        frames.append(rows)
+        i += 9 + n
+    return np.array(steps), np.array(frames)
+
+
+def parse_shape_off(path: str):
+    """<num>.off of interface_off (src/functions.cpp:134-167) -> (positions [V,3], faces [F,3], colours [F,4])."""
+    with open(path) as fh:
+        t = fh.read().split()
+    assert t[0] == "OFF"
+    nv, nf = int(t[1]), int(t[2])
+    pos = np.array(t[4:4 + 3 * nv], dtype=np.float64).reshape(nv, 3)
+    rows = np.array(t[4 + 3 * nv:4 + 3 * nv + 8 * nf], dtype=np.float64).reshape(nf, 8)
+    return pos, rows[:, 1:4].astype(np.int32), rows[:, 4:8].copy()

@@ -107,3 +107,44 @@ def test_readme_final_values(name, tmp_path):
     assert abs(res["E"] - E) <= 0.01 * E, (res, E)
     rows = [l.split() for l in open(tmp_path / "outfiles" / "energy_nanomembrane.dat")]
     assert len(rows) == 3 + 25000 // 500  # steps 0,1,2 and every 500
+
+
+@pytest.mark.gpu
+def test_host_cpp_snapshot_writers_match_reference(tmp_path):
+    """p.lammpstrj (interface_movie), <num>.off (interface_off) and the four local_*_E.off maps of a 5000-step README
+    disc run against what the compiled reference wrote for the same run (tests/golden/writers_disc_D4.npz): same
+    frames at the same steps, positions / vertex areas / charge densities / per-face energies to trajectory accuracy."""
+    from oracle import refdump as R
+    build_host()
+    g = golden("disc_D4")
+    w = np.load(os.path.join(ROOT, "tests", "golden", "writers_disc_D4.npz"))
+    K = int(w["steps"])
+    M.write_dat(str(tmp_path / "m.dat"), M.Mesh(pos=g["pos0"], edges=g["edges"], faces=g["faces"]))
+    out = tmp_path / "outfiles"
+    r = subprocess.run([BIN, "--mesh", str(tmp_path / "m.dat"), "-S", str(K), "--out", str(out)] + RECIPES["disc_D4"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    for label in ("electrostatic range", "elastic range", "stretching range", "bending range"):
+        assert label in r.stdout  # the scale-bar lines of src/interface.cpp:1166,1221,1305-1308
+    # movie: the driver adds the initial frame ("time step -1", src/main.cpp:417), then one frame per 1000 steps
+    steps, frames = R.parse_lammpstrj(str(out / "p.lammpstrj"))
+    assert steps.tolist() == [-1] + [int(x) for x in w["movie_all_timesteps"]]
+    n = g.nv()
+    assert np.allclose(frames[0][:, 2:5], g["pos0"], atol=1e-11) and frames.shape == (len(steps), n, 8)
+    for ts, ref in zip(w["movie_timesteps"], w["movie_frames"]):
+        mine = frames[steps.tolist().index(int(ts))]
+        assert np.array_equal(mine[:, :2], ref[:, :2])                       # index, type
+        assert np.max(np.abs(mine[:, 2:5] - ref[:, 2:5])) <= 1e-6           # x y z (unit-sphere scale)
+        assert np.max(np.abs(mine[:, 5] - ref[:, 5])) <= 1e-11              # Vq
+        assert np.max(np.abs(mine[:, 6] / ref[:, 6] - 1)) <= 1e-5           # Va
+        assert np.max(np.abs(mine[:, 7] / ref[:, 7] - 1)) <= 1e-5           # Vq/a
+    pos, faces, colours = R.parse_shape_off(str(out / ("%d.off" % K)))
+    assert np.array_equal(faces, w["off_faces"]) and np.array_equal(colours, w["off_colours"])
+    assert np.max(np.abs(pos - w["off_pos"])) <= 2e-5                        # 6 printed digits
+    assert not (out / "2500.off").exists()  # only when both moviefreq and offfreq divide the step, src/newmd.cpp:231-237
+    for key, fn in R.LOCAL_OFF.items():
+        p2, e = R.parse_local_off(str(out / fn))
+        ref = w["local_" + key]
+        tol = {"stretching": 5e-3, "elastic": 5e-3, "bending": 1e-3, "electrostatic": 1e-4}[key]
+        assert np.max(np.abs(e - ref)) <= tol * float(np.max(np.abs(ref))), (key, np.max(np.abs(e - ref)))
+        assert np.max(np.abs(p2 - w["off_pos"])) <= 2e-5
