@@ -134,7 +134,7 @@ class INTERFACE:
         b.total_area, b.total_volume = p["ref_area"], p["ref_volume"]
         b.lj_length_mesh_mesh, b.elj = p["lj_length_mesh_mesh"], p["elj"]
         b.dt = inp.dt
-        b.q = M.assign_charges(mesh, inp.q, inp.N, inp.p)
+        b.q = M.assign_charges(mesh, inp.q, inp.N, inp.p, 1.0, inp.F, inp.H)
         b.scalefactor = p["scalefactor"]
         return b
 

@@ -19,11 +19,13 @@ int main(int argc, char **argv) {
     double R = 10, q = 600, conc = 0.005, t = 1, v = 1, b = 40, s = 40, p = 0.5, dt = 0.001, T = 0.001, Qm = 0.01, Qi = 0.01;
     int N = 1, steps = 25000, D = 4, C = 5, writedata = 500;
     char B = 'n', Fflag = 'n', H = 'n', G = 'N';
-    std::string mesh_file, outdir = "outfiles";
+    std::string mesh_file, outdir = "outfiles", externalPattern = "None";
+    int dump_q = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         if (a == "-h" || a == "--help") {
             std::puts("np_shape_lab_b200 [-R r] [-q q] [-c conc] [-t st] [-v vt] [-b bend] [-s stretch] [-B y|n] [-N 1|2] [-p frac]\n"
+                      "                  [-H n|y|c] [-F n|y] [-E pattern] [-G N|V]\n"
                       "                  [-S steps] [-D disc] [-d dt] [-T temp] [-Q Qmesh] [-C chain] [-W writedata]\n"
                       "                  [--mesh file.dat] [--out dir]   (needs a CUDA device; there is no CPU path)");
             return 0;
@@ -38,6 +40,7 @@ int main(int argc, char **argv) {
         else if (a == "-d") dt = atof(val); else if (a == "-T") T = atof(val); else if (a == "-Q") Qm = atof(val);
         else if (a == "-Y") Qi = atof(val); else if (a == "-C") C = atoi(val); else if (a == "-W") writedata = atoi(val);
         else if (a == "--mesh") mesh_file = val; else if (a == "--out") outdir = val;
+        else if (a == "-E") externalPattern = val; else if (a == "--dump-q") dump_q = atoi(val);
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     try {
@@ -59,7 +62,12 @@ int main(int argc, char **argv) {
         const double z_out = 1;
         boundary.inv_kappa_out = conc == 0 ? 100000000 : (0.257 / std::sqrt(z_out * boundary.lB_out * R * conc)) / R;
         if (mesh_file.empty()) boundary.discretize(3, D); else boundary.discretize_file(mesh_file);
-        boundary.assign_random_q_values(q, 1.0, N, p, Fflag, H);
+        if (externalPattern == "None") boundary.assign_random_q_values(q, 1.0, N, p, Fflag, H);  // src/main.cpp:244-247
+        else boundary.assign_external_q_values(q, externalPattern);
+        if (dump_q) {  // charges only (no device needed): one "%.17g" line per vertex
+            for (size_t i = 0; i < boundary.V.size(); i++) std::printf("%.17g\n", boundary.V[i].q);
+            return 0;
+        }
         boundary.lj_length_mesh_mesh = 0.1 * boundary.avg_edge_length;
         boundary.elj = 1.0;
         boundary.dressup(0, 0);

@@ -138,36 +138,116 @@ void INTERFACE::discretize_file(const string &path) {
     avg_edge_length /= E.size();
 }
 
-// Deterministic branch only: vertices ranked by (z, index); the vertex of rank i receives the area share of
-// vertex i; total rescaled to an integer number of charges.
-void INTERFACE::assign_random_q_values(double q_strength, double /*alpha*/, int num_divisions, double frac_patch,
-                                       char randomFlag, char functionFlag) {
-    if (randomFlag != 'n' || functionFlag != 'n' || num_divisions < 1 || num_divisions > 2)
-        throw npsl_error(NPSL_ERR_ARG, "only the deterministic patterns -F n -H n with -N 1|2 are mirrored");
-    const size_t n = V.size();
-    // face areas at the current positions
-    vector<double> farea(F.size());
+namespace {
+// vertex areas (a third of the incident faces) and the total area at the current positions
+double vertex_areas(const INTERFACE &b, vector<double> &varea) {
+    vector<double> farea(b.F.size());
     double total = 0;
-    for (size_t f = 0; f < F.size(); f++) {
-        const VECTOR3D d = (F[f].itsV[1]->posvec - F[f].itsV[0]->posvec) % (F[f].itsV[2]->posvec - F[f].itsV[1]->posvec);
+    for (size_t f = 0; f < b.F.size(); f++) {
+        const VECTOR3D d = (b.F[f].itsV[1]->posvec - b.F[f].itsV[0]->posvec) % (b.F[f].itsV[2]->posvec - b.F[f].itsV[1]->posvec);
         farea[f] = 0.5 * d.GetMagnitude();
         total += farea[f];
     }
-    vector<double> varea(n, 0.0);
-    for (size_t f = 0; f < F.size(); f++)
-        for (int k = 0; k < 3; k++) varea[F[f].itsV[k]->index] += farea[f];
-    for (size_t i = 0; i < n; i++) varea[i] /= 3.0;
-    vector<std::pair<double, unsigned>> rank(n);
-    for (size_t i = 0; i < n; i++) rank[i] = std::make_pair(V[i].posvec.z, (unsigned) i);
-    std::sort(rank.begin(), rank.end());
-    for (size_t i = 0; i < n; i++) V[i].q = 0;
-    if (q_strength == 0) return;
-    const size_t n_patch = num_divisions == 1 ? n : (size_t) (frac_patch * n);
-    for (size_t i = 0; i < n_patch; i++) V[rank[i].second].q = q_strength * varea[i] / total;
-    const double target = std::round(num_divisions == 1 ? q_strength : frac_patch * q_strength);
+    varea.assign(b.V.size(), 0.0);
+    for (size_t f = 0; f < b.F.size(); f++)
+        for (int k = 0; k < 3; k++) varea[b.F[f].itsV[k]->index] += farea[f];
+    for (size_t i = 0; i < varea.size(); i++) varea[i] /= 3.0;
+    return total;
+}
+
+// "Scale the vertices' charges to achieve the target net charge exactly", src/interface.cpp:776-798, 845-861
+void rescale_charges(vector<VERTEX> &V, double q_target) {
     double actual = 0;
-    for (size_t i = 0; i < n; i++) actual += V[i].q;
-    for (size_t i = 0; i < n; i++) V[i].q = V[i].q * (target / actual);
+    for (size_t i = 0; i < V.size(); i++) actual += V[i].q;
+    for (size_t i = 0; i < V.size(); i++) V[i].q = V[i].q * (q_target / actual);
+}
+}  // namespace
+
+// INTERFACE::assign_random_q_values, src/interface.cpp:339-798. Vertices are ranked by (z, index); the vertex of rank i
+// receives the area share of list entry i (vertex i unless shuffled); -N 1 uniform or cube (-H c), -N 2 Janus or
+// yin-yang (-H y), -N 3..17 stripes about the z axis with the even bands charged; -F y shuffles the occupancy and area
+// lists with srand(123456) + std::random_shuffle exactly like the reference (same libstdc++ / glibc stream); the total
+// is then rescaled to an integer number of charges.
+void INTERFACE::assign_random_q_values(double q_strength, double alpha, int num_divisions, double frac_patch,
+                                       char randomFlag, char functionFlag) {
+    if (num_divisions < 1 || num_divisions > 17) throw npsl_error(NPSL_ERR_ARG, "num_divisions must be in [1, 17]");
+    const unsigned int n = (unsigned int) V.size();
+    vector<double> areaList;
+    const double total = vertex_areas(*this, areaList);
+    vector<std::pair<double, int>> perm(n);
+    for (unsigned int i = 0; i < n; i++) perm[i] = std::make_pair(V[i].posvec.z, (int) i);
+    std::sort(perm.begin(), perm.end());
+    vector<int> state;
+    for (unsigned int i = 1; i <= alpha * n; i++) state.push_back(1);
+    for (unsigned int i = (unsigned int) state.size(); i < n; i++) state.push_back(0);
+    if (randomFlag == 'y') {
+        srand(123456);
+        std::random_shuffle(state.begin(), state.end());
+        std::random_shuffle(areaList.begin(), areaList.end());
+    }
+    auto share = [&](unsigned int i) { return q_strength * areaList[i] / total; };
+    auto at = [&](unsigned int i) -> VERTEX & { return V[perm[i].second]; };
+    const unsigned int nVertPerPatch = (unsigned int) (frac_patch * V.size());
+    const int N = num_divisions;
+    if (N == 1) {
+        for (unsigned int i = 0; i < n; i++) {
+            const VECTOR3D &p = at(i).posvec;
+            const bool on = functionFlag == 'c'
+                                ? (p.x * p.x + p.y * p.y <= 0.25) || (p.y * p.y + p.z * p.z <= 0.25) || (p.x * p.x + p.z * p.z <= 0.25)
+                                : state[i] == 1;
+            at(i).q = on ? share(i) : 0;
+        }
+    } else if (N == 2) {
+        unsigned int i;
+        for (i = 0; i < nVertPerPatch; i++) at(i).q = share(i);
+        for (; i < n; i++) at(i).q = 0;
+        if (functionFlag == 'y')
+            for (i = 0; i < n; i++) {
+                const VECTOR3D &p = at(i).posvec;
+                if (p.z <= 0 && (p.x - 0.5) * (p.x - 0.5) + p.z * p.z <= 0.25) at(i).q = 0;
+                if (p.z >= 0 && (p.x + 0.5) * (p.x + 0.5) + p.z * p.z <= 0.25) at(i).q = share(i);
+            }
+    } else {
+        unsigned int i = 0;
+        for (int k = 1; k < N; k++) {  // the reference's bounds "number_of_vertices * k*(alpha / num_divisions)"
+            const double bound = k == 1 ? n * (alpha / N) : (n * (unsigned int) k) * (alpha / N);
+            for (; i < bound && i < n; i++) at(i).q = (k % 2 == 1) ? share(i) : 0;
+        }
+        for (; i < n; i++) at(i).q = (N % 2 == 1) ? share(i) : 0;
+    }
+    if (q_strength == 0) {
+        for (unsigned int i = 0; i < n; i++) V[i].q = 0;
+        return;
+    }
+    double q_target;
+    if (N == 1) q_target = std::round(q_strength);
+    else if (N == 2) q_target = std::round(frac_patch * q_strength);
+    else q_target = std::round(std::ceil(0.5 * N) * frac_patch * q_strength);
+    rescale_charges(V, q_target);
+}
+
+// INTERFACE::assign_external_q_values, src/interface.cpp:818-862: "index value" rows of
+// infiles/Charge_Patterns/<externalPattern>.dat; vertices the file does not list keep the charge column of the mesh file.
+void INTERFACE::assign_external_q_values(double q_strength, std::string externalPattern) {
+    std::ifstream in(("infiles/Charge_Patterns/" + externalPattern + ".dat").c_str());
+    if (!in) {
+        std::cout << "Charge assignment file could not be opened.  Mesh will be uncharged." << std::endl;
+        for (size_t i = 0; i < V.size(); i++) V[i].q = 0;
+    } else {
+        std::cout << "Charge assignment file opened successfully.  Charging the mesh." << std::endl;
+        vector<double> areaList;
+        const double total = vertex_areas(*this, areaList);
+        int col1;
+        double col2;
+        while (in >> col1 >> col2) V.at(col1).q = (q_strength / total) * col2;
+    }
+    if (q_strength == 0) {
+        for (size_t i = 0; i < V.size(); i++) V[i].q = 0;
+        return;
+    }
+    double actual = 0;
+    for (size_t i = 0; i < V.size(); i++) actual += V[i].q;
+    if (actual != 0) rescale_charges(V, std::round(actual));
 }
 
 npsl_ctx *INTERFACE::context(double scalefactor, char bucklingFlag, const vector<THERMOSTAT> *mesh_bath,

@@ -146,9 +146,11 @@ public:
     void set_up(double unit_radius_sphere);                              // src/interface.cpp:20-29
     void discretize(unsigned int disc1, unsigned int disc2);             // src/interface.cpp:70-256 (infiles/<disc1>_<disc2>.dat)
     void discretize_file(const std::string &path);
-    // deterministic (-F n, -H n) patterns: N = 1 uniform, N = 2 Janus (src/interface.cpp:339-404,776-798)
+    // charge patterns, src/interface.cpp:339-798: -N 1 uniform / cube (-H c), -N 2 Janus / yin-yang (-H y), -N 3..17 stripes,
+    // fractional occupancy alpha, -F y shuffled; and patterns read from infiles/Charge_Patterns/<name>.dat (:818-862)
     void assign_random_q_values(double q_strength, double alpha, int num_divisions, double frac_patch, char randomFlag,
                                 char functionFlag);
+    void assign_external_q_values(double q_strength, std::string externalPattern);
     void dressup(double lambda_a, double lambda_v);                      // src/interface.cpp:33-67
     void compute_energy(int num, std::vector<PARTICLE> &counterions, const double scalefactor, char bucklingFlag);
     // local energy maps: <outdir>/local_electrostatic_E.off, local_elastic_E.off and local_bending_E.off,

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import dataclasses
 import math
+import os
 from typing import Tuple
 
 import numpy as np
@@ -34,6 +35,7 @@ class Mesh:
     pos: np.ndarray    # [N,3] float64
     edges: np.ndarray  # [E,2] int32, file order of the two end points
     faces: np.ndarray  # [F,3] int32, stored winding
+    file_q: np.ndarray | None = None  # [N] fifth column of the vertex records (VERTEX::q until a pattern is assigned)
 
     @property
     def n_vertices(self) -> int:
@@ -67,9 +69,11 @@ def load_dat(path: str) -> Mesh:
 
     nv = header()
     pos = np.zeros((nv, 3), dtype=np.float64)
+    file_q = np.zeros(nv, dtype=np.float64)
     for _ in range(nv):
         idx = int(tok[p])
         pos[idx] = (float(tok[p + 1]), float(tok[p + 2]), float(tok[p + 3]))
+        file_q[idx] = float(tok[p + 4])
         p += 5
     ne = header()
     edges = np.zeros((ne, 2), dtype=np.int32)
@@ -84,7 +88,7 @@ def load_dat(path: str) -> Mesh:
         a, b, c, sign = int(tok[p + 1]), int(tok[p + 2]), int(tok[p + 3]), int(tok[p + 4])
         faces[idx] = (a, b, c) if sign == 1 else (c, b, a)
         p += 6
-    return Mesh(pos, edges, faces)
+    return Mesh(pos, edges, faces, file_q)
 
 
 def write_dat(path: str, mesh: Mesh) -> None:
@@ -93,7 +97,7 @@ def write_dat(path: str, mesh: Mesh) -> None:
     with open(path, "w") as fh:
         fh.write("# Number of Vertices= %d\n\nvertices\n\n" % mesh.n_vertices)
         for i, (x, y, z) in enumerate(mesh.pos):
-            fh.write("%d\t%.17g\t%.17g\t%.17g\t1\n" % (i, x, y, z))
+            fh.write("%d\t%.17g\t%.17g\t%.17g\t%.17g\n" % (i, x, y, z, 1.0 if mesh.file_q is None else mesh.file_q[i]))
         fh.write("\n\n\n# Number of Edges= %d\n\nedges\n\n" % mesh.n_edges)
         for i, (a, b) in enumerate(mesh.edges):
             fh.write("%d\t%d\t%d\t1\n" % (i, a, b))
@@ -196,33 +200,137 @@ def vertex_areas(mesh: Mesh) -> np.ndarray:
     return va / 3.0
 
 
-def assign_charges(mesh: Mesh, q_strength: float, num_divisions: int = 1, frac_patch: float = 0.5) -> np.ndarray:
-    """Deterministic (``-F n``, ``-H n``) branch of ``INTERFACE::assign_random_q_values``
-    (src/interface.cpp:339-404, 776-798) for ``-N 1`` (uniform) and ``-N 2`` (Janus).
+class GlibcRand:
+    """glibc's ``srand`` / ``rand`` (TYPE_3 additive feedback generator, r[i] = r[i-3] + r[i-31]): the stream behind the
+    reference's ``srand(123456); std::random_shuffle(...)`` (src/interface.cpp:367-371) on the platforms it is built on."""
 
-    Vertices are ranked by (z, index); the vertex of rank i receives the area share of vertex i
-    (the reference's deliberate index mismatch, src/interface.cpp:361-364,392); the total is
-    then rescaled to an integer number of charges."""
+    def __init__(self, seed: int):
+        r = [0] * 34
+        r[0] = seed & 0xFFFFFFFF if seed else 1
+        for i in range(1, 31):
+            hi, lo = divmod(r[i - 1] if r[i - 1] < 2 ** 31 else r[i - 1] - 2 ** 32, 127773)
+            word = 16807 * lo - 2836 * hi
+            if word < 0:
+                word += 2147483647
+            r[i] = word
+        for i in range(31, 34):
+            r[i] = r[i - 31]
+        self.r = r
+        for _ in range(310):
+            self._next()
+
+    def _next(self) -> int:
+        v = (self.r[-31] + self.r[-3]) & 0xFFFFFFFF
+        self.r.append(v)
+        self.r.pop(0)
+        return v
+
+    def rand(self) -> int:
+        return self._next() >> 1
+
+
+def random_shuffle(seq: list, rng: GlibcRand) -> None:
+    """libstdc++'s two-iterator ``std::random_shuffle``: swap element i with element rand() % (i + 1), i = 1..n-1."""
+    for i in range(1, len(seq)):
+        j = rng.rand() % (i + 1)
+        if i != j:
+            seq[i], seq[j] = seq[j], seq[i]
+
+
+def assign_charges(mesh: Mesh, q_strength: float, num_divisions: int = 1, frac_patch: float = 0.5, alpha: float = 1.0,
+                   random_flag: str = "n", function_flag: str = "n") -> np.ndarray:
+    """``INTERFACE::assign_random_q_values`` (src/interface.cpp:339-798): uniform (``-N 1``), Janus (``-N 2``, with the
+    yin-yang variant ``-H y``), the cube pattern (``-N 1 -H c``), z-stripes (``-N 3..17``), fractional occupancy
+    ``alpha`` and the shuffled variants (``-F y``: ``srand(123456)`` + ``std::random_shuffle`` of the occupancy and area
+    lists, reproduced for glibc / libstdc++).
+
+    Vertices are ranked by (z, index); the vertex of rank i receives the area share of list entry i (vertex i unless
+    shuffled -- the reference's deliberate index mismatch, src/interface.cpp:361-364,392); the total is then rescaled
+    to an integer number of charges (src/interface.cpp:776-798)."""
     n = mesh.n_vertices
+    if not 1 <= num_divisions <= 17:
+        raise ValueError("num_divisions must be in [1, 17] (src/interface.cpp:343)")
     if q_strength == 0:
         return np.zeros(n)
     perm = np.lexsort((np.arange(n), mesh.pos[:, 2]))
-    area = vertex_areas(mesh)
     total_area = float(np.sum(face_areas(mesh)))
-    q = np.zeros(n)
-    if num_divisions == 1:
-        q[perm] = q_strength * area / total_area
-        q_target = round(q_strength)
-    elif num_divisions == 2:
+    state = [1] * int(alpha * n)
+    state += [0] * (n - len(state))
+    area = [float(a) for a in vertex_areas(mesh)]
+    if random_flag == "y":
+        rng = GlibcRand(123456)
+        random_shuffle(state, rng)
+        random_shuffle(area, rng)
+    share = q_strength * np.array(area) / total_area
+    pos = mesh.pos[perm]
+    q_ranked = np.zeros(n)
+    N = num_divisions
+    if N == 1:
+        if function_flag == "c":
+            x2, y2, z2 = pos[:, 0] * pos[:, 0], pos[:, 1] * pos[:, 1], pos[:, 2] * pos[:, 2]
+            on = (x2 + y2 <= 0.25) | (y2 + z2 <= 0.25) | (x2 + z2 <= 0.25)
+        else:
+            on = np.array(state) == 1
+        q_ranked = np.where(on, share, 0.0)
+    elif N == 2:
         n_patch = int(frac_patch * n)
-        q[perm[:n_patch]] = q_strength * area[:n_patch] / total_area
-        q_target = round(frac_patch * q_strength)
-    else:
-        raise NotImplementedError("striped patterns (-N >= 3) are a 'next' row (SURVEY 8f rank 4)")
+        q_ranked[:n_patch] = share[:n_patch]
+        if function_flag == "y":
+            x, z = pos[:, 0], pos[:, 2]
+            off = (z <= 0) & ((x - 0.5) * (x - 0.5) + z * z <= 0.25)
+            on = (z >= 0) & ((x + 0.5) * (x + 0.5) + z * z <= 0.25)
+            q_ranked = np.where(off, 0.0, q_ranked)
+            q_ranked = np.where(on, share, q_ranked)
+    else:  # stripes about the z axis: bands k = 0..N-1 of the ranking, even bands charged
+        step = alpha / N
+        i = 0
+        for k in range(1, N):
+            bound = (n * step) if k == 1 else float(n * k) * step  # "i < number_of_vertices * k*(alpha / num_divisions)"
+            while i < bound and i < n:
+                q_ranked[i] = share[i] if k % 2 == 1 else 0.0
+                i += 1
+        while i < n:
+            q_ranked[i] = share[i] if N % 2 == 1 else 0.0
+            i += 1
+    q = np.zeros(n)
+    q[perm] = q_ranked
+    q_target = c_round(q_target_raw(q_strength, N, frac_patch))
     q_actual = 0.0
     for v in q:  # same left-to-right double accumulation as the reference
         q_actual += v
     return q * (q_target / q_actual)
+
+
+def c_round(x: float) -> float:
+    """C's round(): half away from zero (Python's round() goes to even)."""
+    return math.copysign(math.floor(abs(x) + 0.5), x)
+
+
+def q_target_raw(q_strength: float, num_divisions: int, frac_patch: float) -> float:
+    """Argument of the reference's ``round`` (C round: half away from zero), src/interface.cpp:788-792."""
+    if num_divisions == 1:
+        return q_strength
+    if num_divisions == 2:
+        return frac_patch * q_strength
+    return math.ceil(0.5 * num_divisions) * frac_patch * q_strength
+
+
+def assign_external_charges(mesh: Mesh, q_strength: float, pattern_file: str) -> np.ndarray:
+    """``INTERFACE::assign_external_q_values`` (src/interface.cpp:818-862): ``index value`` rows of
+    ``infiles/Charge_Patterns/<name>.dat`` scaled by q_strength / total_area, then rescaled to an integer total."""
+    n = mesh.n_vertices
+    if q_strength == 0 or not os.path.isfile(pattern_file):  # "Mesh will be uncharged."
+        return np.zeros(n)
+    # vertices the file does not list keep the charge column of the mesh file (src/interface.cpp:94)
+    q = np.ones(n) if mesh.file_q is None else np.array(mesh.file_q, dtype=np.float64)
+    total_area = float(np.sum(face_areas(mesh)))
+    tok = open(pattern_file).read().split()
+    for k in range(0, len(tok) - 1, 2):
+        q[int(tok[k])] = (q_strength / total_area) * float(tok[k + 1])
+    q_actual = 0.0
+    for v in q:
+        q_actual += v
+    return q * (c_round(q_actual) / q_actual)
 
 
 # --------------------------------------------------------------------------- derived parameters
@@ -242,6 +350,8 @@ class PhysicalInputs:
     B: str = "n"             # -B buckling form of the stretching term
     N: int = 1               # -N number of patches
     p: float = 0.5           # -p patch fraction
+    F: str = "n"             # -F shuffle the occupancy / area lists (the reference's CLI default is 'y')
+    H: str = "n"             # -H pattern variant: 'y' yin-yang (with -N 2), 'c' cube (with -N 1)
     dt: float = 0.001        # -d
     T: float = 0.001         # -T
     Q_mesh: float = 0.01     # -Q

@@ -211,6 +211,40 @@ def writers() -> None:
     shutil.rmtree(wd, ignore_errors=True)
 
 
+CHARGE_CASES = dict(
+    [("N%d" % n, ["-N", str(n), "-p", "0.5"]) for n in range(3, 18)] +
+    [("N2_Hy", ["-N", "2", "-p", "0.5", "-H", "y"]), ("N1_Hc", ["-N", "1", "-H", "c"]),
+     ("N1_Fy", ["-F", "y"]), ("N2_Fy_p0.3", ["-F", "y", "-N", "2", "-p", "0.3"]), ("N5_Fy", ["-F", "y", "-N", "5", "-p", "0.5"]),
+     ("N4_p0.3", ["-N", "4", "-p", "0.3"]), ("alpha0.5_Fn", ["--alpha", "0.5"]), ("alpha0.6_Fy", ["--alpha", "0.6", "-F", "y"]),
+     ("external", ["-E", "test_pattern"])])
+
+
+def charge_patterns() -> None:
+    """tests/golden/charge_patterns.npz: VERTEX::q after INTERFACE::assign_random_q_values / assign_external_q_values of
+    the compiled reference on the 372-vertex mesh (q = 600) for the stripe patterns -N 3..17, yin-yang, cube, shuffled
+    (-F y), fractional-occupancy and external-file variants (src/interface.cpp:339-862)."""
+    scratch = os.path.join("/tmp", "npsl_golden")
+    os.makedirs(scratch, exist_ok=True)
+    mesh_file = os.path.join(REF, "bin", "infiles", "3_4.dat")
+    mesh = M.load_dat(mesh_file)
+    wd = refdump.make_workdir(mesh_file, 4, root=scratch)
+    os.makedirs(os.path.join(wd, "infiles", "Charge_Patterns"))
+    rng = np.random.default_rng(11)
+    idx = rng.permutation(mesh.n_vertices)[:300]
+    val = rng.uniform(-0.02, 0.05, size=300)
+    with open(os.path.join(wd, "infiles", "Charge_Patterns", "test_pattern.dat"), "w") as fh:
+        for i, v in zip(idx, val):
+            fh.write("%d %.12g\n" % (i, v))
+    out = {"file_q": mesh.file_q, "external_index": idx.astype(np.int32), "external_value": np.array([float("%.12g" % v) for v in val])}
+    for name, flags in CHARGE_CASES.items():
+        d = refdump.dump_at_step(wd, 4, ["-q", "600", "-c", "0.005"] + flags, 0)
+        out[name] = d["q"]
+        out[name + "_flags"] = np.array(" ".join(flags))
+        print("charges", name, "sum %.12g nonzero %d" % (d["q"].sum(), int(np.count_nonzero(d["q"]))), flush=True)
+    np.savez_compressed(os.path.join(GOLD, "charge_patterns.npz"), **out)
+    shutil.rmtree(wd, ignore_errors=True)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -224,6 +258,8 @@ def main() -> None:
         local_maps()
     if a.only in (None, "writers"):
         writers()
+    if a.only in (None, "charge_patterns"):
+        charge_patterns()
     for name in CONFIGS:
         if a.only and a.only != name:
             continue

@@ -74,6 +74,8 @@ struct Options {
     long row_lo = 0, row_hi = -1;
     int reps = 1;
     int warm = 0;
+    double alpha = 1.0;        // fractional charge occupancy (hard-wired to 1 in src/main.cpp:213)
+    std::string E = "None";    // external charge pattern, infiles/Charge_Patterns/<E>.dat (src/main.cpp:244-247)
     int local = 0;  // 1: also dump vertex areas / normals and the per-face local energy maps
 };
 
@@ -115,6 +117,8 @@ bool parse(int argc, char **argv, Options &o) {
         else if (a == "--reps") o.reps = atoi(need("--reps"));
         else if (a == "--warm") o.warm = atoi(need("--warm"));
         else if (a == "--local") o.local = atoi(need("--local"));
+        else if (a == "--alpha") o.alpha = atof(need("--alpha"));
+        else if (a == "-E") o.E = need("-E");
         else {
             std::fprintf(stderr, "unknown option %s\n", a.c_str());
             return false;
@@ -186,7 +190,10 @@ int main(int argc, char **argv) {
         boundary.inv_kappa_out = (0.257 / sqrt(z_out * boundary.lB_out * unit_radius_sphere * o.c)) / unit_radius_sphere;
 
     boundary.discretize(3, o.D);
-    boundary.assign_random_q_values(o.q, 1.0, o.N, o.p, o.F, o.H);
+    if (o.E == "None")
+        boundary.assign_random_q_values(o.q, o.alpha, o.N, o.p, o.F, o.H);
+    else
+        boundary.assign_external_q_values(o.q, o.E);
     boundary.dressup(lambda_a, lambda_v);
     boundary.ref_area = boundary.total_area;
     boundary.ref_volume = boundary.total_volume;

@@ -87,16 +87,19 @@ README_FINALS = {
     "janus_D4": (["-q", "600", "-c", "0.005", "-N", "2", "-p", "0.5"], 12.53, 1224.0, 1437.0),
     "buckled_D4": (["-q", "0", "-c", "0.005", "-t", "0", "-v", "0", "-b", "1", "-s", "1000", "-B", "y"],
                    12.3795, 26.86, 127.69),
+    # README.md:55-65: the yin-yang (-N 2 -H y) and cube (-H c, -b 80) patterns
+    "yinyang_D4": (["-q", "600", "-c", "0.005", "-N", "2", "-p", "0.5", "-H", "y"], 12.5099, 1218.48, 1433.25),
+    "cube_D4": (["-q", "600", "-c", "0.005", "-b", "80", "-H", "c"], 12.712, 2852.72, 3626.28),
 }
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(README_FINALS))
 def test_readme_final_values(name, tmp_path):
-    """The four README recipes, 25 000 steps each, through the C++ host driver."""
+    """The six README recipes, 25 000 steps each, through the C++ host driver."""
     build_host()
     flags, A, U, E = README_FINALS[name]
-    g = golden(name)
+    g = golden(name if name in ("disc_D4", "rod_D4", "janus_D4", "buckled_D4") else "disc_D4")  # all on infiles/3_4.dat
     M.write_dat(str(tmp_path / "m.dat"), M.Mesh(pos=g["pos0"], edges=g["edges"], faces=g["faces"]))
     r = subprocess.run([BIN, "--mesh", str(tmp_path / "m.dat"), "-S", "25000", "--out", str(tmp_path / "outfiles")]
                        + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)

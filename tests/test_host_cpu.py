@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT, golden, relerr
+from conftest import GOLD, ROOT, golden, relerr
 from np_shape_lab_b200 import capi
 from np_shape_lab_b200 import mesh as M
 
@@ -123,3 +123,78 @@ def test_product_package_never_touches_the_oracle():
                 src = open(os.path.join(dp, fn)).read()
                 for b in banned:
                     assert b not in src, (fn, b)
+
+
+# ---- charge patterns: stripes, yin-yang, cube, shuffled, external file -------------------------
+
+def _pattern_cases():
+    z = np.load(os.path.join(GOLD, "charge_patterns.npz"))
+    return z, sorted(k for k in z.files if k + "_flags" in z.files)
+
+
+def _pattern_kwargs(flags):
+    kw = dict(num_divisions=1, frac_patch=0.5, alpha=1.0, random_flag="n", function_flag="n")
+    names = {"-N": ("num_divisions", int), "-p": ("frac_patch", float), "-F": ("random_flag", str), "-H": ("function_flag", str),
+             "--alpha": ("alpha", float)}
+    ext = None
+    for f, v in zip(flags[::2], flags[1::2]):
+        if f == "-E":
+            ext = v
+        else:
+            kw[names[f][0]] = names[f][1](v)
+    return kw, ext
+
+
+def test_charge_patterns_match_reference(tmp_path):
+    """Every pattern of INTERFACE::assign_random_q_values / assign_external_q_values (src/interface.cpp:339-862) against
+    VERTEX::q of the compiled reference: stripes -N 3..17, yin-yang, cube, fractional occupancy, external file and the
+    shuffled (-F y) variants, whose srand(123456) + std::random_shuffle stream is reproduced (glibc / libstdc++)."""
+    z, cases = _pattern_cases()
+    g = golden("disc_D4")
+    mesh = M.Mesh(pos=g["pos0"], edges=g["edges"], faces=g["faces"], file_q=z["file_q"])
+    assert len(cases) >= 24
+    for name in cases:
+        kw, ext = _pattern_kwargs(str(z[name + "_flags"]).split())
+        if ext:
+            pat = tmp_path / "pattern.dat"
+            pat.write_text("".join("%d %.12g\n" % (i, v) for i, v in zip(z["external_index"], z["external_value"])))
+            q = M.assign_external_charges(mesh, 600.0, str(pat))
+        else:
+            q = M.assign_charges(mesh, 600.0, **kw)
+        ref = z[name]
+        assert np.array_equal(q == 0, ref == 0), name
+        assert np.max(np.abs(q - ref)) <= 1e-13 * np.max(np.abs(ref)), name
+
+
+def test_glibc_rand_stream():
+    """First outputs of srand(123456); rand() on glibc (known answers, checked against libc when it is glibc)."""
+    r = M.GlibcRand(123456)
+    mine = [r.rand() for _ in range(8)]
+    assert mine == [1303402199, 1406886723, 391888296, 1607856518, 940034812, 1299653596, 1439853304, 6265467]
+
+
+def test_host_cpp_charge_patterns_match_reference(tmp_path):
+    """The C++ host mirror's assign_random_q_values / assign_external_q_values through its driver (--dump-q prints the
+    charges and exits before any device work)."""
+    import subprocess
+    from np_shape_lab_b200 import build as B
+    B.build()
+    host = os.path.join(ROOT, "np-shape-lab_b200", "host_cpp")
+    subprocess.check_call(["make", "-s", "-C", host])
+    z, cases = _pattern_cases()
+    g = golden("disc_D4")
+    os.makedirs(tmp_path / "infiles" / "Charge_Patterns")
+    M.write_dat(str(tmp_path / "infiles" / "3_4.dat"), M.Mesh(pos=g["pos0"], edges=g["edges"], faces=g["faces"], file_q=z["file_q"]))
+    (tmp_path / "infiles" / "Charge_Patterns" / "test_pattern.dat").write_text(
+        "".join("%d %.12g\n" % (i, v) for i, v in zip(z["external_index"], z["external_value"])))
+    for name in cases:
+        flags = [f for f in str(z[name + "_flags"]).split()]
+        if "--alpha" in flags:
+            continue  # alpha is hard-wired to 1 in the reference's main() (src/main.cpp:213) and in the driver
+        r = subprocess.run([os.path.join(host, "np_shape_lab_b200"), "-D", "4", "-q", "600", "--dump-q", "1", "--out", ""] + flags,
+                           cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, (name, r.stderr)
+        q = np.array([float(x) for x in r.stdout.split("\n") if x and x[0] in "-0123456789"])
+        ref = z[name]
+        assert q.shape == ref.shape, (name, r.stdout[:200])
+        assert np.max(np.abs(q - ref)) <= 1e-13 * np.max(np.abs(ref)), name
