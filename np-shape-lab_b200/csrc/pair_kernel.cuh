@@ -39,7 +39,9 @@ constexpr int kPairThreads = 128;  // threads per CTA
 constexpr int kPairTileJ = 256;    // columns staged per shared-memory tile (8 KB)
 constexpr int kExpTab = 1 << NPSL_EXP2_TB;
 
-__constant__ double c_exp2_tab[kExpTab] = {NPSL_EXP2_TABLE};
+// 2^(j / 2^TB), j < 2^TB (8 KB at TB = 10): lives in global memory (L2-resident) and is staged into shared memory by every
+// CTA with coalesced loads; the per-lane lookups in the inner loop then hit shared memory.
+__device__ const double c_exp2_tab[kExpTab] = {NPSL_EXP2_TABLE};
 
 struct PairParams {
     double c2s;         // -log2(e)/lambda * 2^TB
@@ -80,8 +82,7 @@ __device__ __forceinline__ double exp2_neg(double r, double c2s, const double *_
     const double T = tab[n & (kExpTab - 1)];
     const int k = max(n >> NPSL_EXP2_TB, -1000);
     const double Tk = __hiloint2double(__double2hiint(T) + (k << 20), __double2loint(T));
-    double g = fma(f, NPSL_EXP2_G4, NPSL_EXP2_G3);
-    g = fma(g, f, NPSL_EXP2_G2);
+    double g = fma(f, NPSL_EXP2_G3, NPSL_EXP2_G2);
     g = fma(g, f, NPSL_EXP2_G1);
     double q = f * g;
     return fma(Tk, q, Tk);

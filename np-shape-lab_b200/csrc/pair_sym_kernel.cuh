@@ -128,9 +128,7 @@ __device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[R
             T[r] = __hiloint2double(__double2hiint(Tj) + (k << 20), __double2loint(Tj));
         }
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) b[r] = fma(f[r], NPSL_EXP2_G4, NPSL_EXP2_G3);
-#pragma unroll
-        for (int r = 0; r < ROWS; r++) b[r] = fma(b[r], f[r], NPSL_EXP2_G2);
+        for (int r = 0; r < ROWS; r++) b[r] = fma(f[r], NPSL_EXP2_G3, NPSL_EXP2_G2);
 #pragma unroll
         for (int r = 0; r < ROWS; r++) b[r] = fma(b[r], f[r], NPSL_EXP2_G1);
 #pragma unroll
