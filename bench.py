@@ -34,10 +34,10 @@ if ROOT not in sys.path:
 METRIC = "md_steps_per_s"
 UNIT = "steps/s"
 # FP64-pipe instructions the pair kernel executes per ORDERED pair, counted in the SASS of the inner loops
-# (tools/sass_count.py -> profiles/r01_pair_sass_count.txt): k_pair_sym evaluates each unordered pair once
-# with 32.75 instructions (131 per 4 pairs, incl. the column accumulator update) = 16.375 per ordered pair;
-# the ordered k_pair needs 28 (force only).
-DFMA_PER_PAIR = {2: 16.375, 1: 28}
+# (tools/sass_count.py -> profiles/r01_pair_sass_count_v4.txt): k_pair_sym evaluates each unordered pair once
+# with 31.75 instructions (127 per 4 pairs, incl. the column accumulator update) = 15.875 per ordered pair;
+# the ordered k_pair needs 27 (force only).
+DFMA_PER_PAIR = {2: 15.875, 1: 27}
 ALGORITHMIC_FLOPS_PER_PAIR = 24  # force-only, exp and rsqrt counted as one flop each
 
 

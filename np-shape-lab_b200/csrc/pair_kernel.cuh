@@ -19,9 +19,9 @@
 // independent of how rows are sharded across GPUs. No atomics, no tensor cores (this is an
 // N-body with a transcendental per pair, not a contraction).
 //
-// FP64-pipe work per ordered pair: 28 instructions force-only, 30 with energy:
+// FP64-pipe work per ordered pair: 27 instructions force-only, 28.5 with energy:
 //   3 sub, 3 r^2, 5 rsqrt (MUFU.RSQ64H seed + one third-order step), 1 r, 3 range reduction,
-//   5 exp (128-entry 2^(j/128) table in shared memory + degree-4 polynomial), 5 force factor, 3 FMA.
+//   4 exp (1024-entry 2^(j/1024) table in shared memory + cubic polynomial), 5 force factor, 3 FMA.
 // exp: x = -r/lambda <= 0, so 2^x = 2^k T[j] (1 + f g(f)) needs no overflow / NaN handling; k is
 // clamped at -1000 on the integer pipe. exp and rsqrt hold <= 3e-16 relative error.
 // On B200 the FP64 pipe is limited by register-file operand bandwidth (tools/ubench/fp64_pipe.cu): an

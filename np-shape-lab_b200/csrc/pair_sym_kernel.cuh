@@ -15,9 +15,9 @@
 // row block) in a fixed order, and k_vertex adds the 8 results: the value does not depend on which GPU computed which
 // unit, so trajectories are bit-identical on 1, 2, 4 and 8 GPUs.
 //
-// FP64-pipe work per unordered pair: 32.75 instructions (20 for r, 1/r, exp; 4 for the geometry factor;
+// FP64-pipe work per unordered pair: 31.75 instructions (19 for r, 1/r, exp; 4 for the geometry factor;
 // 2 charge products; 6 FMA into the two accumulators; 3 adds per 4 pairs for the column update)
-// = 16.4 per ordered pair, against 28 in k_pair (tools/sass_count.py).
+// = 15.9 per ordered pair, against 27 in k_pair (tools/sass_count.py).
 #pragma once
 #include "pair_kernel.cuh"
 #include "xchg.cuh"
