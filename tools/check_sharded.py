@@ -2,7 +2,7 @@
 single-GPU one. Rank 0 also runs an unsharded context on its own GPU and compares positions,
 velocities, forces, kinetic energy and thermostat state after a number of steps.
 
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_sharded.py [workload] [steps]
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_sharded.py [workload] [steps] [GV]
 """
 import os
 import sys
@@ -16,6 +16,7 @@ from np_shape_lab_b200 import capi, workloads as W
 
 name = sys.argv[1] if len(sys.argv) > 1 else "S32_disc"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+constrained = len(sys.argv) > 3 and sys.argv[3] == "GV"  # rigid volume constraint (replicated plan only)
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -30,7 +31,11 @@ vel = 0.01 * rng.standard_normal(pos.shape)
 
 ctx = capi.Context(w.mesh.edges, w.mesh.faces, w.params["l0"], P, n_vertices=n, rank=rank, world=world, nccl_id=box[0])
 ctx.upload_state(pos, vel, w.q)
+if constrained:
+    ctx.set_volume_constraint(True)
 ctx.force_init()
+if constrained:
+    ctx.constraint_init()
 e0 = ctx.energy()
 ctx.step(steps)
 e1 = ctx.energy()
@@ -44,7 +49,11 @@ ok = True
 if rank == 0:
     with capi.Context(w.mesh.edges, w.mesh.faces, w.params["l0"], P, n_vertices=n) as one:
         one.upload_state(pos, vel, w.q)
+        if constrained:
+            one.set_volume_constraint(True)
         one.force_init()
+        if constrained:
+            one.constraint_init()
         f0 = one.energy()
         one.step(steps)
         f1 = one.energy()
