@@ -51,6 +51,9 @@ CONFIGS = {
     # rigid volume constraint (SHAKE / RATTLE, src/functions.h:33-171); the cubic comes from oracle/shim/gsl/gsl_poly.h
     "disc_D4_GV": ("ref:3_4", 4, DISC + ["-G", "V"], [0, 1, 2], [250, 500, 1000]),
     "janus_D8_GV": ("ref:3_8", 8, JANUS + ["-G", "V"], [0, 1], [500, 1000]),
+    # explicit counterions: 64 monovalent ions placed by the driver (the reference's own placement
+    # loop cannot terminate with its hard-wired box, see oracle/ref_driver.cpp:place_ions)
+    "disc_D4_ions": ("ref:3_4", 4, DISC + ["--ions", "64"], [0, 1, 2], [100, 250, 500]),
 }
 
 FULL_KEYS = ["pos", "vel", "force", "bforce", "sforce", "tforce", "vforce", "pforce", "itsS", "face_area",
@@ -88,14 +91,26 @@ def build(name: str, threads: int | None) -> None:
         out["k%d_scalars" % k] = d["scalars"]
         out["k%d_mesh_bath" % k] = d["mesh_bath"]
         out["k%d_ions_bath" % k] = d["ions_bath"]
+        if "ion_q" in d:
+            if k == full_steps[0]:
+                out["ion_q"] = d["ion_q"]
+                out["ion_pos0"] = d["ion_pos"]
+                out["ion_params"] = np.array([d["ion_diameter"], d["lj_length_mesh_ions"]])
+            for key in ("ion_pos", "ion_vel", "ion_force"):
+                out["k%d_%s" % (k, key)] = d[key]
+            out["k%d_netIonKE" % k] = np.array(d["netIonKE"])
         print(name, "step", k, "E=%.12g" % d["energy"], flush=True)
     for k in traj_steps:
         d = refdump.dump_at_step(wd, D, flags, k, threads=threads, writedata=k)
         out["k%d_scalars" % k] = d["scalars"]
         out["k%d_mesh_bath" % k] = d["mesh_bath"]
         out["k%d_ions_bath" % k] = d["ions_bath"]
+        if "ion_q" in d:
+            out["k%d_netIonKE" % k] = np.array(d["netIonKE"])
         if k == traj_steps[-1]:
             out["k%d_pos" % k] = d["pos"]
+            if "ion_q" in d:
+                out["k%d_ion_pos" % k] = d["ion_pos"]
         print(name, "step", k, "A=%.10g U=%.10g E=%.10g" % (d["total_area"], d["penergy"], d["energy"]), flush=True)
     out["full_steps"] = np.array(full_steps, dtype=np.int64)
     out["traj_steps"] = np.array(traj_steps, dtype=np.int64)

@@ -59,6 +59,12 @@ typedef struct {
     int chain;
     bath_t mesh_bath[16], ions_bath[16];
     int constraint; /* 1: rigid volume constraint, geomConstraint 'V', linear form */
+    /* explicit counterions, src/particle.h (mass 1); all of one diameter */
+    int n_ions;
+    vec3 *ion_pos, *ion_vel, *ion_for;
+    double *ion_q, *ion_ke;
+    double ion_diameter, lj_length_mesh_ions, netIonKE;
+    ld ions_ke;
 } npo_t;
 
 /* ---------------------------------------------------------------- construction */
@@ -136,6 +142,7 @@ void npo_destroy(void *hh) {
     free(h->l0); free(h->pos); free(h->vel); free(h->forvec); free(h->pforce); free(h->bforce); free(h->sforce);
     free(h->tforce); free(h->vforce); free(h->negGradV); free(h->negGradA); free(h->f_dir); free(h->f_gradA);
     free(h->q); free(h->ke); free(h->f_area); free(h->f_vol); free(h->e_S);
+    free(h->ion_pos); free(h->ion_vel); free(h->ion_for); free(h->ion_q); free(h->ion_ke);
     free(h);
 }
 
@@ -222,7 +229,26 @@ static void neg_vgrads(npo_t *h) {
 
 /* ---------------------------------------------------------------- pair term */
 
-/* force_calculation mesh-mesh loop, src/newforces.cpp:153-177 (init twin :18-42), rows [lo,hi] */
+/* one LJ + ES pair force on the particle at p1 (charge q1) from the one at p2, LJ length d: the body shared by the
+ * mesh-mesh, mesh-ion and ion-ion loops of src/newforces.cpp:153-250 */
+static vec3 pair_force(const npo_t *h, vec3 p1, vec3 p2, double q1, double q2, double d) {
+    vec3 lj = v3(0, 0, 0);
+    vec3 r_vec = vsub(p1, p2);
+    double r = (double) vnorm(r_vec);
+    double r2 = (double) vdot(r_vec, r_vec);
+    double d2 = d * d;
+    if (r2 < dcut2 * d2) {
+        double r6 = r2 * r2 * r2, r12 = r6 * r6, d6 = d2 * d2 * d2, d12 = d6 * d6;
+        lj = vscale(r_vec, 48 * h->elj * ((d12 / r12) - 0.5 * (d6 / r6)) * (1 / r2));
+    }
+    double s1 = (-h->scalefactor * q1 * q2 / h->em) * (exp(-(1.0 / h->inv_kappa_out) * r));
+    vec3 es = vscale(vscale(r_vec, (1 / r2)), s1);
+    es = vscale(es, ((-1.0 / r) - (1.0 / h->inv_kappa_out)));
+    return vadd(lj, es);
+}
+
+/* force_calculation mesh-mesh loop, src/newforces.cpp:153-177 (init twin :18-42), rows [lo,hi], followed by the
+ * mesh-ion and ion-ion loops when there are counterions */
 static void pair_forces(npo_t *h, int lo, int hi) {
     const int n = h->nv;
     for (int i = 0; i < n; i++) h->pforce[i] = v3(0, 0, 0);
@@ -245,8 +271,36 @@ static void pair_forces(npo_t *h, int lo, int hi) {
             es = vscale(es, ((-1.0 / r) - (1.0 / h->inv_kappa_out)));
             acc = vadd(acc, vadd(lj, es));
         }
+        for (int j = 0; j < h->n_ions; j++) /* the mesh-ion component (for mesh), src/newforces.cpp:179-200 */
+            acc = vadd(acc, pair_force(h, h->pos[i], h->ion_pos[j], h->q[i], h->ion_q[j], h->lj_length_mesh_ions));
         h->pforce[i] = acc;
     }
+    /* ion rows, src/newforces.cpp:203-250 */
+#pragma omp parallel for schedule(dynamic)
+    for (int i = 0; i < h->n_ions; i++) {
+        vec3 acc = v3(0, 0, 0);
+        for (int j = 0; j < h->n_ions; j++) {
+            if (i == j) continue;
+            acc = vadd(acc, pair_force(h, h->ion_pos[i], h->ion_pos[j], h->ion_q[i], h->ion_q[j], h->ion_diameter));
+        }
+        for (int j = 0; j < n; j++)
+            acc = vadd(acc, pair_force(h, h->ion_pos[i], h->pos[j], h->ion_q[i], h->q[j], h->lj_length_mesh_ions));
+        h->ion_for[i] = acc;
+    }
+}
+
+static double pair_lj(const npo_t *h, vec3 p1, vec3 p2, double d) { /* energy_lj_pair, src/newenergies.cpp:4-17 */
+    vec3 r_vec = vsub(p1, p2);
+    double r2 = (double) vdot(r_vec, r_vec), d2 = d * d;
+    if (r2 < dcut2 * d2) {
+        double r6 = r2 * r2 * r2, d6 = d2 * d2 * d2;
+        return 4 * h->elj * (d6 / r6) * ((d6 / r6) - 1) + h->elj;
+    }
+    return 0;
+}
+static double pair_es(const npo_t *h, vec3 p1, vec3 p2, double q1, double q2) { /* energy_es_pair, :21-40 */
+    double r = (double) vnorm(vsub(p1, p2));
+    return h->scalefactor * q1 * q2 * (exp(-(1.0 / h->inv_kappa_out) * r)) / (h->em * r);
 }
 
 /* energy_lj_pair / energy_es_pair, src/newenergies.cpp:4-25; loop src/interface.cpp:1046-1065 */
@@ -270,9 +324,26 @@ static void pair_energies(npo_t *h, int lo, int hi, double *lj_out, double *es_o
         }
         lj_row[i] = 0.5 * lj;
         es_row[i] = 0.5 * es;
+        double lj_mi = 0, es_mi = 0; /* mesh-ion, counted once: src/interface.cpp:1059-1064 */
+        for (int j = 0; j < h->n_ions; j++) {
+            lj_mi += pair_lj(h, h->pos[i], h->ion_pos[j], h->lj_length_mesh_ions);
+            es_mi += pair_es(h, h->pos[i], h->ion_pos[j], h->q[i], h->ion_q[j]);
+        }
+        lj_row[i] += lj_mi;
+        es_row[i] += es_mi;
     }
     double lj_t = 0, es_t = 0;
     for (int i = lo; i <= hi; i++) { lj_t += lj_row[i]; es_t += es_row[i]; }
+    for (int i = 0; i < h->n_ions; i++) { /* ion-ion, src/interface.cpp:1072-1089 */
+        double lj = 0, es = 0;
+        for (int j = 0; j < h->n_ions; j++) {
+            if (i == j) continue;
+            lj += pair_lj(h, h->ion_pos[i], h->ion_pos[j], h->ion_diameter);
+            es += pair_es(h, h->ion_pos[i], h->ion_pos[j], h->ion_q[i], h->ion_q[j]);
+        }
+        lj_t += 0.5 * lj;
+        es_t += 0.5 * es;
+    }
     free(lj_row); free(es_row);
     *lj_out = lj_t; *es_out = es_t;
 }
@@ -379,6 +450,13 @@ void npo_force(void *hh, int lo, int hi) {
 }
 
 /* compute_kinetic_energy, src/newenergies.h:8-16; VERTEX::real_kinetic_energy src/vertex.h:111-114 */
+static ld ion_kinetic_energy(npo_t *h) { /* src/newenergies.h:18-26, src/particle.h:86-90 */
+    for (int i = 0; i < h->n_ions; i++) h->ion_ke[i] = (double) (0.5 * 1.0 * vdot(h->ion_vel[i], h->ion_vel[i]));
+    ld ke = 0;
+    for (int i = 0; i < h->n_ions; i++) ke += h->ion_ke[i];
+    return ke;
+}
+
 static ld kinetic_energy(npo_t *h) {
     for (int v = 0; v < h->nv; v++) h->ke[v] = (double) (0.5 * 1.0 * vdot(h->vel[v], h->vel[v]));
     ld ke = 0;
@@ -414,7 +492,9 @@ void npo_energy(void *hh, int lo, int hi, double *out) {
     h->penergy = 0;
     h->penergy += h->bE; h->penergy += h->sE; h->penergy += h->tE; h->penergy += h->volE;
     h->penergy += h->ljE + h->esE;
-    h->energy = h->netMeshKE + 0 + h->penergy;
+    h->netIonKE = 0; /* src/interface.cpp:970-972 */
+    for (int i = 0; i < h->n_ions; i++) h->netIonKE += h->ion_ke[i];
+    h->energy = h->netMeshKE + h->netIonKE + h->penergy;
     out[0] = h->netMeshKE; out[1] = h->bE; out[2] = h->sE; out[3] = h->tE; out[4] = h->ljE; out[5] = h->esE;
     out[6] = h->volE; out[7] = h->penergy; out[8] = h->energy;
 }
@@ -496,9 +576,11 @@ static void update_eta(bath_t *b, double dt) { /* src/thermostat.h:53-58 */
 void npo_md_init(void *hh) {
     npo_t *h = (npo_t *) hh;
     for (int v = 0; v < h->nv; v++) h->vel[v] = v3(0, 0, 0);
+    for (int i = 0; i < h->n_ions; i++) h->ion_vel[i] = v3(0, 0, 0);
     npo_dressup(h);
     npo_force(h, 0, h->nv - 1);
     h->vertex_ke = kinetic_energy(h);
+    h->ions_ke = ion_kinetic_energy(h);
 }
 
 /* compute_kinetic_energy at the current velocities (src/newmd.cpp:52) without the velocity reset of
@@ -506,6 +588,7 @@ void npo_md_init(void *hh) {
 void npo_refresh_ke(void *hh) {
     npo_t *h = (npo_t *) hh;
     h->vertex_ke = kinetic_energy(h);
+    h->ions_ke = ion_kinetic_energy(h);
 }
 
 /* gsl_poly_solve_cubic as the reference calls it (src/functions.h:102): GSL is a third-party dependency that is
@@ -581,7 +664,7 @@ void npo_md_step(void *hh) {
     npo_t *h = (npo_t *) hh;
     const double dt = h->dt;
     const int C = h->chain;
-    ld ions_ke = 0;
+    ld ions_ke = h->ions_ke;
     for (int j = C - 1; j > -1; j--) update_chain_xi(j, h->mesh_bath, dt, h->vertex_ke);
     for (int j = C - 1; j > -1; j--) update_chain_xi(j, h->ions_bath, dt, ions_ke);
     for (int j = 0; j < C; j++) update_eta(&h->mesh_bath[j], dt);
@@ -589,14 +672,20 @@ void npo_md_step(void *hh) {
     double expfac = exp(-0.5 * dt * h->mesh_bath[0].xi);
     ld ef = expfac;
     ld kick = 0.5 * dt * sqrtl(ef); /* VERTEX::update_real_velocity, src/vertex.h:105-108 */
+    ld ef_i = (ld) exp(-0.5 * dt * h->ions_bath[0].xi); /* expfac_ions is a long double holding a double, src/newmd.cpp:110 */
+    ld kick_i = 0.5 * dt * sqrtl(ef_i);                  /* PARTICLE::update_real_velocity, src/particle.h:79-83 */
     for (int v = 0; v < h->nv; v++) h->vel[v] = vadd(vscale(h->vel[v], ef), vscale(h->forvec[v], kick));
+    for (int i = 0; i < h->n_ions; i++) h->ion_vel[i] = vadd(vscale(h->ion_vel[i], ef_i), vscale(h->ion_for[i], kick_i));
     for (int v = 0; v < h->nv; v++) h->pos[v] = vadd(h->pos[v], vscale(h->vel[v], dt));
+    for (int i = 0; i < h->n_ions; i++) h->ion_pos[i] = vadd(h->ion_pos[i], vscale(h->ion_vel[i], dt));
     if (h->constraint) shake(h); /* src/newmd.cpp:126 */
     npo_dressup(h);
     npo_force(h, 0, h->nv - 1);
     for (int v = 0; v < h->nv; v++) h->vel[v] = vadd(vscale(h->vel[v], ef), vscale(h->forvec[v], kick));
+    for (int i = 0; i < h->n_ions; i++) h->ion_vel[i] = vadd(vscale(h->ion_vel[i], ef_i), vscale(h->ion_for[i], kick_i));
     if (h->constraint) rattle(h); /* src/newmd.cpp:152 */
     h->vertex_ke = kinetic_energy(h);
+    h->ions_ke = ions_ke = ion_kinetic_energy(h);
     for (int j = 0; j < C; j++) update_eta(&h->mesh_bath[j], dt);
     for (int j = 0; j < C; j++) update_eta(&h->ions_bath[j], dt);
     for (int j = 0; j < C; j++) update_chain_xi(j, h->mesh_bath, dt, h->vertex_ke);
@@ -620,6 +709,41 @@ void npo_bath_energies(void *hh, double *out) {
     }
     out[0] = mk; out[1] = mp; out[2] = ik; out[3] = ip;
 }
+
+/* ---------------------------------------------------------------- explicit counterions */
+
+/* counterions as main() hands them to md_interface (vector<PARTICLE>, src/particle.h): positions, velocities, charges;
+ * one diameter (the ion-ion LJ length, src/newforces.cpp:214) and INTERFACE::lj_length_mesh_ions (src/main.cpp:271-272) */
+void npo_set_ions(void *hh, int n, const double *pos, const double *vel, const double *q, double diameter,
+                  double lj_length_mesh_ions) {
+    npo_t *h = (npo_t *) hh;
+    free(h->ion_pos); free(h->ion_vel); free(h->ion_for); free(h->ion_q); free(h->ion_ke);
+    h->n_ions = n;
+    h->ion_pos = (vec3 *) calloc(n > 0 ? n : 1, sizeof(vec3));
+    h->ion_vel = (vec3 *) calloc(n > 0 ? n : 1, sizeof(vec3));
+    h->ion_for = (vec3 *) calloc(n > 0 ? n : 1, sizeof(vec3));
+    h->ion_q = (double *) calloc(n > 0 ? n : 1, sizeof(double));
+    h->ion_ke = (double *) calloc(n > 0 ? n : 1, sizeof(double));
+    for (int i = 0; i < n; i++) {
+        h->ion_pos[i] = v3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+        if (vel) h->ion_vel[i] = v3(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
+        h->ion_q[i] = q[i];
+    }
+    h->ion_diameter = diameter;
+    h->lj_length_mesh_ions = lj_length_mesh_ions;
+    h->ions_ke = ion_kinetic_energy(h);
+}
+
+/* what: 0 pos 1 vel 2 force */
+void npo_get_ions(void *hh, int what, double *out) {
+    npo_t *h = (npo_t *) hh;
+    const vec3 *src[3] = {h->ion_pos, h->ion_vel, h->ion_for};
+    for (int i = 0; i < h->n_ions; i++) {
+        out[3 * i] = (double) src[what][i].x; out[3 * i + 1] = (double) src[what][i].y; out[3 * i + 2] = (double) src[what][i].z;
+    }
+}
+
+double npo_ions_ke(void *hh) { return (double) ((npo_t *) hh)->netIonKE; }
 
 /* ---------------------------------------------------------------- accessors */
 

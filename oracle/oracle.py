@@ -48,6 +48,10 @@ def lib():
         L.npo_get_vec.argtypes = [vp, C.c_int, dp]
         L.npo_get_scalars.argtypes = [vp, dp]
         L.npo_get_edge_S.argtypes = [vp, dp]
+        L.npo_set_ions.argtypes = [vp, C.c_int, dp, dp, dp, C.c_double, C.c_double]
+        L.npo_get_ions.argtypes = [vp, C.c_int, dp]
+        L.npo_ions_ke.argtypes = [vp]
+        L.npo_ions_ke.restype = C.c_double
         L.npo_vertex_geometry.argtypes = [vp, dp, dp]
         L.npo_local_energies.argtypes = [vp, dp]
         _lib = L
@@ -164,3 +168,21 @@ class Oracle:
         self.L.npo_local_energies(self.h, _dp(out))
         return {"electrostatic": out[:, 0].copy(), "elastic": out[:, 1].copy(), "bending": out[:, 2].copy(),
                 "stretching": out[:, 3].copy()}
+
+    def set_ions(self, pos, vel, q, diameter: float, lj_length_mesh_ions: float):
+        """Explicit counterions (vector<PARTICLE>): positions, velocities (or None), charges."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        vel = None if vel is None else np.ascontiguousarray(vel, dtype=np.float64)
+        self.n_ions = int(pos.shape[0])
+        self.L.npo_set_ions(self.h, self.n_ions, _dp(pos), _dp(vel) if vel is not None else None, _dp(q), float(diameter),
+                            float(lj_length_mesh_ions))
+
+    def ions(self, what: str) -> np.ndarray:
+        out = np.zeros((self.n_ions, 3))
+        self.L.npo_get_ions(self.h, {"pos": 0, "vel": 1, "force": 2}[what], _dp(out))
+        return out
+
+    def ions_ke(self) -> float:
+        """INTERFACE::netIonKE of the last energy() call."""
+        return float(self.L.npo_ions_ke(self.h))

@@ -74,6 +74,8 @@ struct Options {
     long row_lo = 0, row_hi = -1;
     int reps = 1;
     int warm = 0;
+    int ions = 0;              // explicit counterions placed by place_ions() (the reference's own put_counterions cannot
+                               // terminate with its hard-wired box_halflength = 1, src/main.cpp:194, src/interface.cpp:907-958)
     double alpha = 1.0;        // fractional charge occupancy (hard-wired to 1 in src/main.cpp:213)
     std::string E = "None";    // external charge pattern, infiles/Charge_Patterns/<E>.dat (src/main.cpp:244-247)
     int local = 0;  // 1: also dump vertex areas / normals and the per-face local energy maps
@@ -118,6 +120,7 @@ bool parse(int argc, char **argv, Options &o) {
         else if (a == "--warm") o.warm = atoi(need("--warm"));
         else if (a == "--local") o.local = atoi(need("--local"));
         else if (a == "--alpha") o.alpha = atof(need("--alpha"));
+        else if (a == "--ions") o.ions = atoi(need("--ions"));
         else if (a == "-E") o.E = need("-E");
         else {
             std::fprintf(stderr, "unknown option %s\n", a.c_str());
@@ -129,6 +132,26 @@ bool parse(int argc, char **argv, Options &o) {
 
 void pv(FILE *f, const char *name, size_t i, VECTOR3D &a) {
     std::fprintf(f, "%s %zu %.21Lg %.21Lg %.21Lg\n", name, i, a.x, a.y, a.z);
+}
+
+// Deterministic stand-in for INTERFACE::put_counterions: monovalent counterions (PARTICLE(id, diameter, valency,
+// -valency, m = 1, pos), src/interface.cpp:944) on a shell around the unit sphere from a fixed LCG; a few are put close
+// to the membrane (inside the mesh-ion WCA cutoff) and two closer to each other than one ion diameter, so that every
+// branch of the mesh-ion and ion-ion loops (src/newforces.cpp:44-65,179-250) is exercised.
+void place_ions(std::vector<PARTICLE> &ions, int n, double diameter) {
+    unsigned long long st = 88172645463325252ULL;
+    auto rnd = [&]() {
+        st = st * 6364136223846793005ULL + 1442695040888963407ULL;
+        return (double) (st >> 11) * (1.0 / 9007199254740992.0);
+    };
+    for (int k = 0; k < n; k++) {
+        double z = 2 * rnd() - 1, phi = 6.283185307179586 * rnd();
+        double rad = (k % 16 == 0) ? 1.09 + 0.03 * rnd() : 1.3 + 0.5 * rnd();
+        double s = std::sqrt(1 - z * z);
+        VECTOR3D p(rad * s * std::cos(phi), rad * s * std::sin(phi), rad * z);
+        if (k == 1 && n > 1) p = ions[0].posvec + VECTOR3D(0.8 * diameter, 0.1 * diameter, 0);  // overlapping pair
+        ions.push_back(PARTICLE(k + 1, diameter, 1, -1.0, 1.0, p));
+    }
 }
 
 double now_s() {
@@ -143,7 +166,7 @@ int main(int argc, char **argv) {
 
     INTERFACE boundary;
     CONTROL mdremote;
-    vector<PARTICLE> counterions;  // explicit counterions are a "next" row; always empty here
+    vector<PARTICLE> counterions;  // empty unless --ions M
 
     boundary.sigma_a = o.t;
     boundary.sigma_v = o.v;
@@ -203,6 +226,7 @@ int main(int argc, char **argv) {
     boundary.lj_length_mesh_ions = ((2.0 * meshPointRadius + counterion_diameter) / 2.0);
     boundary.elj = 1.0;
 
+    if (o.ions > 0) place_ions(counterions, o.ions, counterion_diameter);
     vector<THERMOSTAT> mesh_bath, ions_bath;
     if (chain_length == 1) {
         mesh_bath.push_back(THERMOSTAT(0, T, 3 * boundary.V.size(), 0.0, 0, 0));
@@ -223,8 +247,8 @@ int main(int argc, char **argv) {
     upperBoundMesh = boundary.V.size() - 1;
     sizFVecMesh = boundary.V.size();
     lowerBoundIons = 0;
-    upperBoundIons = -1;
-    sizFVecIons = 0;
+    upperBoundIons = (int) counterions.size() - 1;
+    sizFVecIons = counterions.size();
 
     const size_t N = boundary.V.size();
 
@@ -328,6 +352,20 @@ int main(int argc, char **argv) {
         }
         ljE += 0.5L * lj_i;
         esE += 0.5L * es_i;
+        for (size_t j = 0; j < counterions.size(); j++) {  // mesh-ion, counted once (src/interface.cpp:1059-1062)
+            ljE += energy_lj_pair(boundary.V[i].posvec, counterions[j].posvec, boundary.lj_length_mesh_ions, boundary.elj);
+            esE += energy_es_pair(boundary.V[i], counterions[j], boundary.em, boundary.inv_kappa_out, scalefactor);
+        }
+    }
+    for (size_t i = 0; i < counterions.size(); i++) {  // ion-ion (src/interface.cpp:1073-1084)
+        long double lj_i = 0, es_i = 0;
+        for (size_t j = 0; j < counterions.size(); j++) {
+            if (i == j) continue;
+            lj_i += energy_lj_pair(counterions[i].posvec, counterions[j].posvec, counterions[0].diameter, boundary.elj);
+            es_i += energy_es_pair(counterions[i], counterions[j], boundary.em, boundary.inv_kappa_out, scalefactor);
+        }
+        ljE += 0.5L * lj_i;
+        esE += 0.5L * es_i;
     }
     long double psum = bE + sE + tE + volE + ljE + esE;
     std::fprintf(f, "bE %.21Lg\nsE %.21Lg\ntE %.17g\nvolE %.17g\nljE %.21Lg\nesE %.21Lg\npenergy_check %.21Lg\n", bE,
@@ -364,6 +402,15 @@ int main(int argc, char **argv) {
         pv(f, "vfo", i, V.VolTForce);
         VECTOR3D pair = V.forvec - V.bforce - V.sforce - V.TForce - V.VolTForce;
         pv(f, "pfo", i, pair);
+    }
+    std::fprintf(f, "n_ions %zu\nion_diameter %.17g\nlj_length_mesh_ions %.17g\nnetIonKE %.17g\n", counterions.size(),
+                 counterion_diameter, boundary.lj_length_mesh_ions, boundary.netIonKE);
+    for (size_t i = 0; i < counterions.size(); i++) {
+        PARTICLE &P = counterions[i];
+        std::fprintf(f, "ionq %zu %.17g\n", i, P.q);
+        pv(f, "ipos", i, P.posvec);
+        pv(f, "ivel", i, P.velvec);
+        pv(f, "ifor", i, P.forvec);
     }
     for (size_t i = 0; i < boundary.E.size(); i++)
         std::fprintf(f, "edge %zu %u %u %.17g %.17g\n", i, boundary.E[i].itsV[0]->index, boundary.E[i].itsV[1]->index,

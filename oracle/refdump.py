@@ -76,6 +76,7 @@ def parse_dump(path: str) -> dict:
     baths: dict = {"mesh_bath": [], "ions_bath": []}
     edges, faces = [], []
     varea, lface = [], []
+    ions = {"ionq": [], "ipos": [], "ivel": [], "ifor": []}
     q = None
     for line in lines:
         t = line.split()
@@ -95,6 +96,8 @@ def parse_dump(path: str) -> dict:
             edges.append([int(t[2]), int(t[3]), float(t[4]), float(t[5])])
         elif k == "face":
             faces.append([int(t[2]), int(t[3]), int(t[4]), float(t[5]), float(t[6])])
+        elif k in ions:
+            ions[k].append([float(x) for x in t[2:]])
         elif k == "varea":
             varea.append([float(x) for x in t[2:6]])
         elif k == "lface":
@@ -117,6 +120,9 @@ def parse_dump(path: str) -> dict:
         va = np.array(varea)
         d["vertex_area"], d["vertex_normal"] = va[:, 0].copy(), va[:, 1:4].copy()
         d["local_faces"] = np.array(lface)  # [F, 4]: electrostatic, elastic, bending, stretching
+    if ions["ionq"]:  # --ions M
+        d["ion_q"] = np.array(ions["ionq"])[:, 0].copy()
+        d["ion_pos"], d["ion_vel"], d["ion_force"] = np.array(ions["ipos"]), np.array(ions["ivel"]), np.array(ions["ifor"])
     d["scalars"] = np.array([d[s] for s in SCALARS])
     d["params"] = np.array([d[s] for s in PARAMS])
     assert d["edges"].shape[0] == e and d["faces"].shape[0] == f

@@ -153,3 +153,37 @@ def test_oracle_row_slices_add_up():
         assert relerr(pf, full.vec("pforce")) < 1e-15
         assert abs(es - ef["esE"]) < 1e-12 * abs(ef["esE"])
         assert lj == ef["ljE"] == 0.0
+
+
+def make_ion_oracle(g):
+    o = make_oracle(g)
+    o.set_ions(g["ion_pos0"], None, g["ion_q"], float(g["ion_params"][0]), float(g["ion_params"][1]))
+    return o
+
+
+def test_oracle_counterions_match_reference():
+    """Explicit counterions (mesh-ion and ion-ion loops of src/newforces.cpp:44-65,179-250, their energies
+    src/interface.cpp:1059-1089, the ion half-kicks / drift and the ion Nose-Hoover chain driven by the ions' kinetic
+    energy, src/newmd.cpp:99-170) against the compiled reference run with 64 hand-placed ions, some inside the
+    mesh-ion WCA cutoff and two overlapping."""
+    g = golden("disc_D4_ions")
+    o = make_ion_oracle(g)
+    o.md_init()
+    done = 0
+    for k in g.full_steps:
+        o.md_steps(k - done)
+        done = k
+        check_step(o, g, k)
+        fi = g["k%d_ion_force" % k]
+        assert relerr(o.ions("force"), fi) < 1e-12
+        assert relerr(o.ions("pos"), g["k%d_ion_pos" % k]) < 1e-13
+        assert relerr(o.ions("vel"), g["k%d_ion_vel" % k], floor=1e-12) < 1e-12
+        assert abs(o.ions_ke() - float(g["k%d_netIonKE" % k])) <= 1e-12 * max(float(g["k%d_netIonKE" % k]), 1e-9)
+    for k in g.traj_steps:
+        o.md_steps(k - done)
+        done = k
+        e, s = o.energy(), g.scalars(k)
+        assert abs(e["penergy"] - s["penergy"]) < 1e-9 * abs(s["penergy"])
+        assert abs(e["energy"] - s["energy"]) < 1e-9 * abs(s["energy"])
+        assert abs(o.ions_ke() - float(g["k%d_netIonKE" % k])) <= 1e-8 * float(g["k%d_netIonKE" % k])
+    assert relerr(o.ions("pos"), g["k%d_ion_pos" % g.traj_steps[-1]]) < 1e-8
