@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NPSL_ABI_VERSION 1
+#define NPSL_ABI_VERSION 2
 #define NPSL_MAX_CHAIN 16   /* links per Nose-Hoover chain, incl. the Q=0 dummy tail */
 #define NPSL_MAX_DEGREE 8   /* maximum vertex valence supported by the gather kernels */
 #define NPSL_NCCL_ID_BYTES 128
@@ -92,6 +92,7 @@ typedef struct {
     double energy;         /* INTERFACE::energy = KE + penergy                      */
     double mesh_bath_ke, mesh_bath_pe, ions_bath_ke, ions_bath_pe; /* src/newenergies.h:28-46 */
     double total_area, total_volume;                               /* INTERFACE::total_*      */
+    double ions_kinetic;   /* INTERFACE::netIonKE (0 without counterions); energy = kinetic + ions_kinetic + potential */
 } npsl_energies;
 
 /* ---- life cycle ------------------------------------------------------------------------ */
@@ -192,6 +193,20 @@ int npsl_constraint_multipliers(npsl_ctx *ctx, double *shake_lambda, double *rat
 
 /* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
 int64_t npsl_launch_count(const npsl_ctx *ctx);
+/* ---- explicit counterions ----------------------------------------------------------------------------------
+ * vector<PARTICLE> counterions as main() hands it to force_calculation / compute_energy / md_interface
+ * (src/particle.h; masses are 1 like the reference's): pos[n][3], vel[n][3] (NULL = at rest), q[n]; diameter = the
+ * ion-ion LJ length (counterions[0].diameter, src/newforces.cpp:214), lj_length_mesh_ions = INTERFACE::lj_length_mesh_ions
+ * (src/main.cpp:271-272). From then on every force evaluation adds the mesh-ion and ion-ion terms
+ * (src/newforces.cpp:44-65,179-250), npsl_energy their energies (src/interface.cpp:1059-1089) and the ions' kinetic
+ * energy, and npsl_step integrates the ions with their own Nose-Hoover chain (the caller sets ions_bath[0].dof = 3 n
+ * like src/main.cpp:283). n = 0 removes the ions. Call before npsl_force_init. Single-GPU contexts and the replicated
+ * sharding plan only. */
+int npsl_set_ions(npsl_ctx *ctx, int n_ions, const double *pos, const double *vel, const double *q, double diameter,
+                  double lj_length_mesh_ions);
+/* PARTICLE::posvec / velvec / forvec of the counterions <- device; any pointer may be NULL. */
+int npsl_download_ions(npsl_ctx *ctx, double *pos, double *vel, double *force);
+
 /* ---- data feeds of the reference's writers ----------------------------------------------------------------
  * Vertex areas (1/3 of the incident face areas) and unit normals (area-weighted face normals), i.e.
  * VERTEX::compute_area_normal for every vertex (src/vertex.cpp:7-18; src/interface.cpp:39-41, src/newmd.cpp:232-235)

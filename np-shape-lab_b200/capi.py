@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(PKG, "libnpsl.so")
 
 NPSL_MAX_CHAIN = 16
 NPSL_NCCL_ID_BYTES = 128
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/npsl.h declares (tests check that the built library exports all of them)
 SYMBOLS = [
@@ -27,7 +27,7 @@ SYMBOLS = [
     "npsl_pair_timing_read", "npsl_owned_rows", "npsl_pair_geometry", "npsl_fp64_peak", "npsl_md_run",
     "npsl_step_timing", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_md_step_host", "npsl_set_pair_mode",
     "npsl_pair_mode", "npsl_exchange_mode", "npsl_shard_plan", "npsl_vertex_geometry", "npsl_local_energies", "npsl_step_profile", "npsl_set_volume_constraint", "npsl_constraint_init",
-    "npsl_constraint_multipliers",
+    "npsl_constraint_multipliers", "npsl_set_ions", "npsl_download_ions",
 ]
 
 
@@ -56,7 +56,7 @@ class Params(C.Structure):
 
 ENERGY_FIELDS = ["kinetic", "bending", "stretching", "tension", "lj", "electrostatic", "volume", "potential",
                  "energy", "mesh_bath_ke", "mesh_bath_pe", "ions_bath_ke", "ions_bath_pe", "total_area",
-                 "total_volume"]
+                 "total_volume", "ions_kinetic"]
 
 
 class Energies(C.Structure):
@@ -116,6 +116,8 @@ def load() -> C.CDLL:
     L.npsl_pair_mode.argtypes = [vp]
     L.npsl_exchange_mode.argtypes = [vp]
     L.npsl_shard_plan.argtypes = [vp]
+    L.npsl_set_ions.argtypes = [vp, C.c_int, dp, dp, dp, C.c_double, C.c_double]
+    L.npsl_download_ions.argtypes = [vp, dp, dp, dp]
     L.npsl_vertex_geometry.argtypes = [vp, dp, dp]
     L.npsl_local_energies.argtypes = [vp, dp, dp, dp, dp]
     L.npsl_set_volume_constraint.argtypes = [vp, C.c_int]
@@ -371,6 +373,20 @@ class Context:
         a, b = C.c_double(), C.c_double()
         self._ck(self.L.npsl_constraint_multipliers(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def set_ions(self, pos, vel, q, diameter: float, lj_length_mesh_ions: float) -> None:
+        """Explicit counterions (vector<PARTICLE>): pos [n,3], vel [n,3] or None, q [n]; call before force_init."""
+        pos = _f64(pos)
+        q = _f64(q)
+        vel = None if vel is None else _f64(vel)
+        self.n_ions = int(pos.shape[0]) if pos is not None else 0
+        self._ck(self.L.npsl_set_ions(self.h, self.n_ions, _dp(pos), _dp(vel), _dp(q), float(diameter), float(lj_length_mesh_ions)))
+
+    def download_ions(self) -> dict:
+        n = getattr(self, "n_ions", 0)
+        out = {k: np.zeros((n, 3)) for k in ("pos", "vel", "force")}
+        self._ck(self.L.npsl_download_ions(self.h, _dp(out["pos"]), _dp(out["vel"]), _dp(out["force"])))
+        return out
 
     def vertex_geometry(self) -> dict:
         """VERTEX::itsarea / itsnormal of every vertex at the positions on the device (src/vertex.cpp:7-18)."""

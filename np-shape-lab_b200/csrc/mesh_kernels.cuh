@@ -51,6 +51,11 @@ enum {
     SC_KICK,      // dt/2 sqrt(expfac)
     SC_LAMBDA,    // SHAKE multiplier of the last step (volume constraint)
     SC_MU,        // RATTLE multiplier of the last step
+    SC_KE_IONS,      // kinetic energy of the explicit counterions (0 without ions)
+    SC_EXPFAC_IONS,  // exp(-dt/2 xi_0) of the ion chain
+    SC_KICK_IONS,    // dt/2 sqrt(.)
+    SC_ES_IONS,      // ion-ion electrostatic energy
+    SC_LJ_IONS,      // ion-ion LJ energy
     SC_COUNT = 16
 };
 
@@ -65,6 +70,7 @@ struct MeshParams {
     int pair_sym;              // 1: pair forces come from the 8 virtual-rank sums of k_pair_reduce
     int npad;                  // plane length of those sums
     int constraint;            // 1: rigid volume constraint (SHAKE / RATTLE, -G V)
+    int n_ions;                // explicit counterions (ion_kernels.cuh); 0: none
     double dt;
     double pair_coef;  // scalefactor / em
     double bkappa, sconstant, sigma_a, sigma_v, ref_volume, avg_edge;
@@ -208,7 +214,8 @@ __device__ __forceinline__ void thermo_finish(Thermo *th_mid, Thermo *th_cur, do
     const int lane = threadIdx.x, who = lane >> 4, j = lane & 15;  // who 0: mesh chain, 1: ion chain
     BathLink *mid = who == 0 ? th_mid->mesh : th_mid->ions;
     BathLink *cur = who == 0 ? th_cur->mesh : th_cur->ions;
-    const double ke = who == 0 ? ke_mesh : 0.0;
+    // the ion chain is driven by the ions' kinetic energy (k_ion_finish left it in the scalar block; 0 without ions)
+    const double ke = who == 0 ? ke_mesh : __ldcg(scal + SC_KE_IONS);
     const int n = P.chain;
     const double dt = P.dt;
     BathLink b = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -221,10 +228,10 @@ __device__ __forceinline__ void thermo_finish(Thermo *th_mid, Thermo *th_cur, do
     chain_sweep<false>(b, j, n, dt, ke);
     if (j < n && b.Q != 0) b.eta = b.eta + 0.5 * dt * b.xi;
     if (j < n) mid[j] = b;
-    if (lane == 0) {
+    if (j == 0) {  // lane 0: mesh chain, lane 16: ion chain (expfac_mesh / expfac_ions, src/newmd.cpp:109-110)
         const double ef = exp(-0.5 * dt * b.xi);
-        scal[SC_EXPFAC] = ef;
-        scal[SC_KICK] = 0.5 * dt * sqrt(ef);
+        scal[who == 0 ? SC_EXPFAC : SC_EXPFAC_IONS] = ef;
+        scal[who == 0 ? SC_KICK : SC_KICK_IONS] = 0.5 * dt * sqrt(ef);
     }
 }
 
@@ -529,7 +536,7 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
          const ForceComponents C, double *__restrict__ partials /* [2][nblocks] */, unsigned int *__restrict__ ticket,
          double *__restrict__ scal, double *__restrict__ ke_warp /* [n_ke_warps] */, int n_ke_warps,
          Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur, double *const *__restrict__ peer_ke,
-         const Xchg X, const MeshParams P) {
+         const Xchg X, const MeshParams P, const double4 *__restrict__ ion_mesh, const double *__restrict__ ion_mesh_lj) {
     __shared__ double red[3 * 32];
     __shared__ bool s_last;
     __shared__ size_t s_fv_off;
@@ -574,6 +581,13 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
             const double4 a = ldcg4(lj_out + (i - P.row_lo));
             fp.x += a.x; fp.y += a.y; fp.z += a.z; ulj = a.w;
         }
+        double ue_ion = 0, ulj_ion = 0;
+        if (P.n_ions > 0) {  // force of the counterions on the vertex, its mesh-ion energies (k_ion_mesh_rows)
+            const double4 a = ldcg4(ion_mesh + i);
+            fp.x += a.x; fp.y += a.y; fp.z += a.z;
+            ue_ion = a.w;
+            ulj_ion = __ldcg(ion_mesh_lj + i);
+        }
         const double4 fm = ldcg4(fmesh + i);
         const V3 f = mk(fp.x + fm.x, fp.y + fm.y, fp.z + fm.z);
         force[i] = make_double4(f.x, f.y, f.z, 0.0);
@@ -586,9 +600,9 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
             vel[i] = v;
         } else {
             C.pair[i] = make_double4(fp.x, fp.y, fp.z, 0.0);
-            C.vertex_e[i] = make_double2(ue, ulj);
-            acc[1] = ue;
-            acc[2] = ulj;
+            C.vertex_e[i] = make_double2(ue, ulj);  // mesh-mesh only: what the local energy maps use
+            acc[1] = ue + ue_ion;
+            acc[2] = ulj + ulj_ion;
         }
         acc[0] = 0.5 * (v.x * v.x + v.y * v.y + v.z * v.z);
     }

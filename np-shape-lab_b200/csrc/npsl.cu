@@ -22,6 +22,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "ion_kernels.cuh"
 #include "mesh_kernels.cuh"
 #include "pair_kernel.cuh"
 #include "pair_sym_kernel.cuh"
@@ -106,6 +107,11 @@ struct npsl_ctx {
     int4 *face_e = nullptr;
     double4 *face_local = nullptr, *vertex_geo = nullptr;
     bool local_valid = false;  // vertex_e / edge_E hold the energy pass at the current positions
+    // explicit counterions (ion_kernels.cuh)
+    IonParams ip;
+    double4 *ion_xyzq = nullptr, *ion_vel = nullptr, *ion_force = nullptr, *ion_mesh = nullptr;
+    double2 *ion_e = nullptr;
+    double *ion_mesh_lj = nullptr;
     double *peak_out = nullptr;
 
     // launch geometry
@@ -488,6 +494,10 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
         k_kick_drift<<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->force, c->scal, c->lj_hit,
                                                                         c->d_peer_xyzq, c->xg, c->mp);
         n++;
+        if (c->mp.n_ions > 0) {
+            k_ion_kick_drift<<<(c->mp.n_ions + 127) / 128, 128, 0, c->s_main>>>(c->ion_xyzq, c->ion_vel, c->ion_force, c->scal, c->ip);
+            n++;
+        }
         mark("k_kick_drift");
         if (c->xg.on & (1 << XK_POS)) {
             k_xchg_wait<<<1, 32, 0, c->s_main>>>(c->xg, XK_POS);
@@ -534,6 +544,11 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
             k_vertex_mesh<VMODE_FORCE><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_side>>>(c->xyzq, c->bslot, vt, fc, c->scal,
                                                                                         c->fmesh, c->ngv, c->mp);
         n++;
+    }
+    if (c->mp.n_ions > 0) {  // mesh-ion and ion-ion terms, beside the mesh-mesh pair kernel
+        k_ion_mesh_rows<<<(c->nv + 127) / 128, 128, 0, c->s_side>>>(c->xyzq, c->ion_xyzq, c->ion_mesh, c->ion_mesh_lj, c->ip);
+        k_ion_rows<<<c->mp.n_ions, 128, 0, c->s_side>>>(c->xyzq, c->ion_xyzq, c->ion_force, c->ion_e, c->ip);
+        n += 2;
     }
     CU(cudaEventRecord(c->ev_join, c->s_side));
         return 0;
@@ -605,15 +620,22 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
     mark("k_pair (ordered) + k_lj");
     CU(cudaStreamWaitEvent(c->s_main, c->ev_join, 0));
     mark("join k_mesh");
+    if (c->mp.n_ions > 0) {  // before the kernel that advances the thermostat chains: it needs the ions' kinetic energy
+        if (step) k_ion_finish<true><<<1, 256, 0, c->s_main>>>(c->ion_vel, c->ion_force, c->ion_e, c->scal, c->ip);
+        else k_ion_finish<false><<<1, 256, 0, c->s_main>>>(c->ion_vel, c->ion_force, c->ion_e, c->scal, c->ip);
+        n++;
+    }
     if (step) {
         k_vertex<VMODE_STEP><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(
             c->xyzq, c->vel, c->force, c->fmesh, c->pair_partial, c->sym_fv, c->lj_out, c->lj_hit, fc, c->part_vert,
-            c->tickets + 1, c->scal, c->ke_warp, c->n_ke_warps, c->th_mid, c->th_cur, c->d_peer_ke, c->xg, c->mp);
+            c->tickets + 1, c->scal, c->ke_warp, c->n_ke_warps, c->th_mid, c->th_cur, c->d_peer_ke, c->xg, c->mp,
+            c->ion_mesh, c->ion_mesh_lj);
         n++;
     } else {
         k_vertex<VMODE_FORCE><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(
             c->xyzq, c->vel, c->force, c->fmesh, c->pair_partial, c->sym_fv, c->lj_out, c->lj_hit, fc, c->part_vert,
-            c->tickets + 1, c->scal, c->ke_warp, c->n_ke_warps, c->th_mid, c->th_cur, c->d_peer_ke, c->xg, c->mp);
+            c->tickets + 1, c->scal, c->ke_warp, c->n_ke_warps, c->th_mid, c->th_cur, c->d_peer_ke, c->xg, c->mp,
+            c->ion_mesh, c->ion_mesh_lj);
         n++;
     }
     mark("k_vertex");
@@ -940,6 +962,8 @@ int create_impl(const npsl_mesh_desc *mesh, const npsl_params *prm, int rank, in
     mp.n_ranks = world; mp.chain = prm->chain; mp.buckling = prm->buckling ? 1 : 0;
     mp.use_pair = 0;
     mp.constraint = 0;
+    mp.n_ions = 0;
+    memset(&c->ip, 0, sizeof c->ip);
     apply_pair_plan(c);
     mp.dt = prm->dt; mp.pair_coef = prm->scalefactor / prm->em;
     mp.bkappa = prm->bkappa; mp.sconstant = prm->sconstant; mp.sigma_a = prm->sigma_a; mp.sigma_v = prm->sigma_v;
@@ -1046,7 +1070,7 @@ void npsl_destroy(npsl_ctx *c) {
     void *ptrs[] = {c->xyzq, c->vel, c->force, c->fmesh, c->ngv, c->part_con, c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->face_v,
                     c->edge_rec, c->l0, c->degree, c->ring, c->bslot_ref, c->ring_l0, c->bslot, c->pair_partial,
                     c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_warp, c->th_cur, c->th_mid, c->part_mesh,
-                    c->part_vert, c->tickets, c->edge_E, c->vertex_e, c->face_e, c->face_local, c->vertex_geo, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units, c->red_groups,
+                    c->part_vert, c->tickets, c->ion_xyzq, c->ion_vel, c->ion_force, c->ion_mesh, c->ion_e, c->ion_mesh_lj, c->edge_E, c->vertex_e, c->face_e, c->face_local, c->vertex_geo, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units, c->red_groups,
                     c->sym_rowpart, c->sym_colpart, c->sym_fv, c->xflags, c->xstate, c->xtickets,
                     c->d_peer_xyzq, c->d_peer_fv, c->d_peer_ke, c->d_peer_flags};
     for (void *p : ptrs)
@@ -1248,6 +1272,11 @@ int npsl_energy(npsl_ctx *c, npsl_energies *out) {
     const npsl_params &p = c->prm;
     ke = s[SC_KE];  // already the sum over all ranks (canonical order, mesh_kernels.cuh)
     out->kinetic = ke;
+    out->ions_kinetic = c->mp.n_ions > 0 ? s[SC_KE_IONS] : 0.0;  // INTERFACE::netIonKE, src/interface.cpp:970-972
+    if (c->mp.n_ions > 0) {  // ion-ion energies (the mesh-ion ones are already in the per-vertex sums)
+        es += s[SC_ES_IONS];
+        lj += s[SC_LJ_IONS];
+    }
     out->bending = s[SC_BE];
     out->stretching = s[SC_SE];
     out->total_area = s[SC_AREA];
@@ -1258,7 +1287,7 @@ int npsl_energy(npsl_ctx *c, npsl_energies *out) {
     out->lj = lj;
     out->electrostatic = es;
     out->potential = out->bending + out->stretching + out->tension + out->volume + (out->lj + out->electrostatic);
-    out->energy = out->kinetic + out->potential;
+    out->energy = out->kinetic + out->ions_kinetic + out->potential;
     double mk = 0, mpe = 0, ik = 0, ipe = 0;  // src/newenergies.h:28-46, src/thermostat.h:61-70 (kB = 1)
     for (int j = 0; j < p.chain; j++) {
         mk += 0.5 * th.mesh[j].Q * th.mesh[j].xi * th.mesh[j].xi;
@@ -1346,6 +1375,68 @@ int npsl_sync(npsl_ctx *c) {
     CU(cudaStreamSynchronize(c->s_main));
     CU(cudaGetLastError());
     return collect_timing(c);
+}
+
+// ---- explicit counterions ---------------------------------------------------------------
+
+int npsl_set_ions(npsl_ctx *c, int n_ions, const double *pos, const double *vel, const double *q, double diameter,
+                  double lj_length_mesh_ions) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    if (n_ions < 0 || (n_ions > 0 && (!pos || !q))) return fail(c, NPSL_ERR_ARG, "bad ion arguments");
+    if (n_ions > 0 && c->mp.n_ranks > 1)
+        return fail(c, NPSL_ERR_ARG, "explicit counterions need a single-GPU context or the replicated sharding plan");
+    if (n_ions > 0 && !(diameter > 0 && lj_length_mesh_ions > 0)) return fail(c, NPSL_ERR_ARG, "ion LJ lengths must be positive");
+    CU(cudaStreamSynchronize(c->s_main));
+    void *old[] = {c->ion_xyzq, c->ion_vel, c->ion_force, c->ion_mesh, c->ion_e, c->ion_mesh_lj};
+    for (void *p : old)
+        if (p) cudaFree(p);
+    c->ion_xyzq = c->ion_vel = c->ion_force = c->ion_mesh = nullptr; c->ion_e = nullptr; c->ion_mesh_lj = nullptr;
+    c->mp.n_ions = n_ions;
+    drop_graph(c);
+    c->forces_valid = c->local_valid = false;
+    double zeros[5] = {0, 1.0, 0.5 * c->prm.dt, 0, 0};  // KE, expfac, kick, ES, LJ of the ions until the first force pass
+    CU(cudaMemcpy(c->scal + SC_KE_IONS, zeros, sizeof zeros, cudaMemcpyHostToDevice));
+    if (n_ions == 0) return NPSL_OK;
+    CU(dalloc(&c->ion_xyzq, n_ions)); CU(dalloc(&c->ion_vel, n_ions)); CU(dalloc(&c->ion_force, n_ions));
+    CU(dalloc(&c->ion_e, n_ions)); CU(dalloc(&c->ion_mesh, c->nv)); CU(dalloc(&c->ion_mesh_lj, c->nv));
+    std::vector<double4> rec(n_ions), vr(n_ions);
+    for (int i = 0; i < n_ions; i++) {
+        rec[i] = make_double4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], q[i]);
+        vr[i] = vel ? make_double4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], 0.0) : make_double4(0, 0, 0, 0);
+    }
+    CU(cudaMemcpy(c->ion_xyzq, rec.data(), sizeof(double4) * n_ions, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->ion_vel, vr.data(), sizeof(double4) * n_ions, cudaMemcpyHostToDevice));
+    IonParams &ip = c->ip;
+    ip.n_ions = n_ions; ip.nv = c->nv;
+    ip.coef = c->prm.scalefactor / c->prm.em;
+    ip.inv_lambda = 1.0 / c->prm.inv_kappa_out;
+    ip.elj = c->prm.elj;
+    ip.d2_mi = lj_length_mesh_ions * lj_length_mesh_ions; ip.cut2_mi = 1.25992104989487316476 * ip.d2_mi;
+    ip.d2_ii = diameter * diameter; ip.cut2_ii = 1.25992104989487316476 * ip.d2_ii;
+    ip.dt = c->prm.dt;
+    // the reverse half-chain of the first step needs the ions' kinetic energy: same preparation as after npsl_set_thermostat
+    k_ion_finish<false><<<1, 256, 0, c->s_main>>>(c->ion_vel, c->ion_force, c->ion_e, c->scal, c->ip);
+    k_thermo_prepare<<<1, 32, 0, c->s_main>>>(c->th_cur, c->th_mid, c->scal, c->mp);
+    c->launches += 2;
+    CU(cudaStreamSynchronize(c->s_main));
+    CU(cudaGetLastError());
+    return NPSL_OK;
+}
+
+int npsl_download_ions(npsl_ctx *c, double *pos, double *vel, double *force) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    const int n = c->mp.n_ions;
+    if (n == 0) return NPSL_OK;
+    std::vector<double4> tmp(n);
+    double *outs[3] = {pos, vel, force};
+    double4 *src[3] = {c->ion_xyzq, c->ion_vel, c->ion_force};
+    for (int k = 0; k < 3; k++) {
+        if (!outs[k]) continue;
+        CU(cudaMemcpyAsync(tmp.data(), src[k], sizeof(double4) * n, cudaMemcpyDeviceToHost, c->s_main));
+        CU(cudaStreamSynchronize(c->s_main));
+        for (int i = 0; i < n; i++) { outs[k][3 * i] = tmp[i].x; outs[k][3 * i + 1] = tmp[i].y; outs[k][3 * i + 2] = tmp[i].z; }
+    }
+    return NPSL_OK;
 }
 
 // ---- data feeds of the writers -------------------------------------------------------

@@ -98,7 +98,7 @@ def test_library_exports_every_symbol_the_header_declares():
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(capi.BathLink) == 40
     assert ctypes.sizeof(capi.Params) == 12 * 8 + 8 + 2 * 16 * 40
-    assert ctypes.sizeof(capi.Energies) == 15 * 8
+    assert ctypes.sizeof(capi.Energies) == 16 * 8  # ABI 2: + ions_kinetic
 
 
 def test_no_cpu_fallback():
