@@ -89,7 +89,8 @@ class INTERFACE:
         self.bkappa = self.sconstant = self.sigma_a = self.sigma_v = 0.0
         self.elj = 1.0
         self.lj_length_mesh_mesh = 0.0
-        self.netMeshKE = self.penergy = self.energy = 0.0
+        self.lj_length_mesh_ions = 0.0  # (2 * 0.5 avg_edge + counterion diameter) / 2, src/main.cpp:271-272
+        self.netMeshKE = self.netIonKE = self.penergy = self.energy = 0.0
         self.energy_parts = {}
         self.dt = 0.001
         self._ctx: Optional[capi.Context] = None
@@ -188,10 +189,9 @@ class INTERFACE:
     def compute_energy(self, num: int, counterions: list, scalefactor: float, bucklingFlag: str,
                        outdir: Optional[str] = None) -> None:
         """src/interface.cpp:964-1137; appends the ``energy_in_parts`` row when ``outdir`` is given."""
-        if counterions:
-            raise NotImplementedError("explicit counterions are a 'next' row (SURVEY 8f rank 1)")
-        ctx = self.context(scalefactor, bucklingFlag)
+        ctx = self.context(scalefactor, bucklingFlag)  # the counterions are on the device since the last force call
         e = ctx.energy()
+        self.netIonKE = e["ions_kinetic"]
         self.energy_parts = e
         self.netMeshKE, self.penergy, self.energy = e["kinetic"], e["potential"], e["energy"]
         self.total_area, self.total_volume = e["total_area"], e["total_volume"]
@@ -234,24 +234,52 @@ class INTERFACE:
         return {k: loc[k] for k in keys}
 
 
+class PARTICLE:
+    """src/particle.h:13-91: one explicit counterion (mass 1)."""
+
+    def __init__(self, id: int = 0, diameter: float = 0.0, valency: int = 0, q: float = 0.0, m: float = 1.0, posvec=(0.0, 0.0, 0.0)):
+        self.id, self.diameter, self.valency, self.q, self.m = id, diameter, valency, q, m
+        self.posvec = np.array(posvec, dtype=np.float64)
+        self.velvec = np.zeros(3)
+        self.forvec = np.zeros(3)
+
+
+def push_ions(boundary: "INTERFACE", ctx: capi.Context, counterions: list) -> None:
+    """vector<PARTICLE> -> device (positions, velocities, charges; ion diameter and INTERFACE::lj_length_mesh_ions)."""
+    if not counterions:
+        if getattr(ctx, "n_ions", 0):
+            ctx.set_ions(None, None, None, 1.0, 1.0)
+        return
+    ctx.set_ions(np.array([p.posvec for p in counterions]), np.array([p.velvec for p in counterions]),
+                 np.array([p.q for p in counterions]), counterions[0].diameter, boundary.lj_length_mesh_ions)
+
+
+def pull_ions(ctx: capi.Context, counterions: list) -> None:
+    if not counterions:
+        return
+    st = ctx.download_ions()
+    for k, p in enumerate(counterions):
+        p.posvec, p.velvec, p.forvec = st["pos"][k].copy(), st["vel"][k].copy(), st["force"][k].copy()
+
+
 def force_calculation_init(boundary: INTERFACE, counterions: list, scalefactor: float, bucklingFlag: str) -> None:
     """src/newforces.cpp:4-135."""
-    if counterions:
-        raise NotImplementedError("explicit counterions are a 'next' row (SURVEY 8f rank 1)")
     ctx = boundary.context(scalefactor, bucklingFlag)
     boundary.push_state(ctx)
+    push_ions(boundary, ctx, counterions)
     ctx.force_init()
     boundary.pull_forces(ctx)
+    pull_ions(ctx, counterions)
 
 
 def force_calculation(boundary: INTERFACE, counterions: list, scalefactor: float, bucklingFlag: str) -> None:
     """src/newforces.cpp:137-289."""
-    if counterions:
-        raise NotImplementedError("explicit counterions are a 'next' row (SURVEY 8f rank 1)")
     ctx = boundary.context(scalefactor, bucklingFlag)
     boundary.push_state(ctx)
+    push_ions(boundary, ctx, counterions)
     ctx.force()
     boundary.pull_forces(ctx)
+    pull_ions(ctx, counterions)
 
 
 def compute_kinetic_energy(boundary: INTERFACE) -> float:
@@ -283,8 +311,6 @@ def md_interface(boundary: INTERFACE, counterions: list, mesh_bath: List[THERMOS
     """src/newmd.cpp:9-323. The loop body runs on the device (one CUDA-graph launch per step);
     the host touches the state only on write steps (``num < 3`` or ``num % writedata == 0``) and for
     annealing. Series files are written to ``outdir`` in the reference's formats."""
-    if counterions:
-        raise NotImplementedError("explicit counterions are a 'next' row (SURVEY 8f rank 1)")
     if geomConstraint not in ("N", "V") or (geomConstraint == "V" and constraintForm != "L"):
         raise NotImplementedError("only the rigid volume constraint in its linear form (-G V) is on the device path")
     boundary.dt = mdremote.timestep
@@ -293,6 +319,9 @@ def md_interface(boundary: INTERFACE, counterions: list, mesh_bath: List[THERMOS
     ctx = boundary.context(scalefactor, bucklingFlag, mesh_bath, ions_bath)
     if geomConstraint == "V":
         ctx.set_volume_constraint(True)
+    for p in counterions or []:
+        p.velvec = np.zeros(3)
+    push_ions(boundary, ctx, counterions)
     ctx.force_init()  # src/newmd.cpp:19
     if geomConstraint == "V":
         ctx.constraint_init()  # SHAKE + RATTLE prior to MD, src/newmd.cpp:33-38
@@ -380,4 +409,5 @@ def md_interface(boundary: INTERFACE, counterions: list, mesh_bath: List[THERMOS
                 ctx.set_thermostat([t.row() for t in mesh_bath], [t.row() for t in ions_bath])
     st = ctx.download_state()
     boundary.posvec, boundary.velvec, boundary.forvec = st["pos"], st["vel"], st["force"]
+    pull_ions(ctx, counterions)
     _sync_baths(ctx, mesh_bath, ions_bath)

@@ -19,7 +19,7 @@ int main(int argc, char **argv) {
     double R = 10, q = 600, conc = 0.005, t = 1, v = 1, b = 40, s = 40, p = 0.5, dt = 0.001, T = 0.001, Qm = 0.01, Qi = 0.01;
     int N = 1, steps = 25000, D = 4, C = 5, writedata = 500;
     char B = 'n', Fflag = 'n', H = 'n', G = 'N';
-    std::string mesh_file, outdir = "outfiles", externalPattern = "None";
+    std::string mesh_file, outdir = "outfiles", externalPattern = "None", ions_file;
     int dump_q = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -27,7 +27,8 @@ int main(int argc, char **argv) {
             std::puts("np_shape_lab_b200 [-R r] [-q q] [-c conc] [-t st] [-v vt] [-b bend] [-s stretch] [-B y|n] [-N 1|2] [-p frac]\n"
                       "                  [-H n|y|c] [-F n|y] [-E pattern] [-G N|V]\n"
                       "                  [-S steps] [-D disc] [-d dt] [-T temp] [-Q Qmesh] [-C chain] [-W writedata]\n"
-                      "                  [--mesh file.dat] [--out dir]   (needs a CUDA device; there is no CPU path)");
+                      "                  [--mesh file.dat] [--out dir] [--ions counterions.xyz]\n"
+                      "                  (needs a CUDA device; there is no CPU path)");
             return 0;
         }
         if (i + 1 >= argc) { std::fprintf(stderr, "missing value for %s\n", a.c_str()); return 2; }
@@ -41,6 +42,7 @@ int main(int argc, char **argv) {
         else if (a == "-Y") Qi = atof(val); else if (a == "-C") C = atoi(val); else if (a == "-W") writedata = atoi(val);
         else if (a == "--mesh") mesh_file = val; else if (a == "--out") outdir = val;
         else if (a == "-E") externalPattern = val; else if (a == "--dump-q") dump_q = atoi(val);
+        else if (a == "--ions") ions_file = val;
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     try {
@@ -69,6 +71,9 @@ int main(int argc, char **argv) {
             return 0;
         }
         boundary.lj_length_mesh_mesh = 0.1 * boundary.avg_edge_length;
+        const double counterion_diameter = 0.6 / R;                                                  // src/main.cpp:196
+        boundary.lj_length_mesh_ions = ((2.0 * (0.5 * boundary.avg_edge_length) + counterion_diameter) / 2.0);  // :271-272
+        if (!ions_file.empty()) read_counterions(ions_file, counterion_diameter, 1, counterions);
         boundary.elj = 1.0;
         boundary.dressup(0, 0);
         boundary.ref_area = boundary.total_area;
@@ -78,14 +83,14 @@ int main(int argc, char **argv) {
         const double n3 = 3.0 * boundary.V.size();
         if (C == 1) {
             mesh_bath.push_back(THERMOSTAT(0, T, n3));
-            ions_bath.push_back(THERMOSTAT(0, T, 0));
+            ions_bath.push_back(THERMOSTAT(0, T, 3.0 * counterions.size()));
         } else {
             mesh_bath.push_back(THERMOSTAT(Qm, T, n3));
-            ions_bath.push_back(THERMOSTAT(Qi, T, 0));
+            ions_bath.push_back(THERMOSTAT(Qi, T, 3.0 * counterions.size()));
             while ((int) mesh_bath.size() != C - 1) mesh_bath.push_back(THERMOSTAT(Qm, T, 1));
             while ((int) ions_bath.size() != C - 1) ions_bath.push_back(THERMOSTAT(Qi, T, 1));
             mesh_bath.push_back(THERMOSTAT(0, T, n3));
-            ions_bath.push_back(THERMOSTAT(0, T, 0));
+            ions_bath.push_back(THERMOSTAT(0, T, 3.0 * counterions.size()));
         }
         for (size_t i = 0; i < boundary.V.size(); i++) boundary.V[i].m = 1.0;
         std::cout << "Number of vertices " << boundary.V.size() << ", edges " << boundary.E.size() << ", faces "

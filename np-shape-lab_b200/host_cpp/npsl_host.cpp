@@ -24,9 +24,6 @@ void check(npsl_ctx *ctx, int st, const char *what) {
     if (st != NPSL_OK) throw npsl_error(st, string(what) + ": " + npsl_last_error(ctx));
 }
 
-void require_no_ions(const vector<PARTICLE> &ions) {
-    if (!ions.empty()) throw npsl_error(NPSL_ERR_ARG, "explicit counterions are not on the device path yet");
-}
 
 void append_line(const string &dir, const char *file, const string &line) {
     if (dir.empty()) return;
@@ -282,6 +279,30 @@ npsl_ctx *INTERFACE::context(double scalefactor, char bucklingFlag, const vector
     return ctx;
 }
 
+void INTERFACE::push_ions(vector<PARTICLE> &ions) {
+    const size_t m = ions.size();
+    vector<double> p(3 * m), v(3 * m), q(m);
+    for (size_t i = 0; i < m; i++) {
+        p[3 * i] = ions[i].posvec.x; p[3 * i + 1] = ions[i].posvec.y; p[3 * i + 2] = ions[i].posvec.z;
+        v[3 * i] = ions[i].velvec.x; v[3 * i + 1] = ions[i].velvec.y; v[3 * i + 2] = ions[i].velvec.z;
+        q[i] = ions[i].q;
+    }
+    check(ctx, npsl_set_ions(ctx, (int) m, p.data(), v.data(), q.data(), m ? ions[0].diameter : 0.0, lj_length_mesh_ions),
+          "npsl_set_ions");
+}
+
+void INTERFACE::pull_ions(vector<PARTICLE> &ions) {
+    const size_t m = ions.size();
+    if (!m) return;
+    vector<double> p(3 * m), v(3 * m), f(3 * m);
+    check(ctx, npsl_download_ions(ctx, p.data(), v.data(), f.data()), "npsl_download_ions");
+    for (size_t i = 0; i < m; i++) {
+        ions[i].posvec = VECTOR3D(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+        ions[i].velvec = VECTOR3D(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+        ions[i].forvec = VECTOR3D(f[3 * i], f[3 * i + 1], f[3 * i + 2]);
+    }
+}
+
 void INTERFACE::push_state() {
     const size_t n = V.size();
     buf_a.resize(3 * n); buf_b.resize(3 * n); buf_c.resize(n);
@@ -352,10 +373,10 @@ void INTERFACE::dressup(double la, double lv) {
 }
 
 void INTERFACE::compute_energy(int num, vector<PARTICLE> &counterions, const double scalefactor, char bucklingFlag) {
-    require_no_ions(counterions);
+    (void) counterions;  // on the device since the last force call / md_interface
     context(scalefactor, bucklingFlag);
     check(ctx, npsl_energy(ctx, &parts), "npsl_energy");
-    netMeshKE = parts.kinetic; penergy = parts.potential; energy = parts.energy;
+    netMeshKE = parts.kinetic; netIonKE = parts.ions_kinetic; penergy = parts.potential; energy = parts.energy;
     total_area = parts.total_area; total_volume = parts.total_volume;
     std::ostringstream row;  // "num KE bE sE tE ljE esE volE", src/interface.cpp:987-1113
     row << num << " " << parts.kinetic << " " << parts.bending << " " << parts.stretching << " " << parts.tension << " "
@@ -450,19 +471,45 @@ void interface_off(int num, INTERFACE &dsphere) {
 }
 
 void force_calculation_init(INTERFACE &boundary, vector<PARTICLE> &counterions, const double scalefactor, char bucklingFlag) {
-    require_no_ions(counterions);
     npsl_ctx *c = boundary.context(scalefactor, bucklingFlag);
     boundary.push_state();
+    boundary.push_ions(counterions);
     check(c, npsl_force_init(c), "npsl_force_init");
     boundary.pull_forces();
+    boundary.pull_ions(counterions);
 }
 
 void force_calculation(INTERFACE &boundary, vector<PARTICLE> &counterions, const double scalefactor, char bucklingFlag) {
-    require_no_ions(counterions);
     npsl_ctx *c = boundary.context(scalefactor, bucklingFlag);
     boundary.push_state();
+    boundary.push_ions(counterions);
     check(c, npsl_force(c), "npsl_force");
     boundary.pull_forces();
+    boundary.pull_ions(counterions);
+}
+
+long double compute_kinetic_energy(vector<PARTICLE> &counterions) {
+    long double ke = 0;
+    for (size_t i = 0; i < counterions.size(); i++) {
+        counterions[i].ke = 0.5 * counterions[i].m * (counterions[i].velvec * counterions[i].velvec);
+        ke += counterions[i].ke;
+    }
+    return ke;
+}
+
+void read_counterions(const string &path, double diameter, int valency, vector<PARTICLE> &counterions) {
+    std::ifstream in(path.c_str());
+    if (!in) throw npsl_error(NPSL_ERR_ARG, "counterion file could not be opened: " + path);
+    size_t n = 0;
+    string tag;
+    in >> n >> tag;  // count, "counterions"
+    counterions.clear();
+    for (size_t i = 0; i < n; i++) {
+        double x, y, z, r;
+        in >> tag >> x >> y >> z >> r;
+        if (!in) throw npsl_error(NPSL_ERR_ARG, "counterion file truncated: " + path);
+        counterions.push_back(PARTICLE((int) i + 1, diameter, valency, valency * -1.0, 1.0, VECTOR3D(x, y, z)));
+    }
 }
 
 long double compute_kinetic_energy(vector<VERTEX> &V) {
@@ -496,7 +543,6 @@ void initialize_velocities_to_zero(vector<VERTEX> &V, vector<PARTICLE> &ions) {
 void md_interface(INTERFACE &boundary, vector<PARTICLE> &counterions, vector<THERMOSTAT> &mesh_bath,
                   vector<THERMOSTAT> &ions_bath, CONTROL &mdremote, char geomConstraint, char bucklingFlag,
                   char constraintForm, const double scalefactor, double box_radius) {
-    require_no_ions(counterions);
     if (geomConstraint == 'V' && constraintForm == 'Q')
         throw npsl_error(NPSL_ERR_ARG, "the quadratic constraint form is not on the device path");
     if (geomConstraint != 'N' && geomConstraint != 'V')
@@ -507,6 +553,7 @@ void md_interface(INTERFACE &boundary, vector<PARTICLE> &counterions, vector<THE
     boundary.drop_context();
     npsl_ctx *c = boundary.context(scalefactor, bucklingFlag, &mesh_bath, &ions_bath, mdremote.timestep);
     if (geomConstraint == 'V') check(c, npsl_set_volume_constraint(c, 1), "npsl_set_volume_constraint");
+    boundary.push_ions(counterions);
     check(c, npsl_force_init(c), "npsl_force_init");
     if (geomConstraint == 'V') check(c, npsl_constraint_init(c), "npsl_constraint_init");  // src/newmd.cpp:33-38
     npsl_bath_link mb[NPSL_MAX_CHAIN], ib[NPSL_MAX_CHAIN];
@@ -526,7 +573,7 @@ void md_interface(INTERFACE &boundary, vector<PARTICLE> &counterions, vector<THE
         const double bke = e.mesh_bath_ke + e.ions_bath_ke, bpe = e.mesh_bath_pe + e.ions_bath_pe;
         const double global = boundary.energy + bke + bpe;
         std::ostringstream s;
-        s << num << cell(boundary.netMeshKE) << cell(boundary.penergy) << cell(boundary.energy) << cell(global)
+        s << num << cell(boundary.netMeshKE + boundary.netIonKE) << cell(boundary.penergy) << cell(boundary.energy) << cell(global)
           << cell(bke) << cell(bpe);
         append_line(dir, "energy_nanomembrane.dat", s.str());
         std::ostringstream a, v, t;
@@ -575,6 +622,7 @@ void md_interface(INTERFACE &boundary, vector<PARTICLE> &counterions, vector<THE
         }
         if (mdremote.moviefreq > 0 && num % mdremote.moviefreq == 0 && !dir.empty()) {  // snapshots, src/newmd.cpp:230-240
             boundary.pull_state();
+            boundary.pull_ions(counterions);
             boundary.compute_vertex_area_normals();
             output_directory() = dir;
             if (mdremote.offfreq > 0 && num % mdremote.offfreq == 0) interface_off(num, boundary);
@@ -604,5 +652,6 @@ void md_interface(INTERFACE &boundary, vector<PARTICLE> &counterions, vector<THE
         }
     }
     boundary.pull_state();
+    boundary.pull_ions(counterions);
     sync_baths();
 }

@@ -89,11 +89,15 @@ public:
     VECTOR3D itsdirection;
 };
 
-// src/particle.h (explicit counterions are a "next" row; the vector must be empty)
+// src/particle.h:13-91 (explicit counterions; all of one diameter, masses 1 like the reference's)
 class PARTICLE {
 public:
+    int id = 0, valency = 0;
     VECTOR3D posvec, velvec, forvec;
-    double q = 0, m = 1, diameter = 0;
+    double q = 0, m = 1, diameter = 0, ke = 0;
+    PARTICLE(int get_id = 0, double get_diameter = 0, int get_valency = 0, double get_charge = 0, double get_mass = 0,
+             VECTOR3D get_position = VECTOR3D(0, 0, 0))
+        : id(get_id), valency(get_valency), posvec(get_position), q(get_charge), m(get_mass), diameter(get_diameter) {}
 };
 
 // src/thermostat.h:8-71
@@ -133,7 +137,7 @@ public:
     double lambda_a = 0, lambda_v = 0, lambda_l = 0;
     double bkappa = 0, sconstant = 0, sigma_a = 0, sigma_v = 0;
     double elj = 1, lj_length_mesh_mesh = 0, lj_length_mesh_ions = 0;
-    double netMeshKE = 0, penergy = 0, energy = 0;
+    double netMeshKE = 0, netIonKE = 0, penergy = 0, energy = 0;
     // components of the last compute_energy (the reference keeps them in locals and prints them)
     npsl_energies parts;
     std::string outdir = "outfiles";  // series files; empty string = write nothing
@@ -166,6 +170,8 @@ public:
     npsl_ctx *context(double scalefactor, char bucklingFlag, const std::vector<THERMOSTAT> *mesh_bath = nullptr,
                       const std::vector<THERMOSTAT> *ions_bath = nullptr, double dt = 0.001);
     void drop_context();
+    void push_ions(std::vector<PARTICLE> &ions);  // counterions -> device (positions, velocities, charges, LJ lengths)
+    void pull_ions(std::vector<PARTICLE> &ions);  // PARTICLE::posvec / velvec / forvec <- device
     void push_state();              // posvec / velvec / q  -> device
     void pull_forces();             // forvec + per-term forces, EDGE::itsS, FACE fields <- device
     void pull_state();              // posvec / velvec / forvec <- device
@@ -183,6 +189,11 @@ void md_interface(INTERFACE &boundary, std::vector<PARTICLE> &counterions, std::
                   char constraintForm, const double scalefactor, double box_radius);
 
 long double compute_kinetic_energy(std::vector<VERTEX> &V);              // src/newenergies.h:8-16 (host arrays)
+long double compute_kinetic_energy(std::vector<PARTICLE> &counterions);  // src/newenergies.h:18-26
+// counterions.xyz as INTERFACE::put_counterions writes it (src/interface.cpp:946-953: count, a comment line, then
+// "C x y z |r|") read back into monovalent PARTICLEs of the given diameter -- the reference's own placement loop cannot
+// terminate with its hard-wired box (src/main.cpp:194), so positions have to come from outside
+void read_counterions(const std::string &path, double diameter, int valency, std::vector<PARTICLE> &counterions);
 double bath_kinetic_energy(std::vector<THERMOSTAT> &bath);               // src/newenergies.h:28-36
 double bath_potential_energy(std::vector<THERMOSTAT> &bath);             // src/newenergies.h:38-46
 void initialize_velocities_to_zero(std::vector<VERTEX> &V, std::vector<PARTICLE> &ions);  // src/functions.cpp:40-47

@@ -87,3 +87,26 @@ def test_counterions_with_the_symmetric_kernel_and_removal():
     assert relerr(i2["pos"], i1["pos"]) < 1e-12
     for k in ("electrostatic", "lj", "ions_kinetic", "energy"):
         assert abs(e2[k] - e1[k]) <= 1e-11 * max(abs(e1[k]), 1e-9), k
+
+
+def test_python_host_mirror_with_counterions():
+    """md_interface / force_calculation of the Python mirror with a list of PARTICLEs."""
+    from np_shape_lab_b200 import host as H, mesh as M
+    g = golden("disc_D4_ions")
+    inp = M.PhysicalInputs(q=600.0, c=0.005)
+    b = H.INTERFACE.from_inputs(M.Mesh(g["pos0"], g["edges"], g["faces"]), inp)
+    d_ion, b.lj_length_mesh_ions = float(g["ion_params"][0]), float(g["ion_params"][1])
+    ions = [H.PARTICLE(k + 1, d_ion, 1, float(q), 1.0, p) for k, (p, q) in enumerate(zip(g["ion_pos0"], g["ion_q"]))]
+    mesh_bath, ions_bath = H.make_baths(inp, g.nv(), len(ions))
+    assert ions_bath[0].dof == 3 * len(ions)
+    sf = g.params["scalefactor"]
+    H.force_calculation_init(b, ions, sf, "n")
+    assert relerr(b.forvec, g["k0_force"]) < TOL
+    assert relerr(np.array([p.forvec for p in ions]), g["k0_ion_force"]) < TOL
+    c = H.CONTROL()
+    c.steps, c.writedata = 100, 100
+    H.md_interface(b, ions, mesh_bath, ions_bath, c, "N", "n", "L", sf)
+    s = g.scalars(100)
+    assert abs(b.penergy - s["penergy"]) <= 1e-6 * abs(s["penergy"])
+    assert abs(b.energy - s["energy"]) <= 1e-6 * abs(s["energy"])
+    assert abs(b.netIonKE - float(g["k100_netIonKE"])) <= 1e-6 * float(g["k100_netIonKE"])

@@ -151,3 +151,33 @@ def test_host_cpp_snapshot_writers_match_reference(tmp_path):
         tol = {"stretching": 5e-3, "elastic": 5e-3, "bending": 1e-3, "electrostatic": 1e-4}[key]
         assert np.max(np.abs(e - ref)) <= tol * float(np.max(np.abs(ref))), (key, np.max(np.abs(e - ref)))
         assert np.max(np.abs(p2 - w["off_pos"])) <= 2e-5
+
+
+@pytest.mark.gpu
+def test_host_cpp_runs_with_explicit_counterions(tmp_path):
+    """md_interface of the C++ mirror with a non-empty vector<PARTICLE> (read from a counterions.xyz in the layout
+    INTERFACE::put_counterions writes): A / U / E after 500 steps against the compiled reference's run with the same 64
+    ions (tests/golden/disc_D4_ions.npz), ions in the movie file."""
+    from oracle import refdump as R
+    build_host()
+    g = golden("disc_D4_ions")
+    M.write_dat(str(tmp_path / "m.dat"), M.Mesh(pos=g["pos0"], edges=g["edges"], faces=g["faces"]))
+    ions = g["ion_pos0"]
+    with open(tmp_path / "counterions.xyz", "w") as fh:
+        fh.write("%d\ncounterions\n" % len(ions))
+        for p in ions:
+            fh.write("C %.17g %.17g %.17g %.17g\n" % (p[0], p[1], p[2], float(np.linalg.norm(p))))
+    k = g.traj_steps[-1]
+    out = tmp_path / "outfiles"
+    r = subprocess.run([BIN, "--mesh", str(tmp_path / "m.dat"), "-S", str(k), "--out", str(out), "--ions",
+                        str(tmp_path / "counterions.xyz")] + RECIPES["disc_D4"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True)
+    assert r.returncode == 0, r.stderr
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    s = g.scalars(k)
+    cons = s["energy"] + s["mesh_bath_ke"] + s["mesh_bath_pe"] + s["ions_bath_ke"] + s["ions_bath_pe"]
+    assert abs(res["A"] - s["total_area"]) <= 1e-6 * s["total_area"]
+    assert abs(res["U"] - s["penergy"]) <= 1e-6 * abs(s["penergy"])
+    assert abs(res["E"] - cons) <= 1e-6 * abs(cons)
+    steps, frames = R.parse_lammpstrj(str(out / "p.lammpstrj"))
+    assert frames.shape[1] == g.nv() + len(ions) and set(frames[0][g.nv():, 1].tolist()) == {2.0}  # ions are type 2
