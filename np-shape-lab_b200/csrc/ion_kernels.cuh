@@ -3,9 +3,10 @@
 // The reference walks, besides the mesh-mesh pairs, every mesh-ion pair twice (once for the force on the vertex,
 // once for the force on the ion) and every ordered ion-ion pair (src/newforces.cpp:44-65,179-250), and repeats the
 // walks for the energies (src/interface.cpp:1059-1089). Ions are few (|q| / valency, hundreds to a few thousand), so
-// these are two small exact kernels beside the mesh-mesh pair kernel: libm-grade exp / sqrt / divisions and an always
-// live WCA branch (ions do touch the membrane and each other), per-class LJ lengths (INTERFACE::lj_length_mesh_ions
-// for mesh-ion, the ion diameter for ion-ion). Fixed summation orders, no atomics.
+// these are two small kernels beside the mesh-mesh pair kernel: the screened-Coulomb part uses the pair kernel's
+// rsqrt / table-exp (<= 3e-16 relative error, pair_kernel.cuh), the WCA branch -- live here, ions do touch the membrane
+// and each other -- the reference's expression with per-class LJ lengths (INTERFACE::lj_length_mesh_ions for
+// mesh-ion, the ion diameter for ion-ion). Fixed summation orders, no atomics.
 //   k_ion_mesh_rows  one thread per mesh vertex, ions staged through shared memory: force of all ions on the vertex
 //                    and the vertex's mesh-ion energies (counted once, on the mesh side, like the reference)
 //   k_ion_rows       one CTA per ion: force of all vertices and all other ions on it (ordered block sum), its
@@ -16,6 +17,7 @@
 //                    energies, one CTA, ordered; runs before the kernel that advances the Nose-Hoover chains.
 #pragma once
 #include "mesh_kernels.cuh"
+#include "pair_kernel.cuh"
 
 namespace npsl {
 
@@ -27,17 +29,19 @@ struct IonParams {
     double d2_mi, cut2_mi;  // mesh-ion LJ length squared and dcut2 * that
     double d2_ii, cut2_ii;  // ion-ion (ion diameter)
     double dt;
+    double c2s;             // -log2(e) / lambda * 2^TB, the argument scale of exp2_neg
 };
 
 // One pair, d = p1 - p2, qq = coef q1 q2. s: force on particle 1 is s * d. es, lj: pair energies.
 __device__ __forceinline__ void ion_pair(const double dx, const double dy, const double dz, const double qq,
-                                         const double inv_lambda, const double elj, const double d2, const double cut2,
-                                         double &s, double &es, double &lj) {
-    const double r2 = dx * dx + dy * dy + dz * dz;
-    const double r = sqrt(r2);
-    const double e = exp(-inv_lambda * r);
-    es = qq * e / r;
-    s = (qq * e) * (1.0 / r2) * ((1.0 / r) + inv_lambda);
+                                         const double inv_lambda, const double c2s, const double *__restrict__ tab,
+                                         const double elj, const double d2, const double cut2, double &s, double &es,
+                                         double &lj) {
+    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    const double rinv = rsqrt_fast(r2);
+    const double qe = qq * exp2_neg(r2 * rinv, c2s, tab);  // coef q1 q2 e^{-r/lambda}
+    es = qe * rinv;
+    s = qe * (rinv * rinv) * (rinv + inv_lambda);
     lj = 0.0;
     if (r2 < cut2) {
         const double r6 = r2 * r2 * r2, r12 = r6 * r6, d6 = d2 * d2 * d2, d12 = d6 * d6;
@@ -50,6 +54,8 @@ __global__ void __launch_bounds__(128)
 k_ion_mesh_rows(const double4 *__restrict__ xyzq, const double4 *__restrict__ ion_xyzq, double4 *__restrict__ out /* f, es */,
                 double *__restrict__ out_lj, const IonParams P) {
     __shared__ double4 sj[256];
+    __shared__ double tab[kExpTab];
+    for (int k = threadIdx.x; k < kExpTab; k += blockDim.x) tab[k] = c_exp2_tab[k];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const double4 pi = xyzq[min(i, P.nv - 1)];
     double fx = 0, fy = 0, fz = 0, es = 0, lj = 0;
@@ -58,11 +64,12 @@ k_ion_mesh_rows(const double4 *__restrict__ xyzq, const double4 *__restrict__ io
         __syncthreads();
         for (int k = threadIdx.x; k < cnt; k += blockDim.x) sj[k] = ion_xyzq[j0 + k];
         __syncthreads();
+#pragma unroll 4  // four independent rsqrt / exp chains in flight; the sums stay in ion order
         for (int k = 0; k < cnt; k++) {
             const double4 pj = sj[k];
             const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
             double s, e1, e2;
-            ion_pair(dx, dy, dz, P.coef * pi.w * pj.w, P.inv_lambda, P.elj, P.d2_mi, P.cut2_mi, s, e1, e2);
+            ion_pair(dx, dy, dz, P.coef * pi.w * pj.w, P.inv_lambda, P.c2s, tab, P.elj, P.d2_mi, P.cut2_mi, s, e1, e2);
             fx += s * dx; fy += s * dy; fz += s * dz;
             es += e1; lj += e2;
         }
@@ -77,23 +84,28 @@ __global__ void __launch_bounds__(128)
 k_ion_rows(const double4 *__restrict__ xyzq, const double4 *__restrict__ ion_xyzq, double4 *__restrict__ ion_force,
            double2 *__restrict__ ion_e, const IonParams P) {
     __shared__ double red[5 * 32];
+    __shared__ double tab[kExpTab];
+    for (int k = threadIdx.x; k < kExpTab; k += blockDim.x) tab[k] = c_exp2_tab[k];
+    __syncthreads();
     const int i = blockIdx.x;
     const double4 pi = ion_xyzq[i];
     double acc[5] = {0, 0, 0, 0, 0};  // fx fy fz es_ii lj_ii
+#pragma unroll 2
     for (int j = threadIdx.x; j < P.n_ions; j += blockDim.x) {  // ion-ion, src/newforces.cpp:203-226
         if (j == i) continue;
         const double4 pj = ion_xyzq[j];
         const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
         double s, e1, e2;
-        ion_pair(dx, dy, dz, P.coef * pi.w * pj.w, P.inv_lambda, P.elj, P.d2_ii, P.cut2_ii, s, e1, e2);
+        ion_pair(dx, dy, dz, P.coef * pi.w * pj.w, P.inv_lambda, P.c2s, tab, P.elj, P.d2_ii, P.cut2_ii, s, e1, e2);
         acc[0] += s * dx; acc[1] += s * dy; acc[2] += s * dz;
         acc[3] += e1; acc[4] += e2;
     }
+#pragma unroll 4
     for (int j = threadIdx.x; j < P.nv; j += blockDim.x) {  // mesh-ion (for ions), src/newforces.cpp:228-249
         const double4 pj = ldg4(xyzq + j);
         const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
         double s, e1, e2;
-        ion_pair(dx, dy, dz, P.coef * pi.w * pj.w, P.inv_lambda, P.elj, P.d2_mi, P.cut2_mi, s, e1, e2);
+        ion_pair(dx, dy, dz, P.coef * pi.w * pj.w, P.inv_lambda, P.c2s, tab, P.elj, P.d2_mi, P.cut2_mi, s, e1, e2);
         acc[0] += s * dx; acc[1] += s * dy; acc[2] += s * dz;
     }
     block_sum<5>(acc, red);

@@ -1414,6 +1414,7 @@ int npsl_set_ions(npsl_ctx *c, int n_ions, const double *pos, const double *vel,
     ip.d2_mi = lj_length_mesh_ions * lj_length_mesh_ions; ip.cut2_mi = 1.25992104989487316476 * ip.d2_mi;
     ip.d2_ii = diameter * diameter; ip.cut2_ii = 1.25992104989487316476 * ip.d2_ii;
     ip.dt = c->prm.dt;
+    ip.c2s = c->pp.c2s;
     // the reverse half-chain of the first step needs the ions' kinetic energy: same preparation as after npsl_set_thermostat
     k_ion_finish<false><<<1, 256, 0, c->s_main>>>(c->ion_vel, c->ion_force, c->ion_e, c->scal, c->ip);
     k_thermo_prepare<<<1, 32, 0, c->s_main>>>(c->th_cur, c->th_mid, c->scal, c->mp);

@@ -12,6 +12,12 @@ with capi.Context(w.mesh.edges, w.mesh.faces, w.params["l0"], P, n_vertices=w.n_
     ctx.upload_state(w.mesh.pos, np.zeros_like(w.mesh.pos), w.q)
     if len(sys.argv) > 4:
         ctx.set_pair_plan(int(sys.argv[3]), int(sys.argv[4]))
+    n_ions = int(os.environ.get("NPSL_PROFILE_IONS", "0"))
+    if n_ions:  # explicit counterions on a shell around the membrane (timing only)
+        rng = np.random.default_rng(1)
+        d = rng.standard_normal((n_ions, 3))
+        ctx.set_ions(d / np.linalg.norm(d, axis=1)[:, None] * rng.uniform(1.1, 1.6, size=(n_ions, 1)), None, -np.ones(n_ions),
+                     0.06, 0.5 * (w.params["avg_edge_length"] + 0.06))
     ctx.force_init()
     ctx.step(steps)
     if os.environ.get("NPSL_PROFILE_SEGMENTS"):
