@@ -7,7 +7,7 @@
 // rsqrt / table-exp (<= 3e-16 relative error, pair_kernel.cuh), the WCA branch -- live here, ions do touch the membrane
 // and each other -- the reference's expression with per-class LJ lengths (INTERFACE::lj_length_mesh_ions for
 // mesh-ion, the ion diameter for ion-ion). Fixed summation orders, no atomics.
-//   k_ion_mesh_rows  one thread per mesh vertex, ions staged through shared memory: force of all ions on the vertex
+//   k_ion_mesh_rows  four lanes per mesh vertex, ions staged through shared memory: force of all ions on the vertex
 //                    and the vertex's mesh-ion energies (counted once, on the mesh side, like the reference)
 //   k_ion_rows       one CTA per ion: force of all vertices and all other ions on it (ordered block sum), its
 //                    ion-ion energies (halved)
@@ -50,37 +50,44 @@ __device__ __forceinline__ void ion_pair(const double dx, const double dy, const
     }
 }
 
+// Four lanes per vertex: lane s of a vertex's quad takes the ions s, s + 4, ... of every staged tile; the four partial
+// sums are combined in the fixed tree (s0 + s1) + (s2 + s3). 32 vertices per CTA.
 __global__ void __launch_bounds__(128)
 k_ion_mesh_rows(const double4 *__restrict__ xyzq, const double4 *__restrict__ ion_xyzq, double4 *__restrict__ out /* f, es */,
                 double *__restrict__ out_lj, const IonParams P) {
     __shared__ double4 sj[256];
     __shared__ double tab[kExpTab];
     for (int k = threadIdx.x; k < kExpTab; k += blockDim.x) tab[k] = c_exp2_tab[k];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * 32 + (threadIdx.x >> 2), sub = threadIdx.x & 3;
     const double4 pi = xyzq[min(i, P.nv - 1)];
-    double fx = 0, fy = 0, fz = 0, es = 0, lj = 0;
+    double acc[5] = {0, 0, 0, 0, 0};  // fx fy fz es lj
     for (int j0 = 0; j0 < P.n_ions; j0 += 256) {
         const int cnt = min(256, P.n_ions - j0);
         __syncthreads();
         for (int k = threadIdx.x; k < cnt; k += blockDim.x) sj[k] = ion_xyzq[j0 + k];
         __syncthreads();
-#pragma unroll 4  // four independent rsqrt / exp chains in flight; the sums stay in ion order
-        for (int k = 0; k < cnt; k++) {
+#pragma unroll 4  // independent rsqrt / exp chains in flight; each lane's sums stay in ion order
+        for (int k = sub; k < cnt; k += 4) {
             const double4 pj = sj[k];
             const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
             double s, e1, e2;
             ion_pair(dx, dy, dz, P.coef * pi.w * pj.w, P.inv_lambda, P.c2s, tab, P.elj, P.d2_mi, P.cut2_mi, s, e1, e2);
-            fx += s * dx; fy += s * dy; fz += s * dz;
-            es += e1; lj += e2;
+            acc[0] += s * dx; acc[1] += s * dy; acc[2] += s * dz;
+            acc[3] += e1; acc[4] += e2;
         }
     }
-    if (i < P.nv) {
-        out[i] = make_double4(fx, fy, fz, es);
-        out_lj[i] = lj;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
+    }
+    if (sub == 0 && i < P.nv) {
+        out[i] = make_double4(acc[0], acc[1], acc[2], acc[3]);
+        out_lj[i] = acc[4];
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_ion_rows(const double4 *__restrict__ xyzq, const double4 *__restrict__ ion_xyzq, double4 *__restrict__ ion_force,
            double2 *__restrict__ ion_e, const IonParams P) {
     __shared__ double red[5 * 32];

@@ -546,8 +546,8 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
         n++;
     }
     if (c->mp.n_ions > 0) {  // mesh-ion and ion-ion terms, beside the mesh-mesh pair kernel
-        k_ion_mesh_rows<<<(c->nv + 127) / 128, 128, 0, c->s_side>>>(c->xyzq, c->ion_xyzq, c->ion_mesh, c->ion_mesh_lj, c->ip);
-        k_ion_rows<<<c->mp.n_ions, 128, 0, c->s_side>>>(c->xyzq, c->ion_xyzq, c->ion_force, c->ion_e, c->ip);
+        k_ion_mesh_rows<<<(c->nv + 31) / 32, 128, 0, c->s_side>>>(c->xyzq, c->ion_xyzq, c->ion_mesh, c->ion_mesh_lj, c->ip);
+        k_ion_rows<<<c->mp.n_ions, 256, 0, c->s_side>>>(c->xyzq, c->ion_xyzq, c->ion_force, c->ion_e, c->ip);
         n += 2;
     }
     CU(cudaEventRecord(c->ev_join, c->s_side));
