@@ -259,7 +259,7 @@ def run_b200(args) -> None:
     geo = ctx.pair_geometry()
     lo, hi = ctx.owned_rows()
 
-    profile_txt = ctx.step_profile(20) if args.profile else None
+    profile_txt = ctx.step_profile(20)  # per-segment device time of directly launched steps (CUDA events between launches)
 
     # ---- end to end through the host-buffer entry point: state lives in host memory between steps
     pos = np.ascontiguousarray(ctx.download_state()["pos"])
@@ -297,6 +297,21 @@ def run_b200(args) -> None:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("%s:%d" % (args.workload, world), {}).get("bytes")
     except Exception:
         pass
+
+    # the O(N) kernels on the critical path: algorithmic bytes / segment time against the measured HBM peak
+    seg = {}
+    for ln in profile_txt.splitlines():
+        t = ln.split()
+        if len(t) >= 3 and t[-1] == "us":
+            seg[" ".join(t[:-2])] = float(t[-2])
+    n_own = hi - lo
+    hbm_kernels = []
+    for name, nbytes, what in (
+            ("k_kick_drift", 160 * n_own, "x, v, f read, x, v written: 160 B per integrated vertex"),
+            ("k_vertex", (8 * 24 + 32 + 32 + 8 + 64) * n_own, "8 pair sums, fmesh, v, q read, f, v written: 328 B per integrated vertex")):
+        if name in seg and seg[name] > 0:
+            hbm_kernels.append({"kernel": name, "us": seg[name], "algorithmic_bytes": nbytes, "gbs": nbytes / seg[name] * 1e-3,
+                                "bytes": what})
 
     ctx.close()
     if rank != 0:
@@ -346,6 +361,10 @@ def run_b200(args) -> None:
                            (nominal_mhz, 148 * 64 * 2 * nominal_mhz * 1e-6),
             "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
         },
+        "hbm_kernels": {"peak_gbs": peaks.get("hbm_gbs"), "kernels": hbm_kernels, "segments_us": seg,
+                        "note": "segments of directly launched steps, event to event, so each includes its launch gap; these "
+                                "kernels are latency-bound at this size (DESIGN.md section 3 has the ncu durations and the "
+                                "bandwidth-bound k_pair_reduce)"},
         "checks": {"conserved_energy_drift": cons(e1) / cons(e0) - 1.0, "finite": bool(np.isfinite(cons(e1))),
                    "kinetic_after_e2e": ke},
     }
@@ -358,7 +377,7 @@ def run_b200(args) -> None:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "reference",
                                     "sample": "unavailable: %s" % ex}
     print(json.dumps(line), flush=True)
-    if profile_txt:
+    if profile_txt and args.profile:
         sys.stderr.write("step breakdown on rank 0 (%d GPU(s)):\n%s" % (world, profile_txt))
     if world > 1:
         dist.barrier()
