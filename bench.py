@@ -27,6 +27,17 @@ import sys
 import tempfile
 import time
 
+# stdout carries exactly one JSON line. NCCL writes its "NCCL version ..." banner (and any NCCL_DEBUG output) to the C
+# stdout of rank 0, so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a duplicate
+# of the original stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -177,7 +188,7 @@ def run_reference(args) -> None:
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -376,7 +387,7 @@ def run_b200(args) -> None:
         except Exception as ex:  # the baseline is reported, never required for the GPU numbers
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "reference",
                                     "sample": "unavailable: %s" % ex}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if profile_txt and args.profile:
         sys.stderr.write("step breakdown on rank 0 (%d GPU(s)):\n%s" % (world, profile_txt))
     if world > 1:
