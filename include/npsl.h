@@ -246,6 +246,14 @@ int npsl_pair_mode(const npsl_ctx *ctx);
  * 0 single GPU, 1 NCCL all-gathers, 2 direct stores into peer memory over NVLink (CUDA IPC; default when the
  * buffers can be mapped; NPSL_EXCHANGE=nccl in the environment forces 1). */
 int npsl_exchange_mode(const npsl_ctx *ctx);
+/* The work decomposition of the symmetric pair kernel, computed on the host without touching a device (for tests and
+ * tools): the units (row block, column chunk) that rank `rank` of `world` computes, in launch order. Per unit four
+ * int32 in `units` (at most max_units are written): row block, chunk, first column, one past the last column; a unit
+ * covers the pairs (i, j) with i in the row block, j in [first, last) and j > i. geometry (6 int32, may be NULL): rows per
+ * row block, column granularity, number of chunks, number of full-width chunks, tiles per full-width and per
+ * half-width chunk. Returns the number of units of that rank (>= 0) or a negative status. The decomposition depends on
+ * the vertex count only; ranks own the virtual ranks [8 rank / world, 8 (rank + 1) / world). */
+int npsl_plan_pair_units(int n_vertices, int rank, int world, int32_t *units, int max_units, int32_t *geometry);
 /* Sharding plan of a multi-GPU context: 0 single GPU; 1 rows -- vertices are owned in slices like the reference's
  * MPI ranks (src/main.cpp:448-455), three exchanges per step; 2 replicated integrator -- only the pair term is
  * split and every rank integrates all vertices, as the reference does after its all_gather of forces

@@ -27,7 +27,7 @@ SYMBOLS = [
     "npsl_pair_timing_read", "npsl_owned_rows", "npsl_pair_geometry", "npsl_fp64_peak", "npsl_md_run",
     "npsl_step_timing", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_md_step_host", "npsl_set_pair_mode",
     "npsl_pair_mode", "npsl_exchange_mode", "npsl_shard_plan", "npsl_vertex_geometry", "npsl_local_energies", "npsl_step_profile", "npsl_set_volume_constraint", "npsl_constraint_init",
-    "npsl_constraint_multipliers", "npsl_set_ions", "npsl_download_ions",
+    "npsl_constraint_multipliers", "npsl_set_ions", "npsl_download_ions", "npsl_plan_pair_units",
 ]
 
 
@@ -116,6 +116,7 @@ def load() -> C.CDLL:
     L.npsl_pair_mode.argtypes = [vp]
     L.npsl_exchange_mode.argtypes = [vp]
     L.npsl_shard_plan.argtypes = [vp]
+    L.npsl_plan_pair_units.argtypes = [C.c_int, C.c_int, C.c_int, ip, C.c_int, ip]
     L.npsl_set_ions.argtypes = [vp, C.c_int, dp, dp, dp, C.c_double, C.c_double]
     L.npsl_download_ions.argtypes = [vp, dp, dp, dp]
     L.npsl_vertex_geometry.argtypes = [vp, dp, dp]
@@ -164,6 +165,20 @@ def make_params(p: dict, mesh_bath, ions_bath) -> Params:
     fill_bath(P.mesh_bath, mesh_bath)
     fill_bath(P.ions_bath, ions_bath)
     return P
+
+
+def plan_pair_units(n_vertices: int, rank: int = 0, world: int = 1):
+    """Units of the symmetric pair kernel for one rank, without a device: (units [k,4] = row block, chunk, first column,
+    one past the last column; geometry dict)."""
+    L = load()
+    geo = np.zeros(6, dtype=np.int32)
+    n = L.npsl_plan_pair_units(n_vertices, rank, world, None, 0, geo.ctypes.data_as(C.POINTER(C.c_int32)))
+    if n < 0:
+        raise NpslError(n, (L.npsl_last_error(None) or b"").decode())
+    units = np.zeros((n, 4), dtype=np.int32)
+    L.npsl_plan_pair_units(n_vertices, rank, world, units.ctypes.data_as(C.POINTER(C.c_int32)), n, None)
+    return units, dict(zip(["rows_per_block", "column_granularity", "chunks", "full_chunks", "tiles_full", "tiles_half"],
+                           [int(x) for x in geo]))
 
 
 def nccl_unique_id() -> bytes:

@@ -365,15 +365,12 @@ void apply_pair_plan(npsl_ctx *c) {
     c->mp.row_stride = c->pair_row_stride;
 }
 
-// Units of the symmetric pair kernel. Everything here depends on the vertex count only, except which of
-// the 8 virtual ranks this rank computes: [rank*8/world, (rank+1)*8/world). A row block's units all belong
-// to sym_vrank(row block).
-int plan_sym(npsl_ctx *c) {
-    const int nv = c->nv;
-    SymParams &sp = c->sp;
+// Column-chunk geometry of the symmetric pair kernel: a function of the vertex count and the kernel variant's
+// row-block size only (plus the two measurement knobs), never of the rank count.
+void sym_geometry(int nv, int rb, SymParams &sp) {
     sp.n = nv;
     sp.npad = (nv + kSymPad - 1) / kSymPad * kSymPad;
-    sp.rb = c->sym_rows * c->sym_threads;
+    sp.rb = rb;
     // 256 columns per unit up to 32768 vertices, at most 256 chunks beyond: fine-grained enough to fill 8 GPUs
     sp.chunk_tiles = std::max(2, (nv + 256 * kSymCT - 1) / (256 * kSymCT));
     if (const char *e = getenv("NPSL_SYM_CHUNK_TILES"))  // measurement knob; changes the grouping of the row sums
@@ -389,6 +386,36 @@ int plan_sym(npsl_ctx *c) {
     sp.n_coarse = fine_pct >= 100 ? 0 : (coarse_tiles + sp.chunk_tiles - 1) / sp.chunk_tiles;
     const int rest = std::max(0, n_tiles - sp.n_coarse * sp.chunk_tiles);
     sp.n_chunks = sp.n_coarse + (rest + sp.fine_tiles - 1) / sp.fine_tiles;
+}
+
+struct SymUnit { int I, cc, work; };
+
+// Units (row block, column chunk) of the virtual ranks [v_first, v_first + v_count), heaviest first; returns the
+// number of units of all virtual ranks. A row block's units all belong to sym_vrank(row block).
+int sym_units_of(const SymParams &sp, int v_first, int v_count, std::vector<SymUnit> &mine) {
+    const int n_tiles = (sp.n + kSymCT - 1) / kSymCT, n_rb = (sp.n + sp.rb - 1) / sp.rb;
+    int total = 0;
+    mine.clear();
+    for (int I = 0; I < n_rb; I++) {
+        const int v = sym_vrank(I);
+        for (int cc = 0; cc < sp.n_chunks; cc++) {
+            const int tile_end = std::min(sym_chunk_tile0(sp, cc + 1), n_tiles);
+            const int tile_begin = std::max(sym_chunk_tile0(sp, cc), I * sp.rb / kSymCT);
+            if (tile_end <= tile_begin) continue;
+            total++;
+            if (v >= v_first && v < v_first + v_count) mine.push_back({I, cc, tile_end - tile_begin});
+        }
+    }
+    std::stable_sort(mine.begin(), mine.end(), [](const SymUnit &a, const SymUnit &b) { return a.work > b.work; });
+    return total;
+}
+
+// Units of the symmetric pair kernel. Everything here depends on the vertex count only, except which of
+// the 8 virtual ranks this rank computes: [rank*8/world, (rank+1)*8/world).
+int plan_sym(npsl_ctx *c) {
+    const int nv = c->nv;
+    SymParams &sp = c->sp;
+    sym_geometry(nv, c->sym_rows * c->sym_threads, sp);
     sp.c2s = c->pp.c2s; sp.inv_lambda = c->pp.inv_lambda; sp.lj_cut_hi = c->pp.lj_cut_hi;
     const int n_rb = (nv + sp.rb - 1) / sp.rb;
     const bool want = c->pair_mode == 2 || (c->pair_mode == 0 && nv >= 4096);
@@ -407,21 +434,8 @@ int plan_sym(npsl_ctx *c) {
             c->sym_v_first = er * c->sym_v_count;
         }
     }
-    struct U { int I, cc, work; };
-    std::vector<U> mine;
-    int total = 0;
-    for (int I = 0; I < n_rb; I++) {
-        const int v = sym_vrank(I);
-        for (int cc = 0; cc < sp.n_chunks; cc++) {
-            const int tile_end = std::min(sym_chunk_tile0(sp, cc + 1), n_tiles);
-            const int tile_begin = std::max(sym_chunk_tile0(sp, cc), I * sp.rb / kSymCT);
-            if (tile_end <= tile_begin) continue;
-            total++;
-            if (v >= c->sym_v_first && v < c->sym_v_first + c->sym_v_count) mine.push_back({I, cc, tile_end - tile_begin});
-        }
-    }
-    c->sym_n_units_total = total;
-    std::stable_sort(mine.begin(), mine.end(), [](const U &a, const U &b) { return a.work > b.work; });
+    std::vector<SymUnit> mine;
+    c->sym_n_units_total = sym_units_of(sp, c->sym_v_first, c->sym_v_count, mine);
     std::vector<int2> units(mine.size());
     for (size_t k = 0; k < mine.size(); k++) units[k] = make_int2(mine[k].I, mine[k].cc);
     c->sym_n_units = (int) units.size();
@@ -1679,6 +1693,28 @@ int npsl_set_pair_mode(npsl_ctx *c, int mode) {
 int npsl_pair_mode(const npsl_ctx *c) { return c ? (c->use_sym ? 2 : 1) : NPSL_ERR_ARG; }
 
 int npsl_exchange_mode(const npsl_ctx *c) { return c ? (c->world == 1 ? 0 : (c->p2p ? 2 : 1)) : NPSL_ERR_ARG; }
+
+int npsl_plan_pair_units(int n_vertices, int rank, int world, int32_t *units, int max_units, int32_t *geometry) {
+    npsl_ctx *c = nullptr;
+    if (n_vertices < 1 || world < 1 || rank < 0 || rank >= world || kSymV % world != 0)
+        return fail(c, NPSL_ERR_ARG, "bad arguments (the rank count must divide 8)");
+    SymParams sp;
+    memset(&sp, 0, sizeof sp);
+    sym_geometry(n_vertices, 4 * 128, sp);
+    std::vector<SymUnit> mine;
+    const int v_count = kSymV / world;
+    sym_units_of(sp, rank * v_count, v_count, mine);
+    if (geometry) {
+        geometry[0] = sp.rb; geometry[1] = kSymCT; geometry[2] = sp.n_chunks;
+        geometry[3] = sp.n_coarse; geometry[4] = sp.chunk_tiles; geometry[5] = sp.fine_tiles;
+    }
+    for (int k = 0; k < (int) mine.size() && k < max_units; k++) {
+        const int t0 = std::max(sym_chunk_tile0(sp, mine[k].cc) * kSymCT, mine[k].I * sp.rb);
+        const int t1 = std::min(sym_chunk_tile0(sp, mine[k].cc + 1) * kSymCT, n_vertices);
+        units[4 * k] = mine[k].I; units[4 * k + 1] = mine[k].cc; units[4 * k + 2] = t0; units[4 * k + 3] = t1;
+    }
+    return (int) mine.size();
+}
 
 int npsl_shard_plan(const npsl_ctx *c) { return c ? (c->world == 1 ? 0 : (c->replicated ? 2 : 1)) : NPSL_ERR_ARG; }
 

@@ -133,3 +133,44 @@ def test_shard_ranges_tile_the_rows(n, world):
     # never more than one warp of rows away from the reference's ceil(N/P) slices
     ref = M.row_partition(n, 0, world)
     assert 0 <= M.shard_range(n, 0, world)[1] - ref[1] < 32
+
+
+# ---- the symmetric pair kernel's work decomposition (host-side planner, no device needed) -----------------------
+
+def _pair_count(units, n):
+    """Number of pairs (i, j), j > i, that the units cover, and a coverage check on a coarse grid."""
+    total = 0
+    for I, c, j0, j1 in units:
+        i0, i1 = I * 512, min((I + 1) * 512, n)
+        for i in (range(i0, i1) if j0 < i1 else ()):  # rows that overlap the column range (diagonal units)
+            total += max(0, j1 - max(j0, i + 1))
+        if j0 >= i1:
+            total += (i1 - i0) * (j1 - j0)
+    return total
+
+
+@pytest.mark.parametrize("n", [4096, 10242, 40962])
+def test_symmetric_units_cover_every_pair_exactly_once_on_any_rank_count(n):
+    """Units are a function of the vertex count only; the ranks of a 1/2/4/8-GPU job share them out by virtual rank.
+    Together they cover each unordered pair once, and the shares are balanced."""
+    from np_shape_lab_b200 import capi
+    all_units, geo1 = capi.plan_pair_units(n, 0, 1)
+    assert geo1["rows_per_block"] == 512 and geo1["column_granularity"] == 128
+    assert _pair_count(all_units.tolist(), n) == n * (n - 1) // 2
+    keys1 = sorted((int(u[0]), int(u[1])) for u in all_units)
+    assert len(set(keys1)) == len(keys1)
+    work = np.array([(u[3] - u[2]) for u in all_units])
+    assert np.all(np.diff(-((work + 127) // 128)) >= 0)  # launch order: heaviest (most column tiles) first
+    for world in (2, 4, 8):
+        per_rank, keys = [], []
+        for r in range(world):
+            u, geo = capi.plan_pair_units(n, r, world)
+            assert geo == geo1  # the decomposition does not depend on the rank count
+            keys += [(int(a[0]), int(a[1])) for a in u]
+            per_rank.append(_pair_count(u.tolist(), n))
+        assert sorted(keys) == keys1
+        assert sum(per_rank) == n * (n - 1) // 2
+        if n >= 40962:
+            assert max(per_rank) <= 1.01 * min(per_rank), per_rank  # balanced shares
+    with pytest.raises(capi.NpslError):
+        capi.plan_pair_units(n, 0, 3)
