@@ -1,16 +1,16 @@
 // Explicit counterions, FP64, sm_100a.
 //
 // The reference walks, besides the mesh-mesh pairs, every mesh-ion pair twice (once for the force on the vertex,
-// once for the force on the ion) and every ordered ion-ion pair (src/newforces.cpp:44-65,179-250), and repeats the
+// once for the force on the ion; here once) and every ordered ion-ion pair (src/newforces.cpp:44-65,179-250), and repeats the
 // walks for the energies (src/interface.cpp:1059-1089). Ions are few (|q| / valency, hundreds to a few thousand), so
 // these are two small kernels beside the mesh-mesh pair kernel: the screened-Coulomb part uses the pair kernel's
 // rsqrt / table-exp (<= 3e-16 relative error, pair_kernel.cuh), the WCA branch -- live here, ions do touch the membrane
 // and each other -- the reference's expression with per-class LJ lengths (INTERFACE::lj_length_mesh_ions for
 // mesh-ion, the ion diameter for ion-ion). Fixed summation orders, no atomics.
-//   k_ion_mesh_rows  four lanes per mesh vertex, ions staged through shared memory: force of all ions on the vertex
-//                    and the vertex's mesh-ion energies (counted once, on the mesh side, like the reference)
-//   k_ion_rows       one CTA per ion: force of all vertices and all other ions on it (ordered block sum), its
-//                    ion-ion energies (halved)
+//   k_ion_mesh       every mesh-ion pair once: force of all ions on each vertex, the vertex's mesh-ion energies (counted
+//                    once, on the mesh side, like the reference), and per CTA the vertices' pull on every ion
+//   k_ion_rows       one CTA per ion: all other ions on it plus the per-CTA sums of k_ion_mesh (ordered block sum),
+//                    its ion-ion energies (halved)
 //   k_ion_kick_drift first half-kick and drift of the ions (PARTICLE::update_real_velocity / update_real_position,
 //                    src/particle.h:66-83, src/newmd.cpp:116-123)
 //   k_ion_finish     second half-kick, the ions' kinetic energy (src/newenergies.h:18-26) and the totals of the ion-ion
@@ -50,46 +50,74 @@ __device__ __forceinline__ void ion_pair(const double dx, const double dy, const
     }
 }
 
-// Four lanes per vertex: lane s of a vertex's quad takes the ions s, s + 4, ... of every staged tile; the four partial
-// sums are combined in the fixed tree (s0 + s1) + (s2 + s3). 32 vertices per CTA.
+// Every mesh-ion pair once (Newton's third law), the way k_pair_sym treats the mesh-mesh pairs: a CTA owns 128
+// vertices (one per thread, force and energies in registers) and walks the ions in tiles of 128 staged in shared memory
+// together with one force accumulator per ion. The four warps work on the four 32-ion groups of a tile and rotate
+// groups between four phases; inside a phase lane l visits ion (l + s) mod 32 at step s, so an ion's accumulator is
+// touched by exactly one thread at a time: no atomics, fixed order. Grid = (vertex blocks, ion tiles): a CTA works on
+// one tile, so that a few hundred ions still give every SM enough warps. The vertices' sums go to out[tile][vertex]
+// (k_vertex adds the tiles in order), the ions' sums to ion_part[vertex block][3][n_ions] (k_ion_rows adds the blocks
+// in order).
+constexpr int kIonTile = 128;
+
 __global__ void __launch_bounds__(128)
-k_ion_mesh_rows(const double4 *__restrict__ xyzq, const double4 *__restrict__ ion_xyzq, double4 *__restrict__ out /* f, es */,
-                double *__restrict__ out_lj, const IonParams P) {
-    __shared__ double4 sj[256];
+k_ion_mesh(const double4 *__restrict__ xyzq, const double4 *__restrict__ ion_xyzq, double4 *__restrict__ out /* f, es */,
+           double *__restrict__ out_lj, double *__restrict__ ion_part, const IonParams P) {
+    __shared__ double sx[kIonTile], sy[kIonTile], sz[kIonTile], sq[kIonTile];
+    __shared__ double sax[kIonTile], say[kIonTile], saz[kIonTile];
     __shared__ double tab[kExpTab];
-    for (int k = threadIdx.x; k < kExpTab; k += blockDim.x) tab[k] = c_exp2_tab[k];
-    const int i = blockIdx.x * 32 + (threadIdx.x >> 2), sub = threadIdx.x & 3;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    for (int k = t; k < kExpTab; k += blockDim.x) tab[k] = c_exp2_tab[k];
+    const int i = blockIdx.x * blockDim.x + t;
     const double4 pi = xyzq[min(i, P.nv - 1)];
-    double acc[5] = {0, 0, 0, 0, 0};  // fx fy fz es lj
-    for (int j0 = 0; j0 < P.n_ions; j0 += 256) {
-        const int cnt = min(256, P.n_ions - j0);
+    const double qi = P.coef * pi.w;
+    double fx = 0, fy = 0, fz = 0, es = 0, lj = 0;
+    {
+        const int j0 = blockIdx.y * kIonTile;
+        const int j = j0 + t;
+        if (j < P.n_ions) {
+            const double4 v = ion_xyzq[j];
+            sx[t] = v.x; sy[t] = v.y; sz[t] = v.z; sq[t] = v.w;
+        } else {  // padding ions: far away, no charge
+            sx[t] = 1.0e3 + t; sy[t] = 0.0; sz[t] = 0.0; sq[t] = 0.0;
+        }
+        sax[t] = 0.0; say[t] = 0.0; saz[t] = 0.0;
         __syncthreads();
-        for (int k = threadIdx.x; k < cnt; k += blockDim.x) sj[k] = ion_xyzq[j0 + k];
-        __syncthreads();
-#pragma unroll 4  // independent rsqrt / exp chains in flight; each lane's sums stay in ion order
-        for (int k = sub; k < cnt; k += 4) {
-            const double4 pj = sj[k];
-            const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-            double s, e1, e2;
-            ion_pair(dx, dy, dz, P.coef * pi.w * pj.w, P.inv_lambda, P.c2s, tab, P.elj, P.d2_mi, P.cut2_mi, s, e1, e2);
-            acc[0] += s * dx; acc[1] += s * dy; acc[2] += s * dz;
-            acc[3] += e1; acc[4] += e2;
+        for (int p = 0; p < 4; p++) {
+            const int o = ((warp + p) & 3) * 32;
+            if (j0 + o < P.n_ions) {
+#pragma unroll 2
+                for (int s = 0; s < 32; s++) {
+                    const int col = o + ((lane + s) & 31);
+                    const double dx = pi.x - sx[col], dy = pi.y - sy[col], dz = pi.z - sz[col];
+                    double f, e1, e2;
+                    ion_pair(dx, dy, dz, qi * sq[col], P.inv_lambda, P.c2s, tab, P.elj, P.d2_mi, P.cut2_mi, f, e1, e2);
+                    if (i >= P.nv || j0 + col >= P.n_ions) { f = 0.0; e1 = 0.0; e2 = 0.0; }  // rows / ions past the end
+                    const double gx = f * dx, gy = f * dy, gz = f * dz;
+                    fx += gx; fy += gy; fz += gz;
+                    es += e1; lj += e2;
+                    sax[col] -= gx; say[col] -= gy; saz[col] -= gz;
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+        }
+        if (j < P.n_ions) {
+            double *q = ion_part + (size_t) blockIdx.x * 3 * P.n_ions + j;
+            q[0] = sax[t];
+            q[P.n_ions] = say[t];
+            q[2 * (size_t) P.n_ions] = saz[t];
         }
     }
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
-        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
-    }
-    if (sub == 0 && i < P.nv) {
-        out[i] = make_double4(acc[0], acc[1], acc[2], acc[3]);
-        out_lj[i] = acc[4];
+    if (i < P.nv) {
+        out[(size_t) blockIdx.y * P.nv + i] = make_double4(fx, fy, fz, es);
+        out_lj[(size_t) blockIdx.y * P.nv + i] = lj;
     }
 }
 
 __global__ void __launch_bounds__(256)
-k_ion_rows(const double4 *__restrict__ xyzq, const double4 *__restrict__ ion_xyzq, double4 *__restrict__ ion_force,
-           double2 *__restrict__ ion_e, const IonParams P) {
+k_ion_rows(const double4 *__restrict__ ion_xyzq, const double *__restrict__ ion_part, int n_mesh_ctas,
+           double4 *__restrict__ ion_force, double2 *__restrict__ ion_e, const IonParams P) {
     __shared__ double red[5 * 32];
     __shared__ double tab[kExpTab];
     for (int k = threadIdx.x; k < kExpTab; k += blockDim.x) tab[k] = c_exp2_tab[k];
@@ -107,13 +135,9 @@ k_ion_rows(const double4 *__restrict__ xyzq, const double4 *__restrict__ ion_xyz
         acc[0] += s * dx; acc[1] += s * dy; acc[2] += s * dz;
         acc[3] += e1; acc[4] += e2;
     }
-#pragma unroll 4
-    for (int j = threadIdx.x; j < P.nv; j += blockDim.x) {  // mesh-ion (for ions), src/newforces.cpp:228-249
-        const double4 pj = ldg4(xyzq + j);
-        const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-        double s, e1, e2;
-        ion_pair(dx, dy, dz, P.coef * pi.w * pj.w, P.inv_lambda, P.c2s, tab, P.elj, P.d2_mi, P.cut2_mi, s, e1, e2);
-        acc[0] += s * dx; acc[1] += s * dy; acc[2] += s * dz;
+    for (int b = threadIdx.x; b < n_mesh_ctas; b += blockDim.x) {  // the vertices' pull: per-CTA sums of k_ion_mesh
+        const double *q = ion_part + (size_t) b * 3 * P.n_ions + i;
+        acc[0] += __ldcg(q); acc[1] += __ldcg(q + P.n_ions); acc[2] += __ldcg(q + 2 * (size_t) P.n_ions);
     }
     block_sum<5>(acc, red);
     if (threadIdx.x == 0) {

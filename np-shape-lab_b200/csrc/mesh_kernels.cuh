@@ -582,11 +582,15 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
             fp.x += a.x; fp.y += a.y; fp.z += a.z; ulj = a.w;
         }
         double ue_ion = 0, ulj_ion = 0;
-        if (P.n_ions > 0) {  // force of the counterions on the vertex, its mesh-ion energies (k_ion_mesh_rows)
-            const double4 a = ldcg4(ion_mesh + i);
-            fp.x += a.x; fp.y += a.y; fp.z += a.z;
-            ue_ion = a.w;
-            ulj_ion = __ldcg(ion_mesh_lj + i);
+        if (P.n_ions > 0) {  // force of the counterions on the vertex and its mesh-ion energies: k_ion_mesh's ion tiles, in order
+            double ax = 0, ay = 0, az = 0;
+            for (int tile = 0; tile < (P.n_ions + 127) / 128; tile++) {
+                const double4 a = ldcg4(ion_mesh + (size_t) tile * P.nv + i);
+                ax += a.x; ay += a.y; az += a.z;
+                ue_ion += a.w;
+                ulj_ion += __ldcg(ion_mesh_lj + (size_t) tile * P.nv + i);
+            }
+            fp.x += ax; fp.y += ay; fp.z += az;
         }
         const double4 fm = ldcg4(fmesh + i);
         const V3 f = mk(fp.x + fm.x, fp.y + fm.y, fp.z + fm.z);

@@ -111,7 +111,7 @@ struct npsl_ctx {
     IonParams ip;
     double4 *ion_xyzq = nullptr, *ion_vel = nullptr, *ion_force = nullptr, *ion_mesh = nullptr;
     double2 *ion_e = nullptr;
-    double *ion_mesh_lj = nullptr;
+    double *ion_mesh_lj = nullptr, *ion_part = nullptr;  // ion_part: per-CTA sums of the vertices' pull on the ions
     double *peak_out = nullptr;
 
     // launch geometry
@@ -560,8 +560,10 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
         n++;
     }
     if (c->mp.n_ions > 0) {  // mesh-ion and ion-ion terms, beside the mesh-mesh pair kernel
-        k_ion_mesh_rows<<<(c->nv + 31) / 32, 128, 0, c->s_side>>>(c->xyzq, c->ion_xyzq, c->ion_mesh, c->ion_mesh_lj, c->ip);
-        k_ion_rows<<<c->mp.n_ions, 256, 0, c->s_side>>>(c->xyzq, c->ion_xyzq, c->ion_force, c->ion_e, c->ip);
+        const int ion_ctas = (c->nv + 127) / 128;
+        k_ion_mesh<<<dim3(ion_ctas, (c->mp.n_ions + 127) / 128), 128, 0, c->s_side>>>(c->xyzq, c->ion_xyzq, c->ion_mesh, c->ion_mesh_lj,
+                                                                                        c->ion_part, c->ip);
+        k_ion_rows<<<c->mp.n_ions, 256, 0, c->s_side>>>(c->ion_xyzq, c->ion_part, ion_ctas, c->ion_force, c->ion_e, c->ip);
         n += 2;
     }
     CU(cudaEventRecord(c->ev_join, c->s_side));
@@ -1084,7 +1086,7 @@ void npsl_destroy(npsl_ctx *c) {
     void *ptrs[] = {c->xyzq, c->vel, c->force, c->fmesh, c->ngv, c->part_con, c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->face_v,
                     c->edge_rec, c->l0, c->degree, c->ring, c->bslot_ref, c->ring_l0, c->bslot, c->pair_partial,
                     c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_warp, c->th_cur, c->th_mid, c->part_mesh,
-                    c->part_vert, c->tickets, c->ion_xyzq, c->ion_vel, c->ion_force, c->ion_mesh, c->ion_e, c->ion_mesh_lj, c->edge_E, c->vertex_e, c->face_e, c->face_local, c->vertex_geo, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units, c->red_groups,
+                    c->part_vert, c->tickets, c->ion_xyzq, c->ion_vel, c->ion_force, c->ion_mesh, c->ion_e, c->ion_mesh_lj, c->ion_part, c->edge_E, c->vertex_e, c->face_e, c->face_local, c->vertex_geo, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units, c->red_groups,
                     c->sym_rowpart, c->sym_colpart, c->sym_fv, c->xflags, c->xstate, c->xtickets,
                     c->d_peer_xyzq, c->d_peer_fv, c->d_peer_ke, c->d_peer_flags};
     for (void *p : ptrs)
@@ -1401,10 +1403,10 @@ int npsl_set_ions(npsl_ctx *c, int n_ions, const double *pos, const double *vel,
         return fail(c, NPSL_ERR_ARG, "explicit counterions need a single-GPU context or the replicated sharding plan");
     if (n_ions > 0 && !(diameter > 0 && lj_length_mesh_ions > 0)) return fail(c, NPSL_ERR_ARG, "ion LJ lengths must be positive");
     CU(cudaStreamSynchronize(c->s_main));
-    void *old[] = {c->ion_xyzq, c->ion_vel, c->ion_force, c->ion_mesh, c->ion_e, c->ion_mesh_lj};
+    void *old[] = {c->ion_xyzq, c->ion_vel, c->ion_force, c->ion_mesh, c->ion_e, c->ion_mesh_lj, c->ion_part};
     for (void *p : old)
         if (p) cudaFree(p);
-    c->ion_xyzq = c->ion_vel = c->ion_force = c->ion_mesh = nullptr; c->ion_e = nullptr; c->ion_mesh_lj = nullptr;
+    c->ion_xyzq = c->ion_vel = c->ion_force = c->ion_mesh = nullptr; c->ion_e = nullptr; c->ion_mesh_lj = c->ion_part = nullptr;
     c->mp.n_ions = n_ions;
     drop_graph(c);
     c->forces_valid = c->local_valid = false;
@@ -1412,7 +1414,9 @@ int npsl_set_ions(npsl_ctx *c, int n_ions, const double *pos, const double *vel,
     CU(cudaMemcpy(c->scal + SC_KE_IONS, zeros, sizeof zeros, cudaMemcpyHostToDevice));
     if (n_ions == 0) return NPSL_OK;
     CU(dalloc(&c->ion_xyzq, n_ions)); CU(dalloc(&c->ion_vel, n_ions)); CU(dalloc(&c->ion_force, n_ions));
-    CU(dalloc(&c->ion_e, n_ions)); CU(dalloc(&c->ion_mesh, c->nv)); CU(dalloc(&c->ion_mesh_lj, c->nv));
+    const size_t ion_tiles = (n_ions + 127) / 128;
+    CU(dalloc(&c->ion_e, n_ions)); CU(dalloc(&c->ion_mesh, ion_tiles * c->nv)); CU(dalloc(&c->ion_mesh_lj, ion_tiles * c->nv));
+    CU(dalloc(&c->ion_part, (size_t) ((c->nv + 127) / 128) * 3 * n_ions));
     std::vector<double4> rec(n_ions), vr(n_ions);
     for (int i = 0; i < n_ions; i++) {
         rec[i] = make_double4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], q[i]);
