@@ -144,6 +144,12 @@ def reference_sample(workload_name: str, budget_s: float, threads: int, reps: in
     probe_rows = min(n, 64 * max(1, threads))
     probe = call(probe_rows, 1, 0)
     per_row = max((probe["best_s"] - t_fixed) / probe_rows, 1e-9)
+    # every call of the reference's force_calculation evaluates the mesh terms in full (t_fixed, ~0.24 s at S64) whatever
+    # the row slice is, so a large --steps cannot fit the time budget: the number of timed calls is capped and reported
+    asked = reps
+    max_calls = max(1, int(budget_s / (t_fixed + per_row * probe_rows)))
+    reps = max(1, min(reps, max_calls))
+    warm = max(0, min(warm, max_calls - reps))
     per_call_budget = budget_s / max(1, reps + warm)
     rows = int(max(probe_rows, min(n, (per_call_budget - t_fixed) / per_row)))
     res = call(rows, reps, warm)
@@ -153,11 +159,13 @@ def reference_sample(workload_name: str, budget_s: float, threads: int, reps: in
     shutil.rmtree(wd, ignore_errors=True)
     return {
         "value": 1.0 / t_step, "pairs_per_s": n * (n - 1) / t_step, "t_step_s": t_step, "t_sample_s": t_sample,
-        "t_fixed_s": t_fixed, "rows": rows, "reps": reps, "threads": res["threads"], "n": n,
+        "t_fixed_s": t_fixed, "rows": rows, "reps": reps, "asked_reps": asked, "threads": res["threads"], "n": n,
         "sample": "reference force_calculation (unmodified src/newforces.cpp via oracle/_ref) on rows [0,%d) of %d "
                   "x all %d columns, %d timed call(s), mesh terms in full; extrapolated to a full step as "
                   "t_fixed + (t_sample - t_fixed) * N/rows with t_fixed = %.3f s from a 1-row slice; 1 process x %d "
-                  "OpenMP threads (no MPI launcher in the image)" % (rows, n, n, reps, t_fixed, res["threads"]),
+                  "OpenMP threads (no MPI launcher in the image)%s" % (
+                      rows, n, n, reps, t_fixed, res["threads"],
+                      "" if reps == asked else "; %d steps were asked for, the %.0f s budget fits %d calls" % (asked, budget_s, reps)),
     }
 
 
@@ -185,6 +193,7 @@ def run_reference(args) -> None:
         "config": {"workload": args.workload, "vertices": r["n"], "ordered_pairs_per_step": r["n"] * (r["n"] - 1)},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
                          "sample": r["sample"]},
+        "timed_calls": r["reps"],
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
