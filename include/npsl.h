@@ -101,10 +101,20 @@ typedef struct {
  * by walking INTERFACE on every call (src/newforces.cpp:140-143). */
 int npsl_create(const npsl_mesh_desc *mesh, const npsl_params *params, npsl_ctx **out);
 
-/* One rank of a row-sharded job (one process per GPU). Rows of the pair interaction and the
- * owned vertex range follow the reference's MPI decomposition (src/main.cpp:448-455) with the
- * per-rank range rounded up to the vertex tile. nccl_unique_id: NPSL_NCCL_ID_BYTES bytes
- * obtained from npsl_nccl_unique_id() on rank 0 and distributed by the caller. */
+/* One rank of a sharded job (one process per GPU). The units of the pair interaction are split over the ranks; under
+ * the "rows" plan the owned vertex range follows the reference's MPI decomposition (src/main.cpp:448-455) with the
+ * per-rank range rounded up to a warp of vertices, under the "replicated" plan every rank integrates every vertex
+ * (npsl_shard_plan). nccl_unique_id: NPSL_NCCL_ID_BYTES bytes obtained from npsl_nccl_unique_id() on rank 0 and
+ * distributed by the caller.
+ *
+ * COLLECTIVE CALLS. Like the reference's force_calculation / compute_energy, whose MPI collectives make every rank call
+ * them in lock-step (src/newforces.cpp:268-271, src/interface.cpp:1092-1094), every entry point that evaluates forces
+ * -- npsl_force_init, npsl_force, npsl_force_calculation, npsl_step, npsl_step_timing*, npsl_step_profile,
+ * npsl_energy, npsl_local_energies, npsl_md_run, npsl_md_step_host, npsl_md_step_packed, npsl_constraint_init -- and
+ * npsl_download_state / npsl_download_force_components (rows plan: they gather) must be issued by ALL ranks of the
+ * context, the same number of times and in the same order (do NOT guard them with rank == 0 the way the reference
+ * guards its file output). The kernels of a rank wait on flags written by its peers; a wait whose peer never arrives
+ * gives up after 30 s and the next npsl_sync / npsl_download_state / npsl_energy returns NPSL_ERR_STATE. */
 int npsl_create_sharded(const npsl_mesh_desc *mesh, const npsl_params *params, int rank, int world,
                         const void *nccl_unique_id, npsl_ctx **out);
 int npsl_nccl_unique_id(void *out_id);
@@ -181,6 +191,16 @@ int npsl_md_run(npsl_ctx *ctx, const double *pos, const double *vel, const doubl
  * previous call). The thermostat chains stay on the device (npsl_get/set_thermostat). */
 int npsl_md_step_host(npsl_ctx *ctx, double *pos, double *vel, double *force, int n_steps, double *kinetic_out);
 
+/* The same loop body over ONE page-locked block owned by the context, laid out [posvec n*3 | velvec n*3 | forvec n*3 |
+ * kinetic energy]: npsl_host_state hands out the four pointers into it (stable for the life of the context); the
+ * caller -- the adapter that flattens VERTEX::posvec / velvec / forvec (src/vertex.h:60-70) anyway -- keeps its state
+ * there. npsl_md_step_packed copies the block in with one transfer, advances n_steps and copies it back (for one step
+ * on a single-GPU or replicated-plan context the kernels read and write the packed image directly, the positions
+ * travel back beside the force evaluation and velocities + forces + kinetic energy in one transfer at the end);
+ * returns after the block holds the new state. Collective on sharded contexts like npsl_step. */
+int npsl_host_state(npsl_ctx *ctx, double **pos, double **vel, double **force, double **kinetic);
+int npsl_md_step_packed(npsl_ctx *ctx, int n_steps);
+
 /* Rigid volume constraint of md_interface with geomConstraint 'V', linear form (src/functions.h:33-171): SHAKE
  * after the drift (src/newmd.cpp:126), RATTLE after the second half-kick (:152), both inside npsl_step.
  * npsl_constraint_init is the SHAKE + RATTLE pass before the first step (src/newmd.cpp:33-38); call it after
@@ -230,6 +250,10 @@ int npsl_pair_timing_read(npsl_ctx *ctx, double *mean_ms, int64_t *launches);
  * context's own stream. flush_l2 != 0: a buffer larger than L2 is overwritten before every step,
  * outside that step's event bracket; the result is the sum of the per-step brackets. */
 int npsl_step_timing(npsl_ctx *ctx, int n_steps, int flush_l2, double *total_ms);
+/* Same measurement, one value per step: lead_in untimed steps (they absorb the skew between the ranks of a sharded job
+ * after a host-side barrier), then n_steps timed ones, all submitted to the stream in one go; per_step_ms[n_steps].
+ * Nothing is allocated inside the call once a call with the same flush_l2 and at least n_steps has been made. */
+int npsl_step_timing_list(npsl_ctx *ctx, int n_steps, int flush_l2, int lead_in, double *per_step_ms);
 /* Per-segment device time of a step (CUDA events between the launches of n_steps directly launched steps),
  * formatted as text into out. Measurement only. */
 int npsl_step_profile(npsl_ctx *ctx, int n_steps, char *out, int out_len);

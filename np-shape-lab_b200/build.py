@@ -17,7 +17,11 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libnpsl.so")
 SOURCES = ["npsl.cu"]
-DEPENDS = ["npsl.cu", "pair_kernel.cuh", "pair_sym_kernel.cuh", "mesh_kernels.cuh", "xchg.cuh", "exp2_table.inc", os.path.join(ROOT, "include", "npsl.h")]
+import glob
+
+# every source, header and table under csrc/ plus the public header: a stale library is never picked up silently
+DEPENDS = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+                 glob.glob(os.path.join(CSRC, "*.inc"))) + [os.path.join(ROOT, "include", "npsl.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -25,7 +25,7 @@ SYMBOLS = [
     "npsl_download_mesh_fields", "npsl_get_thermostat", "npsl_set_thermostat", "npsl_dressup", "npsl_force_init",
     "npsl_force", "npsl_step", "npsl_energy", "npsl_sync", "npsl_launch_count", "npsl_pair_timing",
     "npsl_pair_timing_read", "npsl_owned_rows", "npsl_pair_geometry", "npsl_fp64_peak", "npsl_md_run",
-    "npsl_step_timing", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_md_step_host", "npsl_set_pair_mode",
+    "npsl_step_timing", "npsl_step_timing_list", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_md_step_host", "npsl_host_state", "npsl_md_step_packed", "npsl_set_pair_mode",
     "npsl_pair_mode", "npsl_exchange_mode", "npsl_shard_plan", "npsl_vertex_geometry", "npsl_local_energies", "npsl_step_profile", "npsl_set_volume_constraint", "npsl_constraint_init",
     "npsl_constraint_multipliers", "npsl_set_ions", "npsl_download_ions", "npsl_plan_pair_units",
 ]
@@ -109,8 +109,11 @@ def load() -> C.CDLL:
     L.npsl_fp64_peak.argtypes = [dp, dp]
     L.npsl_md_run.argtypes = [vp, dp, dp, dp, C.c_int, C.POINTER(Energies), dp, dp]
     L.npsl_step_timing.argtypes = [vp, C.c_int, C.c_int, dp]
+    L.npsl_step_timing_list.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
     L.npsl_force_calculation.argtypes = [vp, dp, dp]
     L.npsl_md_step_host.argtypes = [vp, dp, dp, dp, C.c_int, dp]
+    L.npsl_host_state.argtypes = [vp] + [C.POINTER(dp)] * 4
+    L.npsl_md_step_packed.argtypes = [vp, C.c_int]
     L.npsl_set_pair_plan.argtypes = [vp, C.c_int, C.c_int]
     L.npsl_set_pair_mode.argtypes = [vp, C.c_int]
     L.npsl_pair_mode.argtypes = [vp]
@@ -334,6 +337,12 @@ class Context:
         self._ck(self.L.npsl_step_timing(self.h, int(n_steps), 1 if flush_l2 else 0, C.byref(ms)))
         return ms.value
 
+    def step_timing_list(self, n_steps: int, flush_l2: bool = True, lead_in: int = 1) -> np.ndarray:
+        """Device time (ms) of each of ``n_steps`` graph-launched steps after ``lead_in`` untimed ones."""
+        out = np.zeros(int(n_steps))
+        self._ck(self.L.npsl_step_timing_list(self.h, int(n_steps), 1 if flush_l2 else 0, int(lead_in), _dp(out)))
+        return out
+
     def force_calculation(self, pos, force_out: np.ndarray | None = None):
         """Host-buffer force_calculation: positions in, total forces out (npsl_force_calculation).
         ``pos`` / ``force_out`` must be C-contiguous float64 [n,3]; no copies are made here."""
@@ -353,6 +362,18 @@ class Context:
         ke = C.c_double()
         self._ck(self.L.npsl_md_step_host(self.h, _dp(pos), _dp(vel), _dp(force), int(n_steps), C.byref(ke)))
         return ke.value
+
+    def host_state(self):
+        """The context's page-locked state block as numpy views (npsl_host_state): pos, vel, force [n,3] and the
+        kinetic energy [1]. Valid until the context is closed."""
+        ptr = [C.POINTER(C.c_double)() for _ in range(4)]
+        self._ck(self.L.npsl_host_state(self.h, *[C.byref(p) for p in ptr]))
+        views = [np.ctypeslib.as_array(p, shape=(self.nv, 3)) for p in ptr[:3]]
+        return views[0], views[1], views[2], np.ctypeslib.as_array(ptr[3], shape=(1,))
+
+    def md_step_packed(self, n_steps: int = 1) -> None:
+        """Loop body of md_interface over the page-locked state block (npsl_md_step_packed)."""
+        self._ck(self.L.npsl_md_step_packed(self.h, int(n_steps)))
 
     def owned_rows(self):
         lo, hi = C.c_int32(), C.c_int32()

@@ -243,17 +243,33 @@ __global__ void k_thermo_prepare(Thermo *th_cur, Thermo *th_mid, double *scal, c
 // ------------------------------------------------------------------------------------------------
 // k_kick_drift: first half-kick and drift of the owned vertices, src/newmd.cpp:114-123. The reverse
 // half-chain of this step was already done by thermo_finish at the end of the previous force evaluation.
+// Packed host-state step (npsl_md_step_packed): pk_in = [pos | vel | force] as packed [n][3] doubles that were just
+// copied from the caller's pinned block; pk_out = [pos | vel | force | KE], the block that goes back. Null: the state
+// is resident in the records.
+struct Packed {
+    const double *in;
+    double *out;
+};
+
 __global__ void __launch_bounds__(kMeshThreads)
 k_kick_drift(double4 *__restrict__ xyzq, double4 *__restrict__ vel, const double4 *__restrict__ force,
              const double *__restrict__ scal, int *__restrict__ lj_hit, double4 *const *__restrict__ peer_xyzq,
-             const Xchg X, const MeshParams P) {
+             const Xchg X, const MeshParams P, const Packed K) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *lj_hit = 0;
     const int i = P.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P.row_hi) {
         const double ef = __ldcg(scal + SC_EXPFAC), kick = __ldcg(scal + SC_KICK), dt = P.dt;
-        double4 v = vel[i];
-        const double4 f = force[i];
-        double4 x = xyzq[i];
+        double4 v, f, x;
+        if (K.in) {  // (P.nv is the plane length of the packed block)
+            const double *px = K.in + 3 * (size_t) i, *pv = px + 3 * (size_t) P.nv, *pf = pv + 3 * (size_t) P.nv;
+            x = make_double4(px[0], px[1], px[2], xyzq[i].w);
+            v = make_double4(pv[0], pv[1], pv[2], 0.0);
+            f = make_double4(pf[0], pf[1], pf[2], 0.0);
+        } else {
+            v = vel[i];
+            f = force[i];
+            x = xyzq[i];
+        }
         v.x = fma(v.x, ef, f.x * kick);
         v.y = fma(v.y, ef, f.y * kick);
         v.z = fma(v.z, ef, f.z * kick);
@@ -265,6 +281,10 @@ k_kick_drift(double4 *__restrict__ xyzq, double4 *__restrict__ vel, const double
             for (int r = 0; r < X.world; r++) peer_xyzq[r][i] = x;
         } else {
             xyzq[i] = x;
+        }
+        if (K.out) {
+            double *po = K.out + 3 * (size_t) i;
+            po[0] = x.x; po[1] = x.y; po[2] = x.z;
         }
     }
     if (xchg_has(X, XK_POS)) xchg_signal(X, XK_POS, gridDim.x);
@@ -536,7 +556,8 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
          const ForceComponents C, double *__restrict__ partials /* [2][nblocks] */, unsigned int *__restrict__ ticket,
          double *__restrict__ scal, double *__restrict__ ke_warp /* [n_ke_warps] */, int n_ke_warps,
          Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur, double *const *__restrict__ peer_ke,
-         const Xchg X, const MeshParams P, const double4 *__restrict__ ion_mesh, const double *__restrict__ ion_mesh_lj) {
+         const Xchg X, const MeshParams P, const double4 *__restrict__ ion_mesh, const double *__restrict__ ion_mesh_lj,
+         const Packed K) {
     __shared__ double red[3 * 32];
     __shared__ bool s_last;
     __shared__ size_t s_fv_off;
@@ -602,6 +623,11 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
             v.y = fma(v.y, ef, f.y * kick);
             v.z = fma(v.z, ef, f.z * kick);
             vel[i] = v;
+            if (K.out) {  // packed host-state step: velvec and forvec go straight into the block that is copied back
+                double *pv = K.out + 3 * ((size_t) P.nv + i), *pf = pv + 3 * (size_t) P.nv;
+                pv[0] = v.x; pv[1] = v.y; pv[2] = v.z;
+                pf[0] = f.x; pf[1] = f.y; pf[2] = f.z;
+            }
         } else {
             C.pair[i] = make_double4(fp.x, fp.y, fp.z, 0.0);
             C.vertex_e[i] = make_double2(ue, ulj);  // mesh-mesh only: what the local energy maps use
@@ -611,8 +637,9 @@ k_vertex(const double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *_
         acc[0] = 0.5 * (v.x * v.x + v.y * v.y + v.z * v.z);
     }
     if (MODE == VMODE_STEP && P.constraint) return;  // RATTLE follows: k_rattle_apply finishes the step
-    vertex_tail<MODE == VMODE_FORCE, MODE == VMODE_STEP>(acc, partials, ticket, scal, ke_warp, n_ke_warps, th_mid, th_cur,
-                                                         peer_ke, X, P, red, &s_last);
+    const bool done = vertex_tail<MODE == VMODE_FORCE, MODE == VMODE_STEP>(acc, partials, ticket, scal, ke_warp, n_ke_warps,
+                                                                            th_mid, th_cur, peer_ke, X, P, red, &s_last);
+    if (MODE == VMODE_STEP && K.out && done && threadIdx.x == 0) K.out[9 * (size_t) P.nv] = red[0];  // kinetic energy
 }
 
 // Sharded runs: after the all-gather of every rank's warp partials, one block sums them in the
@@ -842,6 +869,29 @@ __global__ void k_gather3(const double4 *__restrict__ rec, double *__restrict__ 
     packed[3 * i] = v.x;
     packed[3 * i + 1] = v.y;
     packed[3 * i + 2] = v.z;
+}
+
+// packed block [pos | vel | force (| KE)] <-> records, one launch for the three arrays (npsl_md_step_packed)
+__global__ void k_unpack_state(double4 *__restrict__ xyzq, double4 *__restrict__ vel, double4 *__restrict__ force,
+                               const double *__restrict__ packed, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *px = packed + 3 * (size_t) i, *pv = px + 3 * (size_t) n, *pf = pv + 3 * (size_t) n;
+    xyzq[i] = make_double4(px[0], px[1], px[2], xyzq[i].w);
+    vel[i] = make_double4(pv[0], pv[1], pv[2], 0.0);
+    force[i] = make_double4(pf[0], pf[1], pf[2], 0.0);
+}
+__global__ void k_pack_state(const double4 *__restrict__ xyzq, const double4 *__restrict__ vel,
+                             const double4 *__restrict__ force, const double *__restrict__ scal, double *__restrict__ packed,
+                             int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) packed[9 * (size_t) n] = scal[SC_KE];
+    if (i >= n) return;
+    double *px = packed + 3 * (size_t) i, *pv = px + 3 * (size_t) n, *pf = pv + 3 * (size_t) n;
+    const double4 x = xyzq[i], v = vel[i], f = force[i];
+    px[0] = x.x; px[1] = x.y; px[2] = x.z;
+    pv[0] = v.x; pv[1] = v.y; pv[2] = v.z;
+    pf[0] = f.x; pf[1] = f.y; pf[2] = f.z;
 }
 
 }  // namespace npsl

@@ -124,6 +124,12 @@ struct npsl_ctx {
     cudaStream_t s_main = nullptr, s_side = nullptr, s_aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_lj_fork = nullptr, ev_lj_join = nullptr;
     cudaGraphExec_t step_graph = nullptr;
+    // packed host-state step (npsl_md_step_packed): pinned block [pos | vel | force | KE], its device images and a
+    // graph of its own (copy in -> the step, reading / writing the packed images -> copies out)
+    double *h_state = nullptr, *d_state_in = nullptr, *d_state_out = nullptr;
+    cudaGraphExec_t packed_graph = nullptr;
+    cudaStream_t s_copy = nullptr;
+    cudaEvent_t ev_copy_fork = nullptr, ev_copy_join = nullptr;
     ncclComm_t comm = nullptr;
 
     // measurement
@@ -174,6 +180,8 @@ struct npsl_ctx {
     unsigned long long *xflags = nullptr;         // [XK_KINDS][kMaxRanks], written by the peers
     unsigned long long *xstate = nullptr;         // epochs
     unsigned int *xtickets = nullptr;
+    int *x_timed_out = nullptr;                   // set by a wait that gave up (xchg.cuh)
+    int *lj_all = nullptr;                        // NCCL exchanges: every rank's collision flag
     void *peer_map[4][kMaxRanks] = {};            // host copies of the mapped peer pointers (xyzq, fv, ke, flags)
     double4 **d_peer_xyzq = nullptr;
     double **d_peer_fv = nullptr, **d_peer_ke = nullptr;
@@ -487,7 +495,8 @@ void launch_pair(npsl_ctx *c, bool energy, cudaStream_t s) {
 
 // Issues the kernels of one force evaluation (and, with step=true, of one whole MD step) on the
 // context's streams. Used both for direct execution and under stream capture.
-int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
+int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair, bool packed = false) {
+    const Packed pk = {packed ? c->d_state_in : nullptr, packed ? c->d_state_out : nullptr};
     const VertexTables vt = {c->degree, c->ring, c->ring_l0, c->bslot_ref};
     const ForceComponents fc = {c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->vertex_e};
     int n = 0;
@@ -506,8 +515,14 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
     mark("begin");
     if (step) {
         k_kick_drift<<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->force, c->scal, c->lj_hit,
-                                                                        c->d_peer_xyzq, c->xg, c->mp);
+                                                                        c->d_peer_xyzq, c->xg, c->mp, pk);
         n++;
+        if (packed) {  // the new positions are final: their copy to the host runs beside the force evaluation
+            CU(cudaEventRecord(c->ev_copy_fork, c->s_main));
+            CU(cudaStreamWaitEvent(c->s_copy, c->ev_copy_fork, 0));
+            CU(cudaMemcpyAsync(c->h_state, c->d_state_out, sizeof(double) * 3 * c->nv, cudaMemcpyDeviceToHost, c->s_copy));
+            CU(cudaEventRecord(c->ev_copy_join, c->s_copy));
+        }
         if (c->mp.n_ions > 0) {
             k_ion_kick_drift<<<(c->mp.n_ions + 127) / 128, 128, 0, c->s_main>>>(c->ion_xyzq, c->ion_vel, c->ion_force, c->scal, c->ip);
             n++;
@@ -598,10 +613,19 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
             if (e1) CU(cudaEventRecord(e1, c->s_main));
             mark("k_pair_sym");
             { int r = issue_mesh(); if (r < 0) return r; mesh_issued = true; }
+            if (!ordered && c->world > 1 && !c->p2p) {  // NCCL exchanges: every rank's collision flag, OR-ed (see k_lj_flag)
+                NC(g_nccl.AllGather(c->lj_hit, c->lj_all, sizeof(int), 1 /* ncclChar */, c->comm, c->s_main));
+                k_lj_or<<<1, 32, 0, c->s_main>>>(c->lj_all, c->world, c->lj_hit);
+                n++;
+            }
             if (!ordered) {  // the exact LJ pass only needs the collision detector: it runs beside k_pair_reduce
                 CU(cudaEventRecord(c->ev_lj_fork, c->s_main));
                 CU(cudaStreamWaitEvent(c->s_aux, c->ev_lj_fork, 0));
                 lj_stream = c->s_aux;
+                if (c->world > 1 && c->p2p) {  // the detector of k_pair_sym only saw this rank's units
+                    k_lj_flag<<<1, 32, 0, lj_stream>>>(c->xg, c->lj_hit);
+                    n++;
+                }
             }
             k_pair_reduce<<<c->red_n_a + c->red_n_b_ctas, dim3(32, 8), 0, c->s_main>>>(c->sym_rowpart, c->sym_colpart, c->sym_fv,
                                                                             c->red_groups, c->red_n_a, c->red_n_b_groups,
@@ -645,13 +669,13 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair) {
         k_vertex<VMODE_STEP><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(
             c->xyzq, c->vel, c->force, c->fmesh, c->pair_partial, c->sym_fv, c->lj_out, c->lj_hit, fc, c->part_vert,
             c->tickets + 1, c->scal, c->ke_warp, c->n_ke_warps, c->th_mid, c->th_cur, c->d_peer_ke, c->xg, c->mp,
-            c->ion_mesh, c->ion_mesh_lj);
+            c->ion_mesh, c->ion_mesh_lj, pk);
         n++;
     } else {
         k_vertex<VMODE_FORCE><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(
             c->xyzq, c->vel, c->force, c->fmesh, c->pair_partial, c->sym_fv, c->lj_out, c->lj_hit, fc, c->part_vert,
             c->tickets + 1, c->scal, c->ke_warp, c->n_ke_warps, c->th_mid, c->th_cur, c->d_peer_ke, c->xg, c->mp,
-            c->ion_mesh, c->ion_mesh_lj);
+            c->ion_mesh, c->ion_mesh_lj, Packed{nullptr, nullptr});
         n++;
     }
     mark("k_vertex");
@@ -712,6 +736,63 @@ int ensure_graph(npsl_ctx *c) {
     return 0;
 }
 
+// The packed host-state step is one graph: copy of the caller's block in, the step with k_kick_drift reading and
+// k_vertex writing the packed images, the positions copied out beside the force evaluation, velocities + forces +
+// kinetic energy copied out at the end. Single-GPU contexts and the replicated plan without constraint / ions (there
+// every rank integrates every vertex and the thermostat runs inside k_vertex); otherwise npsl_md_step_packed falls
+// back to unpack -> steps -> pack.
+bool packed_fused_ok(const npsl_ctx *c) {
+    return (c->world == 1 || c->replicated) && !c->mp.constraint && c->mp.n_ions == 0;
+}
+
+int ensure_packed_buffers(npsl_ctx *c) {
+    if (c->h_state) return 0;
+    const size_t n = (size_t) 9 * c->nv + 1;
+    CU(cudaMallocHost((void **) &c->h_state, sizeof(double) * n));
+    memset(c->h_state, 0, sizeof(double) * n);
+    CU(dalloc(&c->d_state_in, n));
+    CU(dalloc(&c->d_state_out, n));
+    CU(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_copy_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_copy_join, cudaEventDisableTiming));
+    return 0;
+}
+
+int ensure_packed_graph(npsl_ctx *c) {
+    if (c->packed_graph) return 0;
+    cudaGraph_t g = nullptr;
+    const size_t n3 = (size_t) 3 * c->nv;
+    CU(cudaStreamBeginCapture(c->s_main, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e0 = cudaMemcpyAsync(c->d_state_in, c->h_state, sizeof(double) * 3 * n3, cudaMemcpyHostToDevice, c->s_main);
+    int n = e0 == cudaSuccess ? issue(c, true, false, false, false, true) : -1;
+    if (n >= 0) {
+        cudaStreamWaitEvent(c->s_main, c->ev_copy_join, 0);
+        e0 = cudaMemcpyAsync(c->h_state + n3, c->d_state_out + n3, sizeof(double) * (2 * n3 + 1), cudaMemcpyDeviceToHost, c->s_main);
+    }
+    cudaError_t e = cudaStreamEndCapture(c->s_main, &g);
+    if (n < 0 || e0 != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        return n < 0 && e0 == cudaSuccess ? n : fail(c, NPSL_ERR_CUDA, "packed graph capture: %s", cudaGetErrorString(e0));
+    }
+    if (e != cudaSuccess) return fail(c, NPSL_ERR_CUDA, "packed graph capture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiateWithFlags(&c->packed_graph, g, cudaGraphInstantiateFlagUseNodePriority);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(c, NPSL_ERR_CUDA, "packed graph instantiate: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// A wait on a peer that gave up (xchg.cuh: every rank has to issue the same sequence of force evaluations)
+int xchg_status(npsl_ctx *c) {
+    if (!c->x_timed_out) return 0;
+    int v = 0;
+    CU(cudaMemcpy(&v, c->x_timed_out, sizeof(int), cudaMemcpyDeviceToHost));
+    if (v)
+        return fail(c, NPSL_ERR_STATE, "an exchange with a peer GPU timed out after %llu s: the ranks of a sharded context must "
+                    "issue the same sequence of force evaluations (npsl_step, npsl_force*, npsl_energy, ...); results are invalid",
+                    (unsigned long long) (kXchgTimeoutNs / 1000000000ull));
+    return 0;
+}
+
 int collect_timing(npsl_ctx *c) {
     if (!c->t_used) return 0;
     CU(cudaStreamSynchronize(c->s_main));
@@ -766,6 +847,10 @@ void drop_graph(npsl_ctx *c) {
         cudaGraphExecDestroy(c->step_graph);
         c->step_graph = nullptr;
     }
+    if (c->packed_graph) {
+        cudaGraphExecDestroy(c->packed_graph);
+        c->packed_graph = nullptr;
+    }
 }
 
 // Maps every rank's exchange buffers (positions, virtual-rank force sums, kinetic-energy partials, arrival
@@ -773,14 +858,16 @@ void drop_graph(npsl_ctx *c) {
 // the context on the NCCL exchanges.
 int setup_p2p(npsl_ctx *c) {
     c->xg.world = c->world; c->xg.rank = c->rank; c->xg.on = 0; c->xg.fv_bcast = 0; c->xg.cta_fence_sys = 0;
-    c->xg.peer_flags = nullptr; c->xg.state = nullptr; c->xg.tickets = nullptr;
+    c->xg.peer_flags = nullptr; c->xg.state = nullptr; c->xg.tickets = nullptr; c->xg.timed_out = nullptr;
     if (c->world == 1) return 0;
+    CU(dalloc(&c->lj_all, c->world));
     const char *env = getenv("NPSL_EXCHANGE");
     if (env && strcmp(env, "nccl") == 0) return 0;
     if (c->world > kMaxRanks || !c->sym_fv) return 0;
     CU(dalloc(&c->xflags, XK_KINDS * kMaxRanks));
     CU(dalloc(&c->xstate, 2 * XK_KINDS));
     CU(dalloc(&c->xtickets, XK_KINDS));
+    CU(dalloc(&c->x_timed_out, 1));
     struct Handles { cudaIpcMemHandle_t h[4]; int ok; int pad[15]; };
     Handles mine;
     memset(&mine, 0, sizeof mine);
@@ -827,8 +914,9 @@ int setup_p2p(npsl_ctx *c) {
     CU(cudaMemcpy(c->d_peer_ke, c->peer_map[2], sizeof(void *) * c->world, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_peer_flags, c->peer_map[3], sizeof(void *) * c->world, cudaMemcpyHostToDevice));
     c->xg.peer_flags = c->d_peer_flags; c->xg.state = c->xstate; c->xg.tickets = c->xtickets;
+    c->xg.timed_out = c->x_timed_out;
     c->p2p = true;
-    c->xg.on = (1 << XK_KINDS) - 1;
+    c->xg.on = (1 << XK_POS) | (1 << XK_FV) | (1 << XK_KE);
     return 0;
 }
 
@@ -858,7 +946,7 @@ int apply_shard_plan(npsl_ctx *c) {
     c->pp.row_lo = c->ljp.row_lo = c->mp.row_lo = c->row_lo;
     c->pp.row_hi = c->ljp.row_hi = c->mp.row_hi = c->row_hi;
     c->mp.n_ranks = c->replicated ? 1 : c->world;
-    c->xg.on = !c->p2p ? 0 : (c->replicated ? (1 << XK_FV) : (1 << XK_KINDS) - 1);
+    c->xg.on = !c->p2p ? 0 : (c->replicated ? (1 << XK_FV) : (1 << XK_POS) | (1 << XK_FV) | (1 << XK_KE));
     c->xg.fv_bcast = c->replicated ? 1 : 0;
     c->xg.cta_fence_sys = 0;
     if (const char *e = getenv("NPSL_CTA_FENCE_SYS")) c->xg.cta_fence_sys = atoi(e) ? 1 : 0;  // measurement knob
@@ -1070,6 +1158,13 @@ void npsl_destroy(npsl_ctx *c) {
     if (c->s_side) cudaStreamSynchronize(c->s_side);
     if (c->s_aux) cudaStreamSynchronize(c->s_aux);
     if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+    if (c->packed_graph) cudaGraphExecDestroy(c->packed_graph);
+    if (c->s_copy) { cudaStreamSynchronize(c->s_copy); cudaStreamDestroy(c->s_copy); }
+    if (c->ev_copy_fork) cudaEventDestroy(c->ev_copy_fork);
+    if (c->ev_copy_join) cudaEventDestroy(c->ev_copy_join);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->d_state_in) cudaFree(c->d_state_in);
+    if (c->d_state_out) cudaFree(c->d_state_out);
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
     for (auto &e : c->pinned_user) cudaHostUnregister(e.first);
     for (int k = 0; k < 4; k++)
@@ -1087,7 +1182,7 @@ void npsl_destroy(npsl_ctx *c) {
                     c->edge_rec, c->l0, c->degree, c->ring, c->bslot_ref, c->ring_l0, c->bslot, c->pair_partial,
                     c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_warp, c->th_cur, c->th_mid, c->part_mesh,
                     c->part_vert, c->tickets, c->ion_xyzq, c->ion_vel, c->ion_force, c->ion_mesh, c->ion_e, c->ion_mesh_lj, c->ion_part, c->edge_E, c->vertex_e, c->face_e, c->face_local, c->vertex_geo, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units, c->red_groups,
-                    c->sym_rowpart, c->sym_colpart, c->sym_fv, c->xflags, c->xstate, c->xtickets,
+                    c->sym_rowpart, c->sym_colpart, c->sym_fv, c->xflags, c->xstate, c->xtickets, c->x_timed_out, c->lj_all,
                     c->d_peer_xyzq, c->d_peer_fv, c->d_peer_ke, c->d_peer_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -1142,6 +1237,7 @@ int npsl_download_state(npsl_ctx *c, double *pos, double *vel, double *force) {
     if ((r = download_records(c, c->xyzq, pos, false, 0))) return r;
     if ((r = download_records(c, c->vel, vel, true, 1))) return r;
     if ((r = download_records(c, c->force, force, true, 0))) return r;
+    if ((r = xchg_status(c))) return r;
     return collect_timing(c);
 }
 
@@ -1312,6 +1408,7 @@ int npsl_energy(npsl_ctx *c, npsl_energies *out) {
         ipe += th.ions[j].dof * th.ions[j].T * th.ions[j].eta;
     }
     out->mesh_bath_ke = mk; out->mesh_bath_pe = mpe; out->ions_bath_ke = ik; out->ions_bath_pe = ipe;
+    if ((r = xchg_status(c))) return r;
     if (!std::isfinite(out->energy)) return fail(c, NPSL_ERR_NUMERIC, "non-finite energy");
     return NPSL_OK;
 }
@@ -1386,10 +1483,56 @@ int npsl_md_step_host(npsl_ctx *c, double *pos, double *vel, double *force, int 
     return NPSL_OK;
 }
 
+int npsl_host_state(npsl_ctx *c, double **pos, double **vel, double **force, double **kinetic) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    int r = ensure_packed_buffers(c);
+    if (r) return r;
+    const size_t n3 = (size_t) 3 * c->nv;
+    if (pos) *pos = c->h_state;
+    if (vel) *vel = c->h_state + n3;
+    if (force) *force = c->h_state + 2 * n3;
+    if (kinetic) *kinetic = c->h_state + 3 * n3;
+    return NPSL_OK;
+}
+
+int npsl_md_step_packed(npsl_ctx *c, int n_steps) {
+    if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
+    if (n_steps < 1) return fail(c, NPSL_ERR_ARG, "n_steps < 1");
+    int r = ensure_packed_buffers(c);
+    if (r) return r;
+    const size_t n3 = (size_t) 3 * c->nv;
+    c->forces_valid = true;  // the caller's forvec is the force at the caller's posvec (src/newmd.cpp:114-117)
+    c->local_valid = false;
+    if (n_steps == 1 && packed_fused_ok(c)) {
+        if ((r = ensure_packed_graph(c))) return r;
+        CU(cudaGraphLaunch(c->packed_graph, c->s_main));
+        c->launches += c->launches_per_step;
+        CU(cudaStreamSynchronize(c->s_main));
+        CU(cudaGetLastError());
+        return NPSL_OK;
+    }
+    // general form: one copy in, one unpacking kernel, the resident steps, one packing kernel, one copy out
+    if ((r = ensure_graph(c))) return r;
+    const int nb = (c->nv + 255) / 256;
+    CU(cudaMemcpyAsync(c->d_state_in, c->h_state, sizeof(double) * 3 * n3, cudaMemcpyHostToDevice, c->s_main));
+    k_unpack_state<<<nb, 256, 0, c->s_main>>>(c->xyzq, c->vel, c->force, c->d_state_in, c->nv);
+    for (int k = 0; k < n_steps; k++) CU(cudaGraphLaunch(c->step_graph, c->s_main));
+    if ((r = gather_records(c, c->vel))) return r;
+    if ((r = gather_records(c, c->force))) return r;
+    k_pack_state<<<nb, 256, 0, c->s_main>>>(c->xyzq, c->vel, c->force, c->scal, c->d_state_out, c->nv);
+    CU(cudaMemcpyAsync(c->h_state, c->d_state_out, sizeof(double) * (3 * n3 + 1), cudaMemcpyDeviceToHost, c->s_main));
+    c->launches += 2 + (int64_t) c->launches_per_step * n_steps;
+    CU(cudaStreamSynchronize(c->s_main));
+    CU(cudaGetLastError());
+    return NPSL_OK;
+}
+
 int npsl_sync(npsl_ctx *c) {
     if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
     CU(cudaStreamSynchronize(c->s_main));
     CU(cudaGetLastError());
+    int r = xchg_status(c);
+    if (r) return r;
     return collect_timing(c);
 }
 
@@ -1530,20 +1673,30 @@ int npsl_pair_timing_read(npsl_ctx *c, double *mean_ms, int64_t *launches) {
     return NPSL_OK;
 }
 
-int npsl_step_timing(npsl_ctx *c, int n_steps, int flush_l2, double *total_ms) {
-    if (!c || !total_ms) return fail(c, NPSL_ERR_ARG, "NULL argument");
-    if (n_steps < 1) return fail(c, NPSL_ERR_ARG, "n_steps < 1");
+// Shared by npsl_step_timing and npsl_step_timing_list: lead_in untimed steps, then n_steps timed ones, all submitted
+// to the stream in one go. Buffers and events are created before anything is enqueued, so that no allocation of this
+// rank can land inside a peer's bracket (a rank's step waits for every peer's exchange signal).
+static int step_timing_impl(npsl_ctx *c, int n_steps, int flush_l2, int lead_in, double *per_step_ms, double *total_ms) {
+    if (n_steps < 1 || lead_in < 0) return fail(c, NPSL_ERR_ARG, "n_steps < 1 or lead_in < 0");
     if (!c->forces_valid) return fail(c, NPSL_ERR_STATE, "npsl_step_timing before npsl_force_init");
     c->local_valid = false;
     int r = ensure_graph(c);
     if (r) return r;
-    if (c->s_ev.size() < 2) {
-        c->s_ev.resize(2);
-        for (auto &e : c->s_ev) CU(cudaEventCreate(&e));
+    const size_t need = flush_l2 ? (size_t) 2 * n_steps : 2;
+    while (c->s_ev.size() < need) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        c->s_ev.push_back(e);
     }
     if (flush_l2 && !c->flush_buf) {
         c->flush_bytes = (size_t) 256 << 20;  // 2x the 126 MB L2
         CU(cudaMalloc(&c->flush_buf, c->flush_bytes));
+        CU(cudaMemset(c->flush_buf, 0, c->flush_bytes));  // touched once here, never inside a timed call
+        CU(cudaDeviceSynchronize());
+    }
+    for (int k = 0; k < lead_in; k++) {
+        if (flush_l2) CU(cudaMemsetAsync(c->flush_buf, k & 0xff, c->flush_bytes, c->s_main));
+        CU(cudaGraphLaunch(c->step_graph, c->s_main));
     }
     double sum = 0;
     if (!flush_l2) {
@@ -1554,14 +1707,10 @@ int npsl_step_timing(npsl_ctx *c, int n_steps, int flush_l2, double *total_ms) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, c->s_ev[0], c->s_ev[1]));
         sum = ms;
+        if (per_step_ms)
+            for (int k = 0; k < n_steps; k++) per_step_ms[k] = ms / n_steps;
     } else {
         // per-step brackets; the flush sits between them
-        const size_t need = (size_t) 2 * n_steps;
-        while (c->s_ev.size() < need) {
-            cudaEvent_t e;
-            CU(cudaEventCreate(&e));
-            c->s_ev.push_back(e);
-        }
         for (int k = 0; k < n_steps; k++) {
             CU(cudaMemsetAsync(c->flush_buf, k & 0xff, c->flush_bytes, c->s_main));
             CU(cudaEventRecord(c->s_ev[2 * k], c->s_main));
@@ -1573,12 +1722,23 @@ int npsl_step_timing(npsl_ctx *c, int n_steps, int flush_l2, double *total_ms) {
             float ms = 0;
             CU(cudaEventElapsedTime(&ms, c->s_ev[2 * k], c->s_ev[2 * k + 1]));
             sum += ms;
+            if (per_step_ms) per_step_ms[k] = ms;
         }
     }
-    c->launches += (int64_t) c->launches_per_step * n_steps;
+    c->launches += (int64_t) c->launches_per_step * (n_steps + lead_in);
     CU(cudaGetLastError());
-    *total_ms = sum;
+    if (total_ms) *total_ms = sum;
     return NPSL_OK;
+}
+
+int npsl_step_timing(npsl_ctx *c, int n_steps, int flush_l2, double *total_ms) {
+    if (!c || !total_ms) return fail(c, NPSL_ERR_ARG, "NULL argument");
+    return step_timing_impl(c, n_steps, flush_l2, 0, nullptr, total_ms);
+}
+
+int npsl_step_timing_list(npsl_ctx *c, int n_steps, int flush_l2, int lead_in, double *per_step_ms) {
+    if (!c || !per_step_ms) return fail(c, NPSL_ERR_ARG, "NULL argument");
+    return step_timing_impl(c, n_steps, flush_l2, lead_in, per_step_ms, nullptr);
 }
 
 int npsl_step_profile(npsl_ctx *c, int n_steps, char *out, int out_len) {

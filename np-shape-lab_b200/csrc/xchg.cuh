@@ -24,7 +24,9 @@
 namespace npsl {
 
 constexpr int kMaxRanks = 8;
-enum { XK_POS = 0, XK_FV = 1, XK_KE = 2, XK_KINDS = 3 };
+// XK_LJ0 / XK_LJ1: the two parities of the collision-flag exchange (k_lj_flag); never part of Xchg::on
+enum { XK_POS = 0, XK_FV = 1, XK_KE = 2, XK_LJ0 = 3, XK_LJ1 = 4, XK_KINDS = 5 };
+constexpr unsigned long long kXchgTimeoutNs = 30ull * 1000000000ull;  // a wait that long means a peer is gone
 
 struct Xchg {
     int world, rank;
@@ -34,6 +36,7 @@ struct Xchg {
     unsigned long long *const *peer_flags;    // [world] -> each rank's flags[XK_KINDS][kMaxRanks]
     unsigned long long *state;                // local: [kind] producer epoch, [XK_KINDS + kind] consumer epoch
     unsigned int *tickets;                    // local: [kind]
+    int *timed_out;                           // local: set when a wait gave up (reported as NPSL_ERR_STATE by the host)
 };
 
 __device__ __forceinline__ bool xchg_has(const Xchg &X, const int kind) { return (X.on >> kind) & 1; }
@@ -74,14 +77,36 @@ __device__ __forceinline__ void xchg_signal(const Xchg &X, const int kind, const
     if (threadIdx.x == 0) xchg_signal_cta(X, kind, nblocks);
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spins (acquire loads) until *f >> shift has reached e. Every rank has to issue the same sequence of force
+// evaluations (include/npsl.h, "collective calls"); if a peer never arrives the wait gives up after kXchgTimeoutNs
+// and leaves a mark that the host turns into NPSL_ERR_STATE, instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long xchg_spin(const Xchg &X, const unsigned long long *f,
+                                                        const unsigned long long e, const int shift, const unsigned ns) {
+    unsigned long long v = ld_acquire_sys(f);
+    if ((v >> shift) >= e) return v;
+    const unsigned long long t0 = global_ns();
+    unsigned int it = 0;
+    while (((v = ld_acquire_sys(f)) >> shift) < e) {
+        __nanosleep(ns);
+        if ((++it & 1023u) == 0 && global_ns() - t0 > kXchgTimeoutNs) {
+            *X.timed_out = 1;
+            break;
+        }
+    }
+    return v;
+}
+
 // One warp: waits until every rank's signal of the next epoch of `kind` has arrived. Returns to all lanes.
 __device__ __forceinline__ void xchg_wait_warp(const Xchg &X, const int kind) {
     const int lane = threadIdx.x & 31;
     const unsigned long long e = X.state[XK_KINDS + kind] + 1;
-    if (lane < X.world) {
-        const unsigned long long *f = X.peer_flags[X.rank] + kind * kMaxRanks + lane;
-        while (ld_acquire_sys(f) < e) __nanosleep(64);
-    }
+    if (lane < X.world) xchg_spin(X, X.peer_flags[X.rank] + kind * kMaxRanks + lane, e, 0, 64);
     __syncwarp();
     if (lane == 0) X.state[XK_KINDS + kind] = e;
     __threadfence();
@@ -94,10 +119,7 @@ __device__ __forceinline__ void xchg_wait_warp(const Xchg &X, const int kind) {
 __device__ __forceinline__ unsigned long long xchg_wait_own_epoch(const Xchg &X, const int kind) {
     const int lane = threadIdx.x & 31;
     const unsigned long long e = X.state[kind];
-    if (lane < X.world) {
-        const unsigned long long *f = X.peer_flags[X.rank] + kind * kMaxRanks + lane;
-        while (ld_acquire_sys(f) < e) __nanosleep(32);
-    }
+    if (lane < X.world) xchg_spin(X, X.peer_flags[X.rank] + kind * kMaxRanks + lane, e, 0, 32);
     __syncwarp();
     __threadfence();
     return e;
@@ -105,6 +127,37 @@ __device__ __forceinline__ unsigned long long xchg_wait_own_epoch(const Xchg &X,
 
 __global__ void k_xchg_wait(const Xchg X, const int kind) {
     if (threadIdx.x < 32) xchg_wait_warp(X, kind);
+}
+
+// The WCA / LJ collision detector of the symmetric pair kernel is per rank (a rank only sees the pairs of its own
+// units), but the reference applies the WCA term on every rank's rows unconditionally (src/newforces.cpp:165-171), so
+// the exact pass k_lj and the gate in k_vertex must act on the OR over all ranks. One warp, right after k_pair_sym on
+// the stream of k_lj: lane r stores (epoch << 1 | my flag) into rank r's slot for this rank, then waits for rank r's
+// slot here; the OR replaces the local flag. The slots alternate with the parity of the epoch: a rank can be at most
+// one force evaluation ahead of the slowest one (it needs everybody's pair-force sums to finish a step).
+__global__ void k_lj_flag(const Xchg X, int *__restrict__ lj_hit) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long e = X.state[XK_LJ0] + 1;
+    const int kind = XK_LJ0 + (int) (e & 1ull);
+    const unsigned long long mine = (e << 1) | (unsigned long long) (*(volatile int *) lj_hit != 0);
+    int hit = 0;
+    if (lane < X.world) {
+        st_release_sys(X.peer_flags[lane] + kind * kMaxRanks + X.rank, mine);
+        hit = (int) (xchg_spin(X, X.peer_flags[X.rank] + kind * kMaxRanks + lane, e, 1, 64) & 1ull);
+    }
+    hit = __any_sync(0xffffffffu, hit);
+    if (lane == 0) {
+        *lj_hit = hit ? 1 : 0;
+        X.state[XK_LJ0] = e;
+    }
+}
+
+// NCCL exchanges: the flags of all ranks were all-gathered into all[world]
+__global__ void k_lj_or(const int *__restrict__ all, int world, int *__restrict__ lj_hit) {
+    int hit = 0;
+    for (int r = threadIdx.x; r < world; r += 32) hit |= all[r];
+    hit = __any_sync(0xffffffffu, hit != 0);
+    if (threadIdx.x == 0) *lj_hit = hit ? 1 : 0;
 }
 
 }  // namespace npsl

@@ -48,6 +48,9 @@ CONFIGS = {
     "janus_D8": ("ref:3_8", 8, JANUS, [0, 1], [250, 500, 750, 1000]),
     "buckling_D8": ("ref:3_8", 8, BUCKLING_CTRL, [0, 1], [500, 1000]),
     "disc_ico6": ("ico:6", 6, DISC, [0, 1], []),  # synthetic class-I icosphere, 362 vertices
+    # BASELINE.json configs[3], the configuration bench.py times: class-I icosphere D=64, 40 962 vertices, every field at
+    # steps 0 and 1 (whole reference steps: ~25 s per force_calculation on 8 threads). -d 2e-4: see workloads.py.
+    "S64_disc": ("ico:64", 64, DISC + ["-d", "0.0002"], [0, 1], []),
     # rigid volume constraint (SHAKE / RATTLE, src/functions.h:33-171); the cubic comes from oracle/shim/gsl/gsl_poly.h
     "disc_D4_GV": ("ref:3_4", 4, DISC + ["-G", "V"], [0, 1, 2], [250, 500, 1000]),
     "janus_D8_GV": ("ref:3_8", 8, JANUS + ["-G", "V"], [0, 1], [500, 1000]),
@@ -80,13 +83,21 @@ def build(name: str, threads: int | None) -> None:
             first = d
             assert np.array_equal(d["edges"], mesh.edges), "edge order differs from file order"
             assert np.array_equal(d["faces"], mesh.faces), "face winding differs from loader"
-            out["pos0"] = mesh.pos
-            out["edges"] = d["edges"]
-            out["faces"] = d["faces"]
-            out["l0"] = d["l0"]
+            if src.startswith("ico:") and mesh.n_vertices > 10000:
+                # large synthetic meshes: the fixture keeps the generator's name instead of 3 MB of topology
+                out["mesh_source"] = np.array(src)
+                out["l0"] = d["l0"]
+                assert np.array_equal(d["pos"], mesh.pos) or k != 0, "positions differ from the generator's"
+            else:
+                out["pos0"] = mesh.pos
+                out["edges"] = d["edges"]
+                out["faces"] = d["faces"]
+                out["l0"] = d["l0"]
             out["q"] = d["q"]
             out["params"] = d["params"]
         for key in FULL_KEYS:
+            if "mesh_source" in out and k == 0 and key in ("pos", "vel"):
+                continue  # = the generator's positions (checked above) and zero
             out["k%d_%s" % (k, key)] = d[key]
         out["k%d_scalars" % k] = d["scalars"]
         out["k%d_mesh_bath" % k] = d["mesh_bath"]
@@ -226,6 +237,77 @@ def writers() -> None:
     shutil.rmtree(wd, ignore_errors=True)
 
 
+WINDOW_CASES = {
+    # BASELINE.json configs[4]: class-I icosphere D=128, 163 842 vertices, rod recipe. A whole reference step is ~7 min on
+    # 8 threads, so the pair force is pinned on three windows of 512 rows through the reference's own row bounds
+    # (src/main.cpp:448-455, src/newforces.cpp:153-177) and the mesh terms in full; "perturbed" repeats it away from
+    # the symmetric sphere (every coordinate moved by up to 2e-4, about 2 % of an edge), mesh terms on the window rows.
+    "S128_rod": ("S128_rod", [(0, 511), (81664, 82175), (163330, 163841)], 2e-4),
+    "S64_disc_perturbed": ("S64_disc", [(0, 511), (20224, 20735), (40450, 40961)], 4e-4),
+}
+
+
+WINDOW_PARAMS = ["scalefactor", "em", "inv_kappa_out", "elj", "lj_length_mesh_mesh", "bkappa", "sconstant", "sigma_a",
+                 "sigma_v", "ref_area", "ref_volume", "avg_edge_length"]
+
+
+def lcg_displacements(n: int, amp: float) -> np.ndarray:
+    """The displacement --perturb applies (oracle/ref_driver.cpp, mode window): amp * (2u - 1) per coordinate, u the top
+    53 bits of a fixed 64-bit LCG."""
+    st = 0x9E3779B97F4A7C15
+    out = np.empty(3 * n)
+    mask = (1 << 64) - 1
+    for k in range(3 * n):
+        st = (st * 6364136223846793005 + 1442695040888963407) & mask
+        out[k] = amp * (2.0 * ((st >> 11) * (1.0 / 9007199254740992.0)) - 1.0)
+    return out.reshape(n, 3)
+
+
+def windows(name: str, threads: int | None) -> None:
+    """tests/golden/<name>_windows.npz from ``npsl_ref --mode window`` (the reference's own force_calculation per row
+    window)."""
+    from np_shape_lab_b200 import workloads as W
+    wl, wins, amp = WINDOW_CASES[name]
+    w = W.build(wl)
+    n = w.n_vertices
+    scratch = os.path.join("/tmp", "npsl_golden")
+    os.makedirs(scratch, exist_ok=True)
+    mesh_file = os.path.join(scratch, "ico_%d.dat" % w.D)
+    M.write_dat(mesh_file, w.mesh)
+    wd = refdump.make_workdir(mesh_file, w.D, root=scratch)
+    out = {"workload": np.array(wl), "windows": np.array(wins, dtype=np.int64), "perturb": np.array(amp)}
+    for tag, a in (("k0", 0.0), ("pert", amp)):
+        od = os.path.join(wd, "out_" + tag)
+        os.makedirs(od)
+        js = refdump.last_json_line(refdump.run_ref(
+            wd, ["--mode", "window", "--out", od, "--windows", ",".join("%d:%d" % t for t in wins), "--perturb", a] +
+            W.reference_flags(w), threads=threads))
+        rd = lambda k, shape=None: np.fromfile(os.path.join(od, k + ".f64")).reshape(shape or -1)
+        rows = rd("rows").astype(np.int64)
+        pos = rd("pos", (n, 3))
+        expect = w.mesh.pos if a == 0 else w.mesh.pos + lcg_displacements(n, a)
+        assert np.array_equal(pos, expect), "positions differ from the host's"
+        # the host's set-up (np_shape_lab_b200/mesh.py) agrees with the reference's to rounding; the fixture keeps the
+        # reference's own charges and derived parameters so that both sides of the comparison see identical inputs
+        assert np.max(np.abs(rd("q") - w.q)) <= 1e-14 * np.max(np.abs(w.q)), "charges differ from the host's assignment"
+        for k in WINDOW_PARAMS:
+            assert abs(js[k] - w.params[k]) <= 1e-13 * abs(js[k]), (k, js[k], w.params[k])
+        if a == 0:
+            out["q"] = rd("q")
+            out["params"] = np.array([js[k] for k in WINDOW_PARAMS])
+            out["param_names"] = np.array(WINDOW_PARAMS)
+        out[tag + "_rows"] = rows
+        out[tag + "_pforce"] = rd("pforce", (len(rows), 3))
+        for k in ("bforce", "sforce", "tforce", "vforce"):
+            full = rd(k, (n, 3))
+            out[tag + "_" + k] = full if a == 0 else full[rows]
+        out[tag + "_total_area"] = np.array(js["total_area"])
+        out[tag + "_total_volume"] = np.array(js["total_volume"])
+        print(name, tag, "rows", len(rows), "force_s", js["force_s"], "A=%.12g V=%.12g" % (js["total_area"], js["total_volume"]), flush=True)
+    np.savez_compressed(os.path.join(GOLD, name + "_windows.npz"), **out)
+    shutil.rmtree(wd, ignore_errors=True)
+
+
 CHARGE_CASES = dict(
     [("N%d" % n, ["-N", str(n), "-p", "0.5"]) for n in range(3, 18)] +
     [("N2_Hy", ["-N", "2", "-p", "0.5", "-H", "y"]), ("N1_Hc", ["-N", "1", "-H", "c"]),
@@ -279,6 +361,9 @@ def main() -> None:
         if a.only and a.only != name:
             continue
         build(name, a.threads)
+    for name in WINDOW_CASES:
+        if a.only in (None, name + "_windows"):
+            windows(name, a.threads)
 
 
 if __name__ == "__main__":

@@ -26,6 +26,12 @@
 //   --mode force : time --reps calls of force_calculation restricted to mesh rows
 //                  [--row-lo, --row-hi] (the reference's own MPI row slice, src/main.cpp:448-455),
 //                  print JSON. Used as CPU baseline for the synthetic large meshes.
+//   --mode window: pins the large synthetic meshes (S64 / S128), where whole reference steps are too slow: optional
+//                  deterministic displacement of every vertex (--perturb amp, fixed LCG), dressup, then ONE call of the
+//                  reference's force_calculation per row window of --windows lo:hi,lo:hi,... (inclusive bounds, the
+//                  reference's own lowerBoundMesh / upperBoundMesh, src/main.cpp:448-455, src/newforces.cpp:153-177).
+//                  Writes raw float64 arrays into the directory --out: pos, q, the pair force of the window rows, and
+//                  the mesh terms (bforce, sforce, TForce, VolTForce), EDGE::itsS, face areas / volumes in full.
 //
 // Run from a working directory that holds infiles/3_<D>.dat and an (empty) outfiles/ directory.
 #include "utility.h"
@@ -79,6 +85,9 @@ struct Options {
     double alpha = 1.0;        // fractional charge occupancy (hard-wired to 1 in src/main.cpp:213)
     std::string E = "None";    // external charge pattern, infiles/Charge_Patterns/<E>.dat (src/main.cpp:244-247)
     int local = 0;  // 1: also dump vertex areas / normals and the per-face local energy maps
+    std::string windows;       // --mode window: "lo:hi,lo:hi,..." inclusive row bounds
+    double perturb = 0;        // --mode window: amplitude of the deterministic displacement (0: none)
+    int anneal_freq = 50000, anneal_duration = 5000;  // CONTROL::annealfreq / annealDuration (src/main.cpp:150-153)
 };
 
 bool parse(int argc, char **argv, Options &o) {
@@ -122,6 +131,10 @@ bool parse(int argc, char **argv, Options &o) {
         else if (a == "--alpha") o.alpha = atof(need("--alpha"));
         else if (a == "--ions") o.ions = atoi(need("--ions"));
         else if (a == "-E") o.E = need("-E");
+        else if (a == "--windows") o.windows = need("--windows");
+        else if (a == "--perturb") o.perturb = atof(need("--perturb"));
+        else if (a == "--anneal-freq") o.anneal_freq = atoi(need("--anneal-freq"));
+        else if (a == "--anneal-duration") o.anneal_duration = atoi(need("--anneal-duration"));
         else {
             std::fprintf(stderr, "unknown option %s\n", a.c_str());
             return false;
@@ -175,8 +188,8 @@ int main(int argc, char **argv) {
     mdremote.steps = o.steps;
     mdremote.timestep = o.dt;
     mdremote.anneal = 'y';
-    mdremote.annealfreq = 50000;
-    mdremote.annealDuration = 5000;
+    mdremote.annealfreq = o.anneal_freq;
+    mdremote.annealDuration = o.anneal_duration;
     mdremote.TAnnealFac = 1.25;
     mdremote.moviestart = 1;
     mdremote.offfreq = 2500;
@@ -280,6 +293,79 @@ int main(int argc, char **argv) {
         std::printf("{\"mode\": \"force\", \"vertices\": %zu, \"rows\": %ld, \"pairs_per_call\": %.0f, \"reps\": %d, "
                     "\"best_s\": %.6f, \"mean_s\": %.6f, \"threads\": %d, \"fx0\": %.17Lg}\n",
                     N, hi - lo + 1, pairs, o.reps, best, total / o.reps, threads, boundary.V[lo].forvec.x);
+        return 0;
+    }
+
+    if (o.mode == "window") {
+        initialize_velocities_to_zero(boundary.V, counterions);
+        if (o.perturb > 0) {  // every coordinate moves by perturb * (2u - 1), u from a fixed 64-bit LCG (top 53 bits)
+            unsigned long long st = 0x9E3779B97F4A7C15ULL;
+            for (size_t i = 0; i < N; i++) {
+                double d[3];
+                for (int k = 0; k < 3; k++) {
+                    st = st * 6364136223846793005ULL + 1442695040888963407ULL;
+                    d[k] = o.perturb * (2.0 * ((double) (st >> 11) * (1.0 / 9007199254740992.0)) - 1.0);
+                }
+                // added in double, so that the displaced coordinates are exactly representable on the device side too
+                const double nx = (double) boundary.V[i].posvec.x + d[0], ny = (double) boundary.V[i].posvec.y + d[1],
+                             nz = (double) boundary.V[i].posvec.z + d[2];
+                boundary.V[i].posvec = VECTOR3D(nx, ny, nz);
+            }
+        }
+        boundary.dressup(lambda_a, lambda_v);  // src/newmd.cpp:130, before force_calculation
+        auto put = [&](const std::string &name, const std::vector<double> &v) {
+            FILE *g = std::fopen((o.out + "/" + name + ".f64").c_str(), "wb");
+            if (!g) { std::perror("open output"); std::exit(1); }
+            std::fwrite(v.data(), sizeof(double), v.size(), g);
+            std::fclose(g);
+        };
+        auto vec3 = [&](std::vector<double> &v, VECTOR3D a) {
+            v.push_back((double) a.x); v.push_back((double) a.y); v.push_back((double) a.z);
+        };
+        std::vector<double> rows, pfo;
+        std::string w = o.windows;
+        double t_force = 0;
+        while (!w.empty()) {
+            size_t comma = w.find(',');
+            std::string one = w.substr(0, comma);
+            w = comma == std::string::npos ? "" : w.substr(comma + 1);
+            long lo = atol(one.c_str()), hi = atol(one.substr(one.find(':') + 1).c_str());
+            if (hi > (long) N - 1) hi = (long) N - 1;
+            lowerBoundMesh = (unsigned) lo;
+            upperBoundMesh = (unsigned) hi;
+            sizFVecMesh = (unsigned) (hi - lo + 1);
+            double t0 = now_s();
+            force_calculation(boundary, counterions, scalefactor, o.B);
+            t_force += now_s() - t0;
+            for (long i = lo; i <= hi; i++) {
+                VERTEX &V = boundary.V[i];
+                rows.push_back((double) i);
+                vec3(pfo, V.forvec - V.bforce - V.sforce - V.TForce - V.VolTForce);
+            }
+        }
+        std::vector<double> pos, q, bfo, sfo, tfo, vfo, itsS, farea, fvol;
+        for (size_t i = 0; i < N; i++) {
+            VERTEX &V = boundary.V[i];
+            vec3(pos, V.posvec); q.push_back(V.q);
+            vec3(bfo, V.bforce); vec3(sfo, V.sforce); vec3(tfo, V.TForce); vec3(vfo, V.VolTForce);
+        }
+        for (size_t i = 0; i < boundary.E.size(); i++) itsS.push_back(boundary.E[i].itsS);
+        for (size_t i = 0; i < boundary.F.size(); i++) {
+            farea.push_back(boundary.F[i].itsarea);
+            fvol.push_back(boundary.F[i].subtends_volume);
+        }
+        put("rows", rows); put("pforce", pfo); put("pos", pos); put("q", q);
+        put("bforce", bfo); put("sforce", sfo); put("tforce", tfo); put("vforce", vfo);
+        put("itsS", itsS); put("face_area", farea); put("face_volume", fvol);
+        std::printf("{\"mode\": \"window\", \"vertices\": %zu, \"edges\": %zu, \"faces\": %zu, \"rows\": %zu, "
+                    "\"force_s\": %.3f, \"scalefactor\": %.17g, \"em\": %.17g, \"inv_kappa_out\": %.17g, \"elj\": %.17g, "
+                    "\"lj_length_mesh_mesh\": %.17g, \"bkappa\": %.17g, \"sconstant\": %.17g, \"sigma_a\": %.17g, "
+                    "\"sigma_v\": %.17g, \"ref_area\": %.17g, \"ref_volume\": %.17g, \"avg_edge_length\": %.17g, "
+                    "\"total_area\": %.17g, \"total_volume\": %.17g}\n",
+                    N, boundary.E.size(), boundary.F.size(), rows.size(), t_force, scalefactor, boundary.em,
+                    boundary.inv_kappa_out, boundary.elj, boundary.lj_length_mesh_mesh, boundary.bkappa, boundary.sconstant,
+                    boundary.sigma_a, boundary.sigma_v, boundary.ref_area, boundary.ref_volume, boundary.avg_edge_length,
+                    boundary.total_area, boundary.total_volume);
         return 0;
     }
 

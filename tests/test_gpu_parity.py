@@ -7,7 +7,7 @@ component to 1e-10 relative at steps 0/1, A/U/E trajectories to 1e-6 relative ov
 import numpy as np
 import pytest
 
-from conftest import golden, make_oracle, relerr
+from conftest import golden, make_oracle, relerr, vertex_relerr
 from np_shape_lab_b200 import capi
 from np_shape_lab_b200 import mesh as M
 
@@ -34,6 +34,7 @@ def check_against_fixture(ctx, g, k):
     fscale = float(np.max(np.abs(fref)))
     st = ctx.download_state()
     assert relerr(st["force"], fref) < TOL, (g.name, k, "force")
+    assert vertex_relerr(st["force"], fref) < TOL, (g.name, k, "force, per vertex")
     assert relerr(st["pos"], g["k%d_pos" % k]) < 1e-13
     assert relerr(st["vel"], g["k%d_vel" % k], floor=1e-9) < TOL
     e = ctx.energy()  # also refreshes the per-term force components and mesh fields
@@ -47,6 +48,8 @@ def check_against_fixture(ctx, g, k):
         # 1e-3 of it.
         floor = fscale if ck == "volume_tension" else 1e-3 * fscale
         assert relerr(comp[ck], g["k%d_%s" % (k, gk)], floor=floor) < TOL, (g.name, k, ck)
+        if ck == "pair" and np.any(g["q"] != 0):
+            assert vertex_relerr(comp[ck], g["k%d_%s" % (k, gk)]) < TOL, (g.name, k, "pair force, per vertex")
     mf = ctx.download_mesh_fields()
     assert relerr(mf["edge_S"], g["k%d_itsS" % k]) < TOL
     assert relerr(mf["face_area"], g["k%d_face_area" % k]) < TOL

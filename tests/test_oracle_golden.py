@@ -187,3 +187,67 @@ def test_oracle_counterions_match_reference():
         assert abs(e["energy"] - s["energy"]) < 1e-9 * abs(s["energy"])
         assert abs(o.ions_ke() - float(g["k%d_netIonKE" % k])) <= 1e-8 * float(g["k%d_netIonKE" % k])
     assert relerr(o.ions("pos"), g["k%d_ion_pos" % g.traj_steps[-1]]) < 1e-8
+
+
+# ---- the large synthetic meshes (BASELINE.json configs[3], configs[4]) ------------------------------------------
+def _window_case(name):
+    import os
+    from conftest import GOLD
+    from np_shape_lab_b200 import workloads as W
+    z = np.load(os.path.join(GOLD, name + "_windows.npz"))
+    w = W.build(str(z["workload"]))
+    prm = dict(w.params)
+    prm.update(zip([str(k) for k in z["param_names"]], [float(v) for v in z["params"]]))
+    return z, w, prm
+
+
+def _lcg(n, amp):
+    st, mask = 0x9E3779B97F4A7C15, (1 << 64) - 1
+    out = np.empty(3 * n)
+    for k in range(3 * n):
+        st = (st * 6364136223846793005 + 1442695040888963407) & mask
+        out[k] = amp * (2.0 * ((st >> 11) * (1.0 / 9007199254740992.0)) - 1.0)
+    return out.reshape(n, 3)
+
+
+@pytest.mark.parametrize("name", ["S64_disc_perturbed", "S128_rod"])
+def test_restatement_matches_reference_row_windows_on_large_meshes(name):
+    """The C restatement against the compiled reference's force_calculation on the bench meshes: pair force on 32 rows
+    of each of the three windows (the fixture holds 512 per window; the CUDA path is checked on all of them), mesh
+    terms on the window rows, in the displaced state."""
+    from oracle import oracle as O
+    z, w, prm = _window_case(name)
+    n = w.n_vertices
+    pos = w.mesh.pos + _lcg(n, float(z["perturb"]))
+    o = O.Oracle(w.mesh.edges, w.mesh.faces, w.params["l0"], {**prm, "T": w.params["T"], "dt": w.params["dt"], "buckling": 0})
+    o.set_state(pos, np.zeros_like(pos), z["q"])
+    o.dressup()
+    rows = z["pert_rows"]
+    pscale = float(np.max(np.abs(z["pert_pforce"])))
+    for lo, hi in z["windows"]:
+        lo, hi = int(lo), int(lo) + 31
+        o.force(lo, hi)
+        sel = np.where((rows >= lo) & (rows <= hi))[0]
+        assert relerr(o.vec("pforce")[lo:hi + 1], z["pert_pforce"][sel]) < 1e-12
+    for ok, gk in (("bforce", "bforce"), ("sforce", "sforce"), ("tforce", "tforce"), ("vforce", "vforce")):
+        assert relerr(o.vec(ok)[rows], z["pert_" + gk], floor=1e-3 * pscale) < 1e-11, gk
+
+
+def test_restatement_matches_reference_on_s64_disc_step_1():
+    """S64_disc (the bench configuration) after one whole reference step: mesh terms, EDGE::itsS, face fields in full,
+    pair force on three windows of 32 rows."""
+    from conftest import golden
+    from oracle import oracle as O
+    g = golden("S64_disc")
+    o = O.Oracle(g["edges"], g["faces"], g["l0"], g.params)
+    o.set_state(g["k1_pos"], g["k1_vel"], g["q"])
+    o.dressup()
+    n = g.nv()
+    fscale = float(np.max(np.abs(g["k1_force"])))
+    for lo in (0, n // 2, n - 32):
+        o.force(lo, lo + 31)
+        assert relerr(o.vec("pforce")[lo:lo + 32], g["k1_pforce"][lo:lo + 32]) < 1e-12
+    for k in ("bforce", "sforce", "tforce"):
+        assert relerr(o.vec(k), g["k1_" + k], floor=1e-3 * fscale) < 1e-11, k
+    assert relerr(o.vec("vforce"), g["k1_vforce"], floor=fscale) < 1e-11
+    assert relerr(o.edge_S(), g["k1_itsS"]) < 1e-12
