@@ -160,6 +160,7 @@ def reference_sample(workload_name: str, budget_s: float, threads: int, reps: in
     return {
         "value": 1.0 / t_step, "pairs_per_s": n * (n - 1) / t_step, "t_step_s": t_step, "t_sample_s": t_sample,
         "t_fixed_s": t_fixed, "rows": rows, "reps": reps, "asked_reps": asked, "threads": res["threads"], "n": n,
+        "config": common_config(w),
         "sample": "reference force_calculation (unmodified src/newforces.cpp via oracle/_ref) on rows [0,%d) of %d "
                   "x all %d columns, %d timed call(s), mesh terms in full; extrapolated to a full step as "
                   "t_fixed + (t_sample - t_fixed) * N/rows with t_fixed = %.3f s from a 1-row slice; 1 process x %d "
@@ -167,6 +168,13 @@ def reference_sample(workload_name: str, budget_s: float, threads: int, reps: in
                       rows, n, n, reps, t_fixed, res["threads"],
                       "" if reps == asked else "; %d steps were asked for, the %.0f s budget fits %d calls" % (asked, budget_s, reps)),
     }
+
+
+def common_config(w) -> dict:
+    """The `config` object: identical on the b200 arm and on the reference arm (the driver compares them)."""
+    n = w.n_vertices
+    return {"workload": w.name, "vertices": n, "edges": w.mesh.n_edges, "faces": w.mesh.n_faces,
+            "ordered_pairs_per_step": n * (n - 1), "dt": w.inp.dt, "reference_cli": w.cli}
 
 
 def host_threads() -> int:
@@ -190,7 +198,7 @@ def run_reference(args) -> None:
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["t_step_s"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64 (x87 80-bit vectors in the reference)",
         "data": "synthetic", "pair_interactions_per_s": r["pairs_per_s"],
-        "config": {"workload": args.workload, "vertices": r["n"], "ordered_pairs_per_step": r["n"] * (r["n"] - 1)},
+        "config": r["config"],
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
                          "sample": r["sample"]},
         "timed_calls": r["reps"],
@@ -249,8 +257,14 @@ def run_b200(args) -> None:
     launches0 = ctx.launch_count()
 
     # ---- device-resident steps: W warm-up, then K timed (one CUDA-graph launch per step)
-    ctx.step(max(args.warmup, 3))
+    warm = max(args.warmup, 3)
+    ctx.step(warm)
+    # a short untimed pass through the timing entry point: allocates and touches the L2-flush buffer and the events,
+    # so that nothing is allocated inside the timed call (in a sharded job a rank's allocation would otherwise land in
+    # its peers' brackets: every step waits for every rank's exchange signal)
+    ctx.step_timing_list(min(args.steps, 3), flush_l2=True, lead_in=0)
     ctx.sync()
+    extra_untimed = min(args.steps, 3) + 1
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -258,12 +272,18 @@ def run_b200(args) -> None:
     barrier()
     l_before = ctx.launch_count()
     t0 = time.perf_counter()
-    dev_ms = ctx.step_timing(args.steps, flush_l2=True)
+    # one untimed lead-in step absorbs the skew the host-side barrier leaves between the ranks, then EXACTLY K timed
+    # steps, each in its own CUDA-event bracket on the context's stream, the L2 flush between the brackets
+    per_step = ctx.step_timing_list(args.steps, flush_l2=True, lead_in=1)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     gpu_launches = ctx.launch_count() - l_before
-    dev_ms = max_over_ranks(dev_ms)
+    dev_ms = max_over_ranks(float(per_step.sum()))
     wall_ms = max_over_ranks(wall_ms)
+    if world > 1:  # per step: the slowest rank
+        tt = torch.tensor(per_step, dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        per_step = tt.cpu().numpy()
     clocks = sampler.stop() if rank == 0 else {}
     ms_per_step = dev_ms / args.steps
     steps_per_s = 1e3 / ms_per_step
@@ -281,19 +301,21 @@ def run_b200(args) -> None:
 
     profile_txt = ctx.step_profile(20)  # per-segment device time of directly launched steps (CUDA events between launches)
 
-    # ---- end to end through the host-buffer entry point: state lives in host memory between steps
-    pos = np.ascontiguousarray(ctx.download_state()["pos"])
+    # ---- end to end through the host-state entry point: the state lives in host memory between steps (the reference
+    # keeps VERTEX::posvec / velvec / forvec there); every step copies the page-locked block in and back out
     st = ctx.download_state()
-    pos, vel, frc = [np.ascontiguousarray(st[k]) for k in ("pos", "vel", "force")]
+    hp, hv, hf, hk = ctx.host_state()
+    hp[:], hv[:], hf[:] = st["pos"], st["vel"], st["force"]
     for _ in range(3):
-        ctx.md_step_host(pos, vel, frc, 1)
+        ctx.md_step_packed(1)
     n_e2e = max(5, min(args.steps, 200))
     barrier()
     t0 = time.perf_counter()
     for _ in range(n_e2e):
-        ke = ctx.md_step_host(pos, vel, frc, 1)
+        ctx.md_step_packed(1)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    ke = float(hk[0])
     e2e_steps_per_s = n_e2e / e2e_s
     bytes_dir = 3 * 3 * 8 * n  # pos, vel, force [n][3] doubles each way (+ 8 B of KE down)
 
@@ -334,6 +356,43 @@ def run_b200(args) -> None:
                                 "bytes": what})
 
     ctx.close()
+
+    # ---- secondary block: BASELINE.json configs[4] (S128 rod, 163 842 vertices, "strong scaling at 1/2/4/8 GPUs"), a few
+    # steps with the same timing discipline, so that every --gpus N line carries a driver-measured point of that curve
+    secondary = None
+    if args.secondary and args.secondary != args.workload:
+        w2 = W.build(args.secondary)
+        n2 = w2.n_vertices
+        P2 = capi.make_params(w2.params, w2.mesh_bath, w2.ions_bath)
+        id2 = None
+        if world > 1:
+            box = [capi.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            id2 = box[0]
+        with capi.Context(w2.mesh.edges, w2.mesh.faces, w2.params["l0"], P2, n_vertices=n2, rank=rank, world=world,
+                          nccl_id=id2) as c2:
+            c2.upload_state(np.ascontiguousarray(w2.mesh.pos), np.zeros_like(w2.mesh.pos), w2.q)
+            c2.force_init()
+            c2.step(3)
+            c2.step_timing_list(2, flush_l2=True, lead_in=0)
+            c2.sync()
+            barrier()
+            k2 = max(3, min(args.steps, 10))
+            per2 = c2.step_timing_list(k2, flush_l2=True, lead_in=1)
+            barrier()
+            ms2 = max_over_ranks(float(per2.sum())) / k2
+            c2.pair_timing(True)
+            c2.step(3)
+            pair2, _ = c2.pair_timing_read()
+            c2.pair_timing(False)
+            pair2 = max_over_ranks(pair2)
+            en2 = c2.energy()
+            plan2 = c2.shard_plan()
+        secondary = {"metric": METRIC, "value": 1e3 / ms2, "unit": UNIT, "n_gpus": world, "steps": k2, "ms_per_step": ms2,
+                     "pair_interactions_per_s": 1e3 / ms2 * n2 * (n2 - 1), "pair_kernel_ms": pair2,
+                     "config": common_config(w2), "shard_plan": {0: "single GPU", 1: "rows", 2: "replicated integrator"}[plan2],
+                     "finite": bool(np.isfinite(en2["energy"])), "scaling": "strong"}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -343,29 +402,35 @@ def run_b200(args) -> None:
     cons = lambda e: e["energy"] + e["mesh_bath_ke"] + e["mesh_bath_pe"] + e["ions_bath_ke"] + e["ions_bath_pe"]
     line = {
         "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "pair_interactions_per_s": steps_per_s * n * (n - 1),
-        "config": {
-            "workload": args.workload, "vertices": n, "edges": w.mesh.n_edges, "faces": w.mesh.n_faces,
-            "ordered_pairs_per_step": n * (n - 1), "reference_cli": w.cli,
+        "config": common_config(w),
+        "setup": {
             "sharding": {0: "single GPU",
                          1: "rows: units of the pair term (8 virtual ranks) and owned vertices split over %d GPUs; positions, "
                             "pair-force sums and kinetic-energy partials exchanged each step" % world,
                          2: "replicated integrator: units of the pair term (8 virtual ranks) split over %d GPUs, every GPU "
                             "integrates all vertices; one exchange (pair-force sums) per step" % world}[ctx_shard_plan],
             "l2": "flushed between timed steps (256 MiB memset outside each step's CUDA-event bracket); "
-                  "ms_per_step = sum of the per-step brackets / K, max over ranks",
+                  "ms_per_step = sum of the K per-step brackets / K, max over ranks; one untimed lead-in step after the "
+                  "barrier; %d further untimed steps (timing path warm-up) beside the W warm-up steps" % extra_untimed,
             "pair_plan": geo, "pair_kernel": {1: "ordered (k_pair)", 2: "symmetric (k_pair_sym)"}[ctx_pair_mode],
             "exchange": {0: "none (single GPU)", 1: "NCCL all-gathers", 2: "direct stores into peer memory over NVLink "
                          "(CUDA IPC) with epoch flags"}[ctx_xchg_mode],
         },
         "wall_ms_per_step_incl_flush": wall_ms / args.steps,
+        "per_step_ms": {"median": float(np.median(per_step)), "max": float(np.max(per_step)), "min": float(np.min(per_step)),
+                        "list": [round(float(x), 5) for x in per_step[:200]],
+                        "note": "each step's bracket, max over ranks; value uses the plain sum of all K"},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "e2e": {"value": e2e_steps_per_s, "unit": UNIT, "h2d_bytes_per_step": bytes_dir,
                 "d2h_bytes_per_step": bytes_dir + 8, "steps": n_e2e,
-                "call": "npsl_md_step_host: posvec/velvec/forvec host->device, one step, device->host, wall clock"},
+                "ms_per_step": 1e3 * e2e_s / n_e2e,
+                "call": "npsl_md_step_packed(ctx, 1) per step on the page-locked block of npsl_host_state: posvec | velvec | "
+                        "forvec host->device in one copy, one step, positions back beside the force evaluation, velvec | "
+                        "forvec | KE back in one copy at the end; wall clock over the calls, max over ranks"},
         "roofline": {
             "bound": "fp64", "achieved": 2e-12 * achieved_dfma, "peak": 2e-12 * dfma_peak, "unit": "TFLOP/s",
             "frac": achieved_dfma / dfma_peak if dfma_peak else None, "traffic": traffic,
@@ -386,8 +451,12 @@ def run_b200(args) -> None:
                                 "kernels are latency-bound at this size (DESIGN.md section 3 has the ncu durations and the "
                                 "bandwidth-bound k_pair_reduce)"},
         "checks": {"conserved_energy_drift": cons(e1) / cons(e0) - 1.0, "finite": bool(np.isfinite(cons(e1))),
-                   "kinetic_after_e2e": ke},
+                   "kinetic_after_e2e": ke,
+                   # the device-timed step can only be faster than the same step with host copies around it
+                   "timing_inconsistent": bool(ms_per_step > 1.02e3 * e2e_s / n_e2e)},
     }
+    if secondary is not None:
+        line["secondary"] = secondary
     if world == 1 and not args.no_cpu_baseline:
         try:
             r = reference_sample(args.workload, args.cpu_budget, host_threads(), reps=1, warm=0)
@@ -411,6 +480,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="S64_disc")
+    ap.add_argument("--secondary", default="S128_rod", help="second workload measured with a few steps ('' = none)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="also print a per-segment device-time breakdown of a step to stderr")

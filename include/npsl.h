@@ -204,10 +204,23 @@ int npsl_md_step_packed(npsl_ctx *ctx, int n_steps);
 /* Rigid volume constraint of md_interface with geomConstraint 'V', linear form (src/functions.h:33-171): SHAKE
  * after the drift (src/newmd.cpp:126), RATTLE after the second half-kick (:152), both inside npsl_step.
  * npsl_constraint_init is the SHAKE + RATTLE pass before the first step (src/newmd.cpp:33-38); call it after
- * npsl_force_init. Single-GPU contexts only. The multipliers of the last pass are available for diagnostics. */
+ * npsl_force_init. Available on single-GPU and on sharded contexts (under the rows plan VERTEX::neg_GradVi and the
+ * velocities are all-gathered for the face sums, which every rank then evaluates in the same order). The multipliers of
+ * the last pass are available for diagnostics. */
 int npsl_set_volume_constraint(npsl_ctx *ctx, int on);
 int npsl_constraint_init(npsl_ctx *ctx);
 int npsl_constraint_multipliers(npsl_ctx *ctx, double *shake_lambda, double *rattle_mu);
+
+/* ---- the pair kernel's radial-factor table ----------------------------------------------------------------
+ * k_pair_sym evaluates G(s) = e^{-r/lambda} (1/r^3 + 1/(lambda r^2)), s = r^2 -- the scalar the reference multiplies r_vec
+ * with (src/newforces.cpp:173-174) -- from a piecewise degree-5 polynomial in s built at context creation for the
+ * context's Debye length (csrc/pair_sym_kernel.cuh). npsl_pair_poly_eval rebuilds that table on the host for
+ * inv_kappa_out and returns, for each s[i] in [2^-21, 2^5), the value the device's Horner evaluation gives and the
+ * extended-precision value of G: the accuracy of the table can be checked without a GPU. Either output may be NULL.
+ * npsl_pair_math: how the context's symmetric pair kernel evaluates G -- 0 rsqrt / exp to 3e-16, 1 the table, 2 the
+ * reduced-accuracy exact scheme (csrc/pair_sym_kernel.cuh; environment NPSL_SYM_MATH overrides the default). */
+int npsl_pair_poly_eval(double inv_kappa_out, const double *s, double *table_value, double *exact_value, int n);
+int npsl_pair_math(const npsl_ctx *ctx);
 
 /* ---- introspection (measurement only) --------------------------------------------------- */
 
@@ -220,8 +233,9 @@ int64_t npsl_launch_count(const npsl_ctx *ctx);
  * (src/main.cpp:271-272). From then on every force evaluation adds the mesh-ion and ion-ion terms
  * (src/newforces.cpp:44-65,179-250), npsl_energy their energies (src/interface.cpp:1059-1089) and the ions' kinetic
  * energy, and npsl_step integrates the ions with their own Nose-Hoover chain (the caller sets ions_bath[0].dof = 3 n
- * like src/main.cpp:283). n = 0 removes the ions. Call before npsl_force_init. Single-GPU contexts and the replicated
- * sharding plan only. */
+ * like src/main.cpp:283). n = 0 removes the ions. Call before npsl_force_init. On sharded contexts every rank is given
+ * the same ions and evaluates the (small) mesh-ion / ion-ion terms and the ion integrator redundantly, in identical
+ * order, while the reference splits the ion loops by rank too (src/newforces.cpp:203-250, src/main.cpp:456-465). */
 int npsl_set_ions(npsl_ctx *ctx, int n_ions, const double *pos, const double *vel, const double *q, double diameter,
                   double lj_length_mesh_ions);
 /* PARTICLE::posvec / velvec / forvec of the counterions <- device; any pointer may be NULL. */

@@ -782,7 +782,8 @@ template <bool INIT>
 __global__ void __launch_bounds__(kMeshThreads)
 k_rattle_apply(double4 *__restrict__ vel, const double4 *__restrict__ ngv, double *__restrict__ partials,
                unsigned int *__restrict__ ticket, double *__restrict__ scal, double *__restrict__ ke_warp, int n_ke_warps,
-               Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur, const Xchg X, const MeshParams P) {
+               Thermo *__restrict__ th_mid, Thermo *__restrict__ th_cur, double *const *__restrict__ peer_ke, const Xchg X,
+               const MeshParams P) {
     __shared__ double red[3 * 32];
     __shared__ bool s_last;
     const int i = P.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
@@ -795,7 +796,7 @@ k_rattle_apply(double4 *__restrict__ vel, const double4 *__restrict__ ngv, doubl
         vel[i] = v;
         acc[0] = 0.5 * (v.x * v.x + v.y * v.y + v.z * v.z);
     }
-    vertex_tail<false, !INIT>(acc, partials, ticket, scal, ke_warp, n_ke_warps, th_mid, th_cur, nullptr, X, P, red, &s_last);
+    vertex_tail<false, !INIT>(acc, partials, ticket, scal, ke_warp, n_ke_warps, th_mid, th_cur, peer_ke, X, P, red, &s_last);
 }
 
 // ------------------------------------------------------------------------------------------------

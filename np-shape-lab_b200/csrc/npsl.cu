@@ -151,7 +151,7 @@ struct npsl_ctx {
     int plan_rows = 0, plan_splits = 0;  // overrides of npsl_set_pair_plan (0 = automatic)
     // symmetric (Newton's-third-law) pair path, pair_sym_kernel.cuh
     int pair_mode = 0;       // 0 automatic, 1 ordered (k_pair), 2 symmetric (k_pair_sym)
-    int sym_rows = 4, sym_threads = 128, sym_minb = 0;  // k_pair_sym variant: rows per thread, threads per CTA
+    int sym_rows = 6, sym_threads = 64, sym_minb = 0;  // k_pair_sym variant: rows per thread, threads per CTA
     bool use_sym = false;
     SymParams sp;
     int2 *sym_units = nullptr;   // this rank's units, heaviest first
@@ -159,6 +159,10 @@ struct npsl_ctx {
     int sym_n_units = 0, sym_n_units_total = 0, sym_v_first = 0, sym_v_count = kSymV;
     int *red_groups = nullptr;  // k_pair_reduce: vertex groups of the CTAs (rows + columns first, then columns only)
     int red_n_a = 0, red_n_b_groups = 0, red_n_b_ctas = 0;
+    double2 *pair_ptab = nullptr;  // piecewise-polynomial table of the radial factor (pair_sym_kernel.cuh), device copy
+    int sym_math = SYM_FAST;       // how k_pair_sym evaluates the radial factor (pair_sym_kernel.cuh); NPSL_SYM_MATH
+    bool sym_shape_set = false;    // rows / threads chosen through npsl_set_pair_plan
+    int sym_unroll = 1;            // pair evaluations in flight per thread = 4 x this; NPSL_SYM_UNROLL
     unsigned long long *sym_trace = nullptr;  // NPSL_SYM_TRACE
     std::vector<int2> sym_trace_units;
     int n_sm = 148;
@@ -396,6 +400,64 @@ void sym_geometry(int nv, int rb, SymParams &sp) {
     sp.n_chunks = sp.n_coarse + (rest + sp.fine_tiles - 1) / sp.fine_tiles;
 }
 
+// Radial factor of the screened-Coulomb force, G(s) = e^{-r/lambda} (1/r^3 + 1/(lambda r^2)), r = sqrt(s), in
+// extended precision (what src/newforces.cpp:173-174 multiplies r_vec with, up to the charge prefactor).
+long double radial_factor(long double s, long double lambda) {
+    const long double r = sqrtl(s);
+    return expl(-r / lambda) * (1.0L / (r * r * r) + 1.0L / (lambda * r * r));
+}
+
+// Table of pair_sym_kernel.cuh: per interval [lo, lo + w) of s (kPolyBits mantissa bits), the degree-5 polynomial in
+// t = s - (lo + w/2) that interpolates G at the six Chebyshev nodes of the interval; coefficients c0..c5 as doubles.
+// Everything is evaluated in long double (the fit is a 6-term Chebyshev series converted to monomials in t / (w/2)).
+void build_pair_table(double lambda, std::vector<double> &tab) {
+    constexpr int N = 6;
+    tab.assign((size_t) kPolyCount * N, 0.0);
+    const long double pi = 3.14159265358979323846264338327950288L;
+    // Chebyshev -> monomial: T0 = 1, T1 = x, T2 = 2x^2-1, T3 = 4x^3-3x, T4 = 8x^4-8x^2+1, T5 = 16x^5-20x^3+5x
+    static const long double T[N][N] = {{1, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 0}, {-1, 0, 2, 0, 0, 0},
+                                        {0, -3, 0, 4, 0, 0}, {1, 0, -8, 0, 8, 0}, {0, 5, 0, -20, 0, 16}};
+    for (int k = 0; k < kPolyCount; k++) {
+        const int oct = k >> kPolyBits, j = k & ((1 << kPolyBits) - 1);
+        const long double w = ldexpl(1.0L, kPolyEmin + oct - kPolyBits);
+        const long double mid = ldexpl(1.0L + (long double) j / (1 << kPolyBits), kPolyEmin + oct) + 0.5L * w;
+        const long double h = 0.5L * w;
+        long double f[N], a[N];
+        for (int m = 0; m < N; m++) f[m] = radial_factor(mid + h * cosl(pi * (m + 0.5L) / N), lambda);
+        for (int n = 0; n < N; n++) {
+            long double sum = 0;
+            for (int m = 0; m < N; m++) sum += f[m] * cosl(pi * n * (m + 0.5L) / N);
+            a[n] = sum * (n == 0 ? 1.0L : 2.0L) / N;
+        }
+        long double hp = 1.0L;
+        for (int p = 0; p < N; p++) {  // coefficient of t^p
+            long double b = 0;
+            for (int n = 0; n < N; n++) b += a[n] * T[n][p];
+            tab[(size_t) k * N + p] = (double) (b / hp);
+            hp *= h;
+        }
+    }
+}
+
+// The polynomial of the table at s, with the device's operations (interval from the high word, Horner in FP64);
+// used by npsl_pair_poly_eval so that the accuracy of the table can be checked without a GPU.
+double eval_pair_table(const std::vector<double> &tab, double s) {
+    int64_t bits;
+    memcpy(&bits, &s, 8);
+    const int hi = (int) (bits >> 32);
+    const int k = std::min(std::max((hi >> kPolyShift) - kPolyBase, 0), kPolyCount - 1);
+    const int64_t mid_bits = (int64_t) ((hi & (int) (0xffffffffu << kPolyShift)) | (1 << (kPolyShift - 1))) << 32;
+    double mid;
+    memcpy(&mid, &mid_bits, 8);
+    const double t = s - mid;
+    const double *c = &tab[(size_t) k * 6];
+    double g = fma(c[5], t, c[4]);
+    g = fma(g, t, c[3]);
+    g = fma(g, t, c[2]);
+    g = fma(g, t, c[1]);
+    return fma(g, t, c[0]);
+}
+
 struct SymUnit { int I, cc, work; };
 
 // Units (row block, column chunk) of the virtual ranks [v_first, v_first + v_count), heaviest first; returns the
@@ -423,8 +485,18 @@ int sym_units_of(const SymParams &sp, int v_first, int v_count, std::vector<SymU
 int plan_sym(npsl_ctx *c) {
     const int nv = c->nv;
     SymParams &sp = c->sp;
+    if (const char *e = getenv("NPSL_SYM_MATH")) c->sym_math = std::max(0, std::min(2, atoi(e)));
+    if (const char *e = getenv("NPSL_SYM_UNROLL")) c->sym_unroll = atoi(e) == 2 ? 2 : 1;
+    if (!c->sym_shape_set && (c->sym_math != SYM_FAST || c->sym_unroll != 1)) { c->sym_rows = 4; c->sym_threads = 128; }
     sym_geometry(nv, c->sym_rows * c->sym_threads, sp);
     sp.c2s = c->pp.c2s; sp.inv_lambda = c->pp.inv_lambda; sp.lj_cut_hi = c->pp.lj_cut_hi;
+    if (!c->pair_ptab) {
+        std::vector<double> tab;
+        build_pair_table(c->prm.inv_kappa_out, tab);
+        CU(dalloc(&c->pair_ptab, tab.size() / 2));
+        CU(cudaMemcpy(c->pair_ptab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+    }
+    sp.ptab = c->pair_ptab;
     const int n_rb = (nv + sp.rb - 1) / sp.rb;
     const bool want = c->pair_mode == 2 || (c->pair_mode == 0 && nv >= 4096);
     c->use_sym = want && (kSymV % c->world == 0);
@@ -493,6 +565,8 @@ void launch_pair(npsl_ctx *c, bool energy, cudaStream_t s) {
         k_pair<ROWS, false><<<grid, kPairThreads, 0, s>>>(c->xyzq, c->pair_partial, c->lj_hit, c->pp);
 }
 
+int gather_records(npsl_ctx *c, double4 *buf);
+
 // Issues the kernels of one force evaluation (and, with step=true, of one whole MD step) on the
 // context's streams. Used both for direct execution and under stream capture.
 int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair, bool packed = false) {
@@ -537,6 +611,9 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair, bool 
         }
         if (c->world > 1 && !c->replicated) mark("exchange positions");
         if (c->mp.constraint) {  // SHAKE, src/newmd.cpp:126
+            // rows plan: the face sums run over all faces on every rank (identical order, identical multiplier) and
+            // need VERTEX::neg_GradVi of every vertex; each rank computed its own slice in the last force evaluation
+            { int r = gather_records(c, c->ngv); if (r) return r; }
             k_constraint_sums<0><<<c->n_face_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv, c->face_v,
                                                                                   c->part_con, c->tickets + 2, c->scal, c->mp);
             k_shake_apply<<<(c->nv + kMeshThreads - 1) / kMeshThreads, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv,
@@ -596,19 +673,47 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair, bool 
         }
         const bool ordered = !c->use_sym || energy;  // the energy sum always comes from the ordered kernel
         if (c->use_sym) {
-#define SYM(R, T, B)                                                                                              \
-    k_pair_sym<R, T, B><<<c->sym_n_units, T, 0, c->s_main>>>(c->xyzq, c->sym_units, c->sym_rowpart, c->sym_colpart, \
-                                                             c->lj_hit, c->sp)
-            switch (c->sym_rows * 1000 + c->sym_threads) {
-                case 4128: if (c->sym_minb >= 8) SYM(4, 128, 4); else SYM(4, 128, 3); break;
-                case 2256: SYM(2, 256, 3); break;
-                case 2128: if (c->sym_minb >= 8) SYM(2, 128, 8); else SYM(2, 128, 6); break;
-                case 1512: SYM(1, 512, 2); break;
-                case 1256: SYM(1, 256, 4); break;
-                case 1128: SYM(1, 128, 8); break;
-                default: return fail(c, NPSL_ERR_ARG, "no k_pair_sym variant for %d rows x %d threads", c->sym_rows, c->sym_threads);
+#define SYM_LAUNCH(R, T, B, MATH, U, SMEM)                                                                           \
+    do {                                                                                                            \
+        if (SMEM > 0) CU(cudaFuncSetAttribute(k_pair_sym<R, T, B, MATH, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); \
+        k_pair_sym<R, T, B, MATH, U><<<c->sym_n_units, T, SMEM, c->s_main>>>(c->xyzq, c->sym_units, c->sym_rowpart,  \
+                                                                             c->sym_colpart, c->lj_hit, c->sp);     \
+    } while (0)
+            // (math, unroll, rows per thread, threads per CTA, tighter register cap) -> instantiation. The default is
+            // SYM_FAST with 6 rows x 64 threads (4 CTAs of 2 warps per SM); the others are kept for A/B measurements
+            // (NPSL_SYM_MATH, NPSL_SYM_UNROLL, npsl_set_pair_plan) and as the full-accuracy reference.
+            constexpr int kPolySmem = kPolyCount * 48;
+            const int key = ((c->sym_math * 10 + c->sym_unroll) * 10 + c->sym_rows) * 10000 + c->sym_threads * 10 + (c->sym_minb >= 8 ? 1 : 0);
+#define KEY(M, U, R, T, TIGHT) ((((M) * 10 + (U)) * 10 + (R)) * 10000 + (T) * 10 + (TIGHT))
+            switch (key) {
+                case KEY(SYM_FAST, 1, 6, 64, 0): SYM_LAUNCH(6, 64, 4, SYM_FAST, 1, 0); break;
+                case KEY(SYM_FAST, 1, 6, 128, 0): SYM_LAUNCH(6, 128, 2, SYM_FAST, 1, 0); break;
+                case KEY(SYM_FAST, 1, 6, 256, 0): SYM_LAUNCH(6, 256, 1, SYM_FAST, 1, 0); break;
+                case KEY(SYM_FAST, 1, 4, 128, 0): SYM_LAUNCH(4, 128, 3, SYM_FAST, 1, 0); break;
+                case KEY(SYM_FAST, 1, 4, 128, 1): SYM_LAUNCH(4, 128, 4, SYM_FAST, 1, 0); break;
+                case KEY(SYM_FAST, 1, 4, 64, 0): SYM_LAUNCH(4, 64, 6, SYM_FAST, 1, 0); break;
+                case KEY(SYM_FAST, 1, 5, 128, 0): SYM_LAUNCH(5, 128, 3, SYM_FAST, 1, 0); break;
+                case KEY(SYM_FAST, 1, 7, 128, 0): SYM_LAUNCH(7, 128, 2, SYM_FAST, 1, 0); break;
+                case KEY(SYM_FAST, 1, 8, 128, 0): SYM_LAUNCH(8, 128, 2, SYM_FAST, 1, 0); break;
+                case KEY(SYM_FAST, 2, 4, 128, 0): SYM_LAUNCH(4, 128, 2, SYM_FAST, 2, 0); break;
+                case KEY(SYM_POLY, 1, 4, 128, 0): SYM_LAUNCH(4, 128, 3, SYM_POLY, 1, kPolySmem); break;
+                case KEY(SYM_EXACT, 1, 4, 128, 0): SYM_LAUNCH(4, 128, 3, SYM_EXACT, 1, 0); break;
+                case KEY(SYM_EXACT, 1, 4, 128, 1): SYM_LAUNCH(4, 128, 4, SYM_EXACT, 1, 0); break;
+                case KEY(SYM_EXACT, 2, 4, 128, 0): SYM_LAUNCH(4, 128, 2, SYM_EXACT, 2, 0); break;
+                case KEY(SYM_EXACT, 1, 6, 128, 0): SYM_LAUNCH(6, 128, 2, SYM_EXACT, 1, 0); break;
+                case KEY(SYM_EXACT, 1, 6, 64, 0): SYM_LAUNCH(6, 64, 4, SYM_EXACT, 1, 0); break;
+                case KEY(SYM_EXACT, 1, 2, 256, 0): SYM_LAUNCH(2, 256, 3, SYM_EXACT, 1, 0); break;
+                case KEY(SYM_EXACT, 1, 2, 128, 0): SYM_LAUNCH(2, 128, 6, SYM_EXACT, 1, 0); break;
+                case KEY(SYM_EXACT, 1, 2, 128, 1): SYM_LAUNCH(2, 128, 8, SYM_EXACT, 1, 0); break;
+                case KEY(SYM_EXACT, 1, 1, 512, 0): SYM_LAUNCH(1, 512, 2, SYM_EXACT, 1, 0); break;
+                case KEY(SYM_EXACT, 1, 1, 256, 0): SYM_LAUNCH(1, 256, 4, SYM_EXACT, 1, 0); break;
+                case KEY(SYM_EXACT, 1, 1, 128, 0): SYM_LAUNCH(1, 128, 8, SYM_EXACT, 1, 0); break;
+                default:
+                    return fail(c, NPSL_ERR_ARG, "no k_pair_sym instantiation for math %d, unroll %d, %d rows x %d threads%s",
+                                c->sym_math, c->sym_unroll, c->sym_rows, c->sym_threads, c->sym_minb >= 8 ? " (tight)" : "");
             }
-#undef SYM
+#undef KEY
+#undef SYM_LAUNCH
             n++;
             if (e1) CU(cudaEventRecord(e1, c->s_main));
             mark("k_pair_sym");
@@ -680,11 +785,12 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair, bool 
     }
     mark("k_vertex");
     if (step && c->mp.constraint) {  // RATTLE, src/newmd.cpp:152, then the kinetic energy and the thermostat
+        { int r = gather_records(c, c->vel); if (r) return r; }  // rows plan: d/dt of the volume needs every velocity
         k_constraint_sums<1><<<c->n_face_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv, c->face_v,
                                                                               c->part_con, c->tickets + 2, c->scal, c->mp);
         k_rattle_apply<false><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(c->vel, c->ngv, c->part_vert, c->tickets + 1,
                                                                                   c->scal, c->ke_warp, c->n_ke_warps,
-                                                                                  c->th_mid, c->th_cur, c->xg, c->mp);
+                                                                                  c->th_mid, c->th_cur, c->d_peer_ke, c->xg, c->mp);
         n += 2;
         mark("RATTLE");
     }
@@ -933,8 +1039,6 @@ int apply_shard_plan(npsl_ctx *c) {
     const bool can = c->world > 1 && c->p2p && c->use_sym && !c->all_q_zero;
     const bool want = c->shard_pref == 2 || (c->shard_pref == 0 && c->nv <= kReplicateUpTo);
     c->replicated = can && want;
-    if (c->mp.constraint && c->world > 1 && !c->replicated)
-        return fail(c, NPSL_ERR_ARG, "the rigid volume constraint needs a single-GPU context or the replicated sharding plan");
     if (c->replicated) {
         c->row_lo = 0;
         c->row_hi = c->nv;
@@ -1181,7 +1285,7 @@ void npsl_destroy(npsl_ctx *c) {
     void *ptrs[] = {c->xyzq, c->vel, c->force, c->fmesh, c->ngv, c->part_con, c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->face_v,
                     c->edge_rec, c->l0, c->degree, c->ring, c->bslot_ref, c->ring_l0, c->bslot, c->pair_partial,
                     c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_warp, c->th_cur, c->th_mid, c->part_mesh,
-                    c->part_vert, c->tickets, c->ion_xyzq, c->ion_vel, c->ion_force, c->ion_mesh, c->ion_e, c->ion_mesh_lj, c->ion_part, c->edge_E, c->vertex_e, c->face_e, c->face_local, c->vertex_geo, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units, c->red_groups,
+                    c->part_vert, c->tickets, c->ion_xyzq, c->ion_vel, c->ion_force, c->ion_mesh, c->ion_e, c->ion_mesh_lj, c->ion_part, c->edge_E, c->vertex_e, c->face_e, c->face_local, c->vertex_geo, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units, c->red_groups, c->pair_ptab,
                     c->sym_rowpart, c->sym_colpart, c->sym_fv, c->xflags, c->xstate, c->xtickets, c->x_timed_out, c->lj_all,
                     c->d_peer_xyzq, c->d_peer_fv, c->d_peer_ke, c->d_peer_flags};
     for (void *p : ptrs)
@@ -1542,8 +1646,6 @@ int npsl_set_ions(npsl_ctx *c, int n_ions, const double *pos, const double *vel,
                   double lj_length_mesh_ions) {
     if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
     if (n_ions < 0 || (n_ions > 0 && (!pos || !q))) return fail(c, NPSL_ERR_ARG, "bad ion arguments");
-    if (n_ions > 0 && c->mp.n_ranks > 1)
-        return fail(c, NPSL_ERR_ARG, "explicit counterions need a single-GPU context or the replicated sharding plan");
     if (n_ions > 0 && !(diameter > 0 && lj_length_mesh_ions > 0)) return fail(c, NPSL_ERR_ARG, "ion LJ lengths must be positive");
     CU(cudaStreamSynchronize(c->s_main));
     void *old[] = {c->ion_xyzq, c->ion_vel, c->ion_force, c->ion_mesh, c->ion_e, c->ion_mesh_lj, c->ion_part};
@@ -1778,14 +1880,17 @@ int npsl_step_profile(npsl_ctx *c, int n_steps, char *out, int out_len) {
 
 int npsl_set_pair_plan(npsl_ctx *c, int rows_per_thread, int col_splits) {
     if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
-    if (!(rows_per_thread == 0 || rows_per_thread == 1 || rows_per_thread == 2 || rows_per_thread == 4) || col_splits < 0)
-        return fail(c, NPSL_ERR_ARG, "rows_per_thread must be 0,1,2,4 and col_splits >= 0");
+    const bool sym_only = rows_per_thread >= 5 && rows_per_thread <= 8;  // shapes of the symmetric kernel only
+    if (!(rows_per_thread == 0 || rows_per_thread == 1 || rows_per_thread == 2 || rows_per_thread == 4 || (sym_only && c->use_sym)) ||
+        col_splits < 0)
+        return fail(c, NPSL_ERR_ARG, "rows_per_thread must be 0,1,2,4 (6,8: symmetric kernel) and col_splits >= 0");
     CU(cudaStreamSynchronize(c->s_main));
     c->plan_rows = rows_per_thread;
     c->plan_splits = col_splits;
     if (c->use_sym) {  // measurement knob for the symmetric kernel: (rows per thread, threads per CTA [+1: tighter register cap])
         if (rows_per_thread) c->sym_rows = rows_per_thread;
-        if (col_splits >= 128) { c->sym_threads = col_splits & ~1; c->sym_minb = (col_splits & 1) ? 8 : 0; }
+        c->sym_shape_set = true;
+        if (col_splits >= 64) { c->sym_threads = col_splits & ~1; c->sym_minb = (col_splits & 1) ? 8 : 0; }
         c->plan_rows = c->plan_splits = 0;
         plan_pair(c, c->n_sm);
         int r = plan_sym(c);
@@ -1803,8 +1908,6 @@ int npsl_set_pair_plan(npsl_ctx *c, int rows_per_thread, int col_splits) {
 
 int npsl_set_volume_constraint(npsl_ctx *c, int on) {
     if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
-    if (on && c->world > 1 && !c->replicated)
-        return fail(c, NPSL_ERR_ARG, "the rigid volume constraint is not available on row-sharded contexts");
     CU(cudaStreamSynchronize(c->s_main));
     c->mp.constraint = on ? 1 : 0;
     drop_graph(c);
@@ -1816,6 +1919,9 @@ int npsl_constraint_init(npsl_ctx *c) {
     if (!c) return fail(c, NPSL_ERR_ARG, "ctx is NULL");
     if (!c->mp.constraint) return fail(c, NPSL_ERR_STATE, "npsl_constraint_init without npsl_set_volume_constraint");
     if (!c->forces_valid) return fail(c, NPSL_ERR_STATE, "npsl_constraint_init before npsl_force_init");
+    int r;
+    if ((r = gather_records(c, c->ngv))) return r;  // rows plan, see issue()
+    if ((r = gather_records(c, c->vel))) return r;
     k_constraint_sums<0><<<c->n_face_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv, c->face_v, c->part_con,
                                                                           c->tickets + 2, c->scal, c->mp);
     k_shake_apply<<<(c->nv + kMeshThreads - 1) / kMeshThreads, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv, c->scal,
@@ -1824,8 +1930,15 @@ int npsl_constraint_init(npsl_ctx *c) {
                                                                           c->tickets + 2, c->scal, c->mp);
     k_rattle_apply<true><<<c->n_vertex_blocks, kMeshThreads, 0, c->s_main>>>(c->vel, c->ngv, c->part_vert, c->tickets + 1,
                                                                              c->scal, c->ke_warp, c->n_ke_warps, c->th_mid,
-                                                                             c->th_cur, c->xg, c->mp);
+                                                                             c->th_cur, c->d_peer_ke, c->xg, c->mp);
     c->launches += 4;
+    if (c->world > 1 && !c->replicated) {  // rows plan: the kinetic energy is finished after the exchange of the partials
+        const size_t per_rank = (size_t) c->range / 32;
+        if (!c->p2p)
+            NC(g_nccl.AllGather(c->ke_warp + (size_t) c->rank * per_rank, c->ke_warp, per_rank, ncclFloat64_, c->comm, c->s_main));
+        k_ke_post<<<1, kMeshThreads, 0, c->s_main>>>(c->ke_warp, c->n_ke_warps, c->scal, c->th_mid, c->th_cur, 0, c->xg, c->mp);
+        c->launches++;
+    }
     CU(cudaGetLastError());
     return NPSL_OK;
 }
@@ -1864,7 +1977,7 @@ int npsl_plan_pair_units(int n_vertices, int rank, int world, int32_t *units, in
         return fail(c, NPSL_ERR_ARG, "bad arguments (the rank count must divide 8)");
     SymParams sp;
     memset(&sp, 0, sizeof sp);
-    sym_geometry(n_vertices, 4 * 128, sp);
+    sym_geometry(n_vertices, 6 * 64, sp);  // the default shape of k_pair_sym
     std::vector<SymUnit> mine;
     const int v_count = kSymV / world;
     sym_units_of(sp, rank * v_count, v_count, mine);
@@ -1897,6 +2010,23 @@ int npsl_pair_geometry(const npsl_ctx *c, int32_t *rows_per_thread, int32_t *row
     if (col_splits) *col_splits = c->pair_splits;
     if (cols_per_cta) *cols_per_cta = c->pair_cols_per_cta;
     return NPSL_OK;
+}
+
+int npsl_pair_poly_eval(double inv_kappa_out, const double *s, double *table_value, double *exact_value, int n) {
+    npsl_ctx *c = nullptr;
+    if (!(inv_kappa_out > 0) || !s || n < 0) return fail(c, NPSL_ERR_ARG, "bad argument");
+    std::vector<double> tab;
+    build_pair_table(inv_kappa_out, tab);
+    for (int i = 0; i < n; i++) {
+        if (table_value) table_value[i] = eval_pair_table(tab, s[i]);
+        if (exact_value) exact_value[i] = (double) radial_factor((long double) s[i], (long double) inv_kappa_out);
+    }
+    return NPSL_OK;
+}
+
+int npsl_pair_math(const npsl_ctx *c) {
+    if (!c) return NPSL_ERR_ARG;
+    return c->use_sym ? c->sym_math : SYM_EXACT;
 }
 
 int npsl_fp64_peak(double *dfma_per_s, double *sm_clock_mhz) {

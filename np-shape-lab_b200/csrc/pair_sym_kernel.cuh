@@ -21,8 +21,20 @@
 #pragma once
 #include "pair_kernel.cuh"
 #include "xchg.cuh"
+#include "exp2_table_fast.inc"
 
 namespace npsl {
+
+// How k_pair_sym evaluates the radial factor e^{-r/lambda} (1/r^3 + 1/(lambda r^2)) of a pair:
+//   SYM_EXACT  rsqrt and exp to ~3e-16 (31.75 FP64-pipe instructions per pair);
+//   SYM_POLY   piecewise degree-5 polynomial in r^2 from a 39 KB table (20.75; bound by shared-memory bandwidth);
+//   SYM_FAST   the exact scheme with the accuracy the contract of the path does not need taken out: coordinates
+//              pre-scaled by 1/lambda (the factor becomes e^{-r}(1/r^3 + 1/r^2), one FMA less), second-order instead of
+//              third-order correction of the rsqrt seed (3/8 e^2 <= 4e-13), 2048-entry 2^(j/2048) table with a quadratic
+//              (3.2e-13): 28.75 per pair, relative error of the factor < 1e-12 against a contract of 1e-10.
+enum { SYM_EXACT = 0, SYM_POLY = 1, SYM_FAST = 2 };
+constexpr int kExpTabFast = 1 << NPSL_EXP2FAST_TB;
+__device__ const double c_exp2_tab_fast[kExpTabFast] = {NPSL_EXP2FAST_TABLE};
 
 constexpr int kSymPad = 512;  // partial-buffer planes are padded to a multiple of this
 constexpr int kSymV = 8;      // virtual ranks (fixed grouping of the units)
@@ -37,8 +49,26 @@ struct SymParams {
     int fine_tiles;   //   units that are scheduled last and even out the tail of the launch
     int n_chunks;
     int lj_cut_hi;
+    const double2 *ptab;  // piecewise-polynomial table of the radial factor (kPoly* below), null: exact evaluation only
     unsigned long long *trace;  // measurement only (NPSL_SYM_TRACE): per CTA {SM id, start ns, end ns}, else null
 };
+
+// Piecewise polynomial of the whole radial factor  G(s) = e^{-sqrt(s)/lambda} (s^{-3/2} + s^{-1}/lambda),  s = r^2.
+// The contract of the path is 1e-10 (north_star); evaluating rsqrt and exp to 3e-16 costs 17 of the 31.75 FP64
+// instructions per pair. Here the interval comes from the exponent and the top kPolyBits mantissa bits of s (integer
+// pipe), the argument is t = s - (midpoint of the interval) (exact, one DADD), and G is a degree-5 polynomial in t
+// whose six coefficients were fitted per interval at context creation (Chebyshev nodes, long double; npsl.cu
+// build_pair_table): 6 FP64 instructions instead of 17, no MUFU, relative error <= ~3e-12 in the near field
+// (tests/test_pair_table.py). Covered range s in [2^kPolyEmin, 2^(kPolyEmin + kPolyOct)), i.e. r from 4.9e-4 to 5.66
+// reduced units; a unit that meets a pair outside it (or any non-finite distance) is recomputed exactly by the same
+// CTA, so the result stays a function of the unit's data alone (bit-identical on 1..8 GPUs).
+constexpr int kPolyBits = 5;                        // 32 intervals per octave
+constexpr int kPolyEmin = -21, kPolyOct = 26;
+constexpr int kPolyCount = kPolyOct << kPolyBits;   // 832 intervals, 48 B each = 39 936 B of shared memory
+constexpr int kPolyShift = 20 - kPolyBits;          // interval index = (high word of s >> kPolyShift) - kPolyBase
+constexpr int kPolyBase = (1023 + kPolyEmin) << kPolyBits;
+constexpr int kPolyHiMin = kPolyBase << kPolyShift; // high words of the covered range [min, max)
+constexpr int kPolyHiMax = (kPolyBase + kPolyCount) << kPolyShift;
 constexpr int kSymCT = 128;   // granularity of the column chunks (the kernels' column tile is THREADS wide)
 // first tile of chunk c (c == n_chunks: one past the last tile, before clamping to the vertex count)
 __host__ __device__ __forceinline__ int sym_chunk_tile0(const SymParams &P, const int c) {
@@ -72,19 +102,20 @@ struct SymRow {
 // One phase: this warp against one 32-column group. Lane l visits column (l + s) mod 32 at step s. The
 // ROWS pair evaluations of a step are written stage by stage across the rows, so that the instruction
 // stream offers ROWS independent FP64 chains (the dependent-issue latency of the FP64 pipe is ~13 cycles).
-template <int ROWS, bool DIAG>
+template <int ROWS, bool DIAG, int MATH, int UNROLL>
 __device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[ROWS], const int gj0,
                                           const double *__restrict__ sx, const double *__restrict__ sy,
                                           const double *__restrict__ sz, const double *__restrict__ sq,
                                           double *__restrict__ sax, double *__restrict__ say, double *__restrict__ saz,
                                           const int lane, const double c2s, const double inv_lambda,
-                                          const double *__restrict__ tab, int &min_r2_hi) {
+                                          const double *__restrict__ tab, const double2 *__restrict__ ptab, int &min_r2_hi,
+                                          int &max_r2_hi) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-#pragma unroll 1
+#pragma unroll UNROLL
     for (int s = 0; s < 32; s++) {
         const int col = (lane + s) & 31;
         const double xj = sx[col], yj = sy[col], zj = sz[col], qj = sq[col];
-        double dx[ROWS], dy[ROWS], dz[ROWS], qc[ROWS], qr[ROWS], a[ROWS], b[ROWS], y[ROWS];
+        double dx[ROWS], dy[ROWS], dz[ROWS], qc[ROWS], qr[ROWS], a[ROWS];
 #pragma unroll
         for (int r = 0; r < ROWS; r++) {
             double cx = xj;
@@ -100,42 +131,103 @@ __device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[R
         }
 #pragma unroll
         for (int r = 0; r < ROWS; r++) a[r] = fma(dz[r], dz[r], fma(dy[r], dy[r], dx[r] * dx[r]));  // r^2
+        if (MATH == SYM_POLY) {
+            double2 c01[ROWS], c23[ROWS], c45[ROWS];
+            double t[ROWS];
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) {
-            min_r2_hi = min(min_r2_hi, __double2hiint(a[r]));
-            y[r] = rsqrt_seed(a[r]);
-        }
+            for (int r = 0; r < ROWS; r++) {
+                const int hi = __double2hiint(a[r]);
+                min_r2_hi = min(min_r2_hi, hi);
+                max_r2_hi = max(max_r2_hi, hi);
+                const int k = min(max((hi >> kPolyShift) - kPolyBase, 0), kPolyCount - 1);
+                const double2 *e = ptab + 3 * k;
+                c01[r] = e[0]; c23[r] = e[1]; c45[r] = e[2];
+                // midpoint of the interval: the kept mantissa bits, then 1000...0
+                t[r] = a[r] - __hiloint2double((hi & (int) (0xffffffffu << kPolyShift)) | (1 << (kPolyShift - 1)), 0);
+            }
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) b[r] = a[r] * y[r];
+            for (int r = 0; r < ROWS; r++) a[r] = fma(c45[r].y, t[r], c45[r].x);
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) b[r] = fma(-b[r], y[r], 1.0);  // e
+            for (int r = 0; r < ROWS; r++) a[r] = fma(a[r], t[r], c23[r].y);
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) {
-            const double p = fma(b[r], 0.375, 0.5);
-            y[r] = fma(y[r] * b[r], p, y[r]);  // 1/r
-        }
+            for (int r = 0; r < ROWS; r++) a[r] = fma(a[r], t[r], c23[r].x);
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) a[r] = a[r] * y[r];  // r
-        double tt[ROWS], f[ROWS], T[ROWS];
+            for (int r = 0; r < ROWS; r++) a[r] = fma(a[r], t[r], c01[r].y);
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) tt[r] = fma(a[r], c2s, MAGIC);
+            for (int r = 0; r < ROWS; r++) a[r] = fma(a[r], t[r], c01[r].x);  // e^{-r/lambda} (1/r^3 + 1/(lambda r^2))
+        } else if (MATH == SYM_FAST) {  // coordinates are in units of lambda here
+            double b[ROWS], y[ROWS];
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) {
-            f[r] = fma(a[r], c2s, -(tt[r] - MAGIC));
-            const int n = __double2loint(tt[r]);
-            const double Tj = tab[n & (kExpTab - 1)];
-            const int k = max(n >> NPSL_EXP2_TB, -1000);
-            T[r] = __hiloint2double(__double2hiint(Tj) + (k << 20), __double2loint(Tj));
-        }
+            for (int r = 0; r < ROWS; r++) {
+                min_r2_hi = min(min_r2_hi, __double2hiint(a[r]));
+                y[r] = rsqrt_seed(a[r]);
+            }
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) b[r] = fma(f[r], NPSL_EXP2_G3, NPSL_EXP2_G2);
+            for (int r = 0; r < ROWS; r++) b[r] = a[r] * y[r];
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) b[r] = fma(b[r], f[r], NPSL_EXP2_G1);
+            for (int r = 0; r < ROWS; r++) b[r] = fma(-b[r], y[r], 1.0);  // e = 1 - a y0^2
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) {
-            const double ex = fma(T[r], f[r] * b[r], T[r]);
-            const double w = (y[r] * y[r]) * (y[r] + inv_lambda);
-            a[r] = ex * w;  // e^{-r/lambda} (1/r^3 + 1/(lambda r^2))
+            for (int r = 0; r < ROWS; r++) y[r] = fma(y[r] * b[r], 0.5, y[r]);  // 1/r (1 - 3/8 e^2 ...)
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) a[r] = a[r] * y[r];  // r
+            double tt[ROWS], f[ROWS], T[ROWS];
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) tt[r] = fma(a[r], c2s, MAGIC);
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                f[r] = fma(a[r], c2s, -(tt[r] - MAGIC));
+                const int n = __double2loint(tt[r]);
+                const double Tj = tab[n & (kExpTabFast - 1)];
+                const int k = max(n >> NPSL_EXP2FAST_TB, -1000);
+                T[r] = __hiloint2double(__double2hiint(Tj) + (k << 20), __double2loint(Tj));
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) b[r] = fma(f[r], NPSL_EXP2FAST_G2, NPSL_EXP2FAST_G1);
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                const double ex = fma(T[r], f[r] * b[r], T[r]);
+                const double y2 = y[r] * y[r];
+                a[r] = ex * fma(y2, y[r], y2);  // e^{-r} (1/r^3 + 1/r^2)
+            }
+        } else {
+            double b[ROWS], y[ROWS];
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                min_r2_hi = min(min_r2_hi, __double2hiint(a[r]));
+                y[r] = rsqrt_seed(a[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) b[r] = a[r] * y[r];
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) b[r] = fma(-b[r], y[r], 1.0);  // e
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                const double p = fma(b[r], 0.375, 0.5);
+                y[r] = fma(y[r] * b[r], p, y[r]);  // 1/r
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) a[r] = a[r] * y[r];  // r
+            double tt[ROWS], f[ROWS], T[ROWS];
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) tt[r] = fma(a[r], c2s, MAGIC);
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                f[r] = fma(a[r], c2s, -(tt[r] - MAGIC));
+                const int n = __double2loint(tt[r]);
+                const double Tj = tab[n & (kExpTab - 1)];
+                const int k = max(n >> NPSL_EXP2_TB, -1000);
+                T[r] = __hiloint2double(__double2hiint(Tj) + (k << 20), __double2loint(Tj));
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) b[r] = fma(f[r], NPSL_EXP2_G3, NPSL_EXP2_G2);
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) b[r] = fma(b[r], f[r], NPSL_EXP2_G1);
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                const double ex = fma(T[r], f[r] * b[r], T[r]);
+                const double w = (y[r] * y[r]) * (y[r] + inv_lambda);
+                a[r] = ex * w;  // e^{-r/lambda} (1/r^3 + 1/(lambda r^2))
+            }
         }
         double ax = 0.0, ay = 0.0, az = 0.0;
 #pragma unroll
@@ -155,48 +247,37 @@ __device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[R
     }
 }
 
-// grid = units of this rank (heaviest first); block = THREADS; row block = ROWS * THREADS rows (== P.rb).
-template <int ROWS, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, double *__restrict__ rowpart,
-           double *__restrict__ colpart, int *__restrict__ lj_hit, const SymParams P) {
+// One pass over the column tiles of a unit. POLY: groups of 32 columns that are entirely real take the polynomial
+// evaluation; the (single) partial group at the end of the column range, whose padding columns sit far away, takes the
+// exact one. Returns through min / max of the high words of r^2 what the caller needs for the WCA detector and for
+// the range check.
+template <int ROWS, int THREADS, int MATH, int UNROLL>
+__device__ __forceinline__ void sym_unit(SymRow (&row)[ROWS], const int (&gi)[ROWS], const double4 *__restrict__ xyzq,
+                                         double *__restrict__ colpart, const int I, const int row0, const int col_begin,
+                                         const int col_end, double *sx, double *sy, double *sz, double *sq, double *sax,
+                                         double *say, double *saz, const double *__restrict__ tab,
+                                         const double2 *__restrict__ ptab, const SymParams &P, int &min_r2_hi,
+                                         int &max_r2_hi) {
     constexpr int RB = ROWS * THREADS;
     constexpr int GROUPS = THREADS / 32;
-    __shared__ double sx[THREADS], sy[THREADS], sz[THREADS], sq[THREADS];
-    __shared__ double sax[THREADS], say[THREADS], saz[THREADS];
-    __shared__ double tab[kExpTab];
+    // the exact evaluation used by SYM_POLY for partial groups / out-of-range units
+    constexpr int EXACT = MATH == SYM_POLY ? SYM_EXACT : MATH;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    unsigned long long t_begin = 0;
-    if (P.trace && t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
-    for (int k = t; k < kExpTab; k += THREADS) tab[k] = c_exp2_tab[k];
-    const int2 unit = units[blockIdx.x];
-    const int I = unit.x, c = unit.y;
-    const int row0 = I * RB;
-
-    SymRow row[ROWS];
-    int gi[ROWS];
+    const double inv_lambda = P.inv_lambda;
+    // SYM_FAST works in units of lambda: the exponent scale no longer carries 1/lambda, the partial sums come out
+    // lambda^2 too large (d and the radial factor scale by 1/lambda and lambda^3)
+    const double c2s = MATH == SYM_FAST ? -1.4426950408889634074 * (double) kExpTabFast : P.c2s;
+    const double cs = MATH == SYM_FAST ? inv_lambda : 1.0, out_scale = MATH == SYM_FAST ? inv_lambda * inv_lambda : 1.0;
 #pragma unroll
-    for (int r = 0; r < ROWS; r++) {
-        gi[r] = row0 + r * THREADS + t;
-        const double4 v = xyzq[min(gi[r], P.n - 1)];
-        row[r].x = v.x; row[r].y = v.y; row[r].z = v.z;
-        row[r].q = gi[r] < P.n ? v.w : 0.0;  // rows past the end exert nothing and are never stored
-        row[r].fx = row[r].fy = row[r].fz = 0.0;
-    }
-    const double c2s = P.c2s, inv_lambda = P.inv_lambda;
-    int min_r2_hi = 0x7fffffff;
-    // columns of this unit: the chunk, from the start of the row block on (what lies below belongs to other units)
-    const int col_begin = max(sym_chunk_tile0(P, c) * kSymCT, row0);
-    const int col_end = min(sym_chunk_tile0(P, c + 1) * kSymCT, P.n);
-
+    for (int r = 0; r < ROWS; r++) row[r].fx = row[r].fy = row[r].fz = 0.0;
     for (int j0 = col_begin; j0 < col_end; j0 += THREADS) {
         const int j = j0 + t;
         __syncthreads();
         if (j < col_end) {
             const double4 v = xyzq[j];
-            sx[t] = v.x; sy[t] = v.y; sz[t] = v.z; sq[t] = v.w;
+            sx[t] = v.x * cs; sy[t] = v.y * cs; sz[t] = v.z * cs; sq[t] = v.w;
         } else {  // padding columns: far away, no charge
-            sx[t] = 1.0e3 + t; sy[t] = 0.0; sz[t] = 0.0; sq[t] = 0.0;
+            sx[t] = (1.0e3 + t) * cs; sy[t] = 0.0; sz[t] = 0.0; sq[t] = 0.0;
         }
         sax[t] = 0.0; say[t] = 0.0; saz[t] = 0.0;
         __syncthreads();
@@ -205,21 +286,93 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
         for (int p = 0; p < GROUPS; p++) {
             const int o = ((warp + p) % GROUPS) * 32;
             if (j0 + o < col_end) {  // whole group of padding columns: nothing to do
-                if (!diag)
-                    sym_phase<ROWS, false>(row, gi, j0 + o, sx + o, sy + o, sz + o, sq + o, sax + o, say + o, saz + o,
-                                           lane, c2s, inv_lambda, tab, min_r2_hi);
-                else
-                    sym_phase<ROWS, true>(row, gi, j0 + o, sx + o, sy + o, sz + o, sq + o, sax + o, say + o, saz + o,
-                                          lane, c2s, inv_lambda, tab, min_r2_hi);
+                int dummy = 0;
+                if (MATH == SYM_POLY && j0 + o + 32 <= col_end) {
+                    if (!diag)
+                        sym_phase<ROWS, false, SYM_POLY, UNROLL>(row, gi, j0 + o, sx + o, sy + o, sz + o, sq + o, sax + o,
+                                                                 say + o, saz + o, lane, c2s, inv_lambda, tab, ptab,
+                                                                 min_r2_hi, max_r2_hi);
+                    else
+                        sym_phase<ROWS, true, SYM_POLY, UNROLL>(row, gi, j0 + o, sx + o, sy + o, sz + o, sq + o, sax + o,
+                                                                say + o, saz + o, lane, c2s, inv_lambda, tab, ptab,
+                                                                min_r2_hi, max_r2_hi);
+                } else {
+                    if (!diag)
+                        sym_phase<ROWS, false, EXACT, UNROLL>(row, gi, j0 + o, sx + o, sy + o, sz + o, sq + o, sax + o, say + o,
+                                                              saz + o, lane, c2s, inv_lambda, tab, ptab, min_r2_hi, dummy);
+                    else
+                        sym_phase<ROWS, true, EXACT, UNROLL>(row, gi, j0 + o, sx + o, sy + o, sz + o, sq + o, sax + o, say + o,
+                                                             saz + o, lane, c2s, inv_lambda, tab, ptab, min_r2_hi, dummy);
+                }
             }
             __syncthreads();
         }
         if (j < col_end) {
             double *cp = colpart + (size_t) I * 3 * P.npad + j;
-            cp[0] = sax[t];
-            cp[P.npad] = say[t];
-            cp[2 * (size_t) P.npad] = saz[t];
+            cp[0] = sax[t] * out_scale;
+            cp[P.npad] = say[t] * out_scale;
+            cp[2 * (size_t) P.npad] = saz[t] * out_scale;
         }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        row[r].fx *= out_scale; row[r].fy *= out_scale; row[r].fz *= out_scale;
+    }
+}
+
+// grid = units of this rank (heaviest first); block = THREADS; row block = ROWS * THREADS rows (== P.rb).
+// POLY: dynamic shared memory holds the polynomial table (kPolyCount x 48 B); the exact evaluation, needed for partial
+// column groups and for the rare unit that leaves the table's range, then reads its 2^(j/1024) table from global memory.
+template <int ROWS, int THREADS, int MINB, int MATH, int UNROLL>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, double *__restrict__ rowpart,
+           double *__restrict__ colpart, int *__restrict__ lj_hit, const SymParams P) {
+    constexpr int RB = ROWS * THREADS;
+    extern __shared__ double2 s_ptab[];
+    __shared__ double sx[THREADS], sy[THREADS], sz[THREADS], sq[THREADS];
+    __shared__ double sax[THREADS], say[THREADS], saz[THREADS];
+    __shared__ double s_tab[MATH == SYM_POLY ? 1 : (MATH == SYM_FAST ? kExpTabFast : kExpTab)];
+    const int t = threadIdx.x;
+    unsigned long long t_begin = 0;
+    if (P.trace && t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+    const double *tab = s_tab;
+    if (MATH == SYM_POLY) {
+        for (int k = t; k < 3 * kPolyCount; k += THREADS) s_ptab[k] = __ldg(P.ptab + k);
+        tab = c_exp2_tab;
+    } else if (MATH == SYM_FAST) {
+        for (int k = t; k < kExpTabFast; k += THREADS) s_tab[k] = c_exp2_tab_fast[k];
+    } else {
+        for (int k = t; k < kExpTab; k += THREADS) s_tab[k] = c_exp2_tab[k];
+    }
+    const int2 unit = units[blockIdx.x];
+    const int I = unit.x, c = unit.y;
+    const int row0 = I * RB;
+    const double cs = MATH == SYM_FAST ? P.inv_lambda : 1.0;
+
+    SymRow row[ROWS];
+    int gi[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        gi[r] = row0 + r * THREADS + t;
+        const double4 v = xyzq[min(gi[r], P.n - 1)];
+        row[r].x = v.x * cs; row[r].y = v.y * cs; row[r].z = v.z * cs;
+        row[r].q = gi[r] < P.n ? v.w : 0.0;  // rows past the end exert nothing and are never stored
+    }
+    int min_r2_hi = 0x7fffffff, max_r2_hi = 0;
+    // columns of this unit: the chunk, from the start of the row block on (what lies below belongs to other units)
+    const int col_begin = max(sym_chunk_tile0(P, c) * kSymCT, row0);
+    const int col_end = min(sym_chunk_tile0(P, c + 1) * kSymCT, P.n);
+
+    if (MATH == SYM_POLY) {
+        sym_unit<ROWS, THREADS, SYM_POLY, UNROLL>(row, gi, xyzq, colpart, I, row0, col_begin, col_end, sx, sy, sz, sq, sax, say,
+                                                  saz, tab, s_ptab, P, min_r2_hi, max_r2_hi);
+        // a pair outside the table (or a non-finite distance): the whole unit is redone exactly
+        if (__syncthreads_or(min_r2_hi < kPolyHiMin || max_r2_hi >= kPolyHiMax))
+            sym_unit<ROWS, THREADS, SYM_EXACT, UNROLL>(row, gi, xyzq, colpart, I, row0, col_begin, col_end, sx, sy, sz, sq, sax,
+                                                       say, saz, tab, s_ptab, P, min_r2_hi, max_r2_hi);
+    } else {
+        sym_unit<ROWS, THREADS, MATH, UNROLL>(row, gi, xyzq, colpart, I, row0, col_begin, col_end, sx, sy, sz, sq, sax, say, saz,
+                                              tab, s_ptab, P, min_r2_hi, max_r2_hi);
     }
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {

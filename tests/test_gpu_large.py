@@ -8,12 +8,26 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLD, golden, relerr, vertex_relerr
+from conftest import GOLD, bending_term_scale, golden, relerr, vertex_relerr
 from np_shape_lab_b200 import capi
 from np_shape_lab_b200 import workloads as W
 from test_gpu_parity import TOL, check_against_fixture, make_ctx
 
 pytestmark = pytest.mark.gpu
+
+
+def one_ulp_response(ctx, pos):
+    """How far the device's own force moves when every input coordinate moves by one ulp (random direction): the
+    99.9th percentile over the vertices of |F(x~) - F(x)|. From step 1 on the reference's positions are x87 80-bit
+    numbers; the fixture (and any FP64 implementation) holds them rounded to double, i.e. up to half an ulp off, and
+    the bending term turns that into a force difference (stiffness ~ bkappa / edge^3 ~ 1e6 at S64: 1e6 x 1.1e-16 per
+    coordinate, a few 1e-10 per vertex) that no FP64 evaluation can remove. It is negligible against the largest
+    force (max-norm 1e-12) but not against a vertex whose own force is 1e-3."""
+    rng = np.random.default_rng(1)
+    moved = np.where(rng.random(pos.shape) < 0.5, np.nextafter(pos, np.inf), np.nextafter(pos, -np.inf))
+    f1 = ctx.force_calculation(np.ascontiguousarray(moved))
+    f0 = ctx.force_calculation(np.ascontiguousarray(pos))  # back to the state the trajectory is in
+    return float(np.percentile(np.linalg.norm(f1 - f0, axis=1), 99.9)), f0
 
 
 def test_s64_disc_every_field_at_steps_0_and_1():
@@ -26,10 +40,17 @@ def test_s64_disc_every_field_at_steps_0_and_1():
         for k in g.full_steps:
             ctx.step(k - done)
             done = k
-            check_against_fixture(ctx, g, k)
+            allow = 0.0
+            if k > 0:
+                st = ctx.download_state()
+                allow, f_again = one_ulp_response(ctx, st["pos"])
+                assert np.array_equal(f_again, st["force"])  # the force pass reproduces the step's force bit for bit
+                assert allow < 1e-11 * float(np.max(np.abs(st["force"])))  # nothing in the max-norm
+            check_against_fixture(ctx, g, k, vertex_abs=allow)
             comp = ctx.download_force_components()
             assert vertex_relerr(comp["pair"], g["k%d_pforce" % k]) < TOL
-            assert vertex_relerr(comp["bending"], g["k%d_bforce" % k], floor_frac=1e-3) < TOL
+            cond = bending_term_scale(g["edges"], g["faces"], g["k%d_pos" % k], g.params["bkappa"])
+            assert vertex_relerr(comp["bending"], g["k%d_bforce" % k], cond=cond, abs_allow=allow) < TOL
 
 
 def lcg_displacements(n, amp):

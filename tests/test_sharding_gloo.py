@@ -137,11 +137,11 @@ def test_shard_ranges_tile_the_rows(n, world):
 
 # ---- the symmetric pair kernel's work decomposition (host-side planner, no device needed) -----------------------
 
-def _pair_count(units, n):
+def _pair_count(units, n, rb):
     """Number of pairs (i, j), j > i, that the units cover, and a coverage check on a coarse grid."""
     total = 0
     for I, c, j0, j1 in units:
-        i0, i1 = I * 512, min((I + 1) * 512, n)
+        i0, i1 = I * rb, min((I + 1) * rb, n)
         for i in (range(i0, i1) if j0 < i1 else ()):  # rows that overlap the column range (diagonal units)
             total += max(0, j1 - max(j0, i + 1))
         if j0 >= i1:
@@ -155,8 +155,9 @@ def test_symmetric_units_cover_every_pair_exactly_once_on_any_rank_count(n):
     Together they cover each unordered pair once, and the shares are balanced."""
     from np_shape_lab_b200 import capi
     all_units, geo1 = capi.plan_pair_units(n, 0, 1)
-    assert geo1["rows_per_block"] == 512 and geo1["column_granularity"] == 128
-    assert _pair_count(all_units.tolist(), n) == n * (n - 1) // 2
+    rb = geo1["rows_per_block"]
+    assert rb == 6 * 64 and geo1["column_granularity"] == 128  # default shape of k_pair_sym: 6 rows x 64 threads
+    assert _pair_count(all_units.tolist(), n, rb) == n * (n - 1) // 2
     keys1 = sorted((int(u[0]), int(u[1])) for u in all_units)
     assert len(set(keys1)) == len(keys1)
     work = np.array([(u[3] - u[2]) for u in all_units])
@@ -167,7 +168,7 @@ def test_symmetric_units_cover_every_pair_exactly_once_on_any_rank_count(n):
             u, geo = capi.plan_pair_units(n, r, world)
             assert geo == geo1  # the decomposition does not depend on the rank count
             keys += [(int(a[0]), int(a[1])) for a in u]
-            per_rank.append(_pair_count(u.tolist(), n))
+            per_rank.append(_pair_count(u.tolist(), n, rb))
         assert sorted(keys) == keys1
         assert sum(per_rank) == n * (n - 1) // 2
         if n >= 40962:
