@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libnpsl.so")
+# NPSL_LIB: measurement only (A/B of two builds of the library on the GPU box); the product path is libnpsl.so in-tree
+LIB_PATH = os.environ.get("NPSL_LIB") or os.path.join(PKG, "libnpsl.so")
 
 NPSL_MAX_CHAIN = 16
 NPSL_NCCL_ID_BYTES = 128

@@ -384,7 +384,7 @@ void sym_geometry(int nv, int rb, SymParams &sp) {
     sp.npad = (nv + kSymPad - 1) / kSymPad * kSymPad;
     sp.rb = rb;
     // 256 columns per unit up to 32768 vertices, at most 256 chunks beyond: fine-grained enough to fill 8 GPUs
-    sp.chunk_tiles = std::max(2, (nv + 256 * kSymCT - 1) / (256 * kSymCT));
+    sp.chunk_tiles = std::max(256 / kSymCT, (nv + 256 * kSymCT - 1) / (256 * kSymCT));
     if (const char *e = getenv("NPSL_SYM_CHUNK_TILES"))  // measurement knob; changes the grouping of the row sums
         if (atoi(e) > 0) sp.chunk_tiles = atoi(e);
     const int n_tiles = (nv + kSymCT - 1) / kSymCT;
@@ -394,6 +394,8 @@ void sym_geometry(int nv, int rb, SymParams &sp) {
     int fine_pct = 25;
     if (const char *e = getenv("NPSL_SYM_FINE_PCT")) fine_pct = std::max(0, std::min(100, atoi(e)));  // measurement knob
     sp.fine_tiles = std::max(1, sp.chunk_tiles / 2);
+    if (const char *e = getenv("NPSL_SYM_FINE_TILES"))  // measurement knob
+        if (atoi(e) > 0) sp.fine_tiles = atoi(e);
     const int coarse_tiles = n_tiles - (int) ((long) n_tiles * fine_pct / 100);
     sp.n_coarse = fine_pct >= 100 ? 0 : (coarse_tiles + sp.chunk_tiles - 1) / sp.chunk_tiles;
     const int rest = std::max(0, n_tiles - sp.n_coarse * sp.chunk_tiles);
@@ -497,6 +499,7 @@ int plan_sym(npsl_ctx *c) {
         CU(cudaMemcpy(c->pair_ptab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     }
     sp.ptab = c->pair_ptab;
+
     const int n_rb = (nv + sp.rb - 1) / sp.rb;
     const bool want = c->pair_mode == 2 || (c->pair_mode == 0 && nv >= 4096);
     c->use_sym = want && (kSymV % c->world == 0);
@@ -611,9 +614,8 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair, bool 
         }
         if (c->world > 1 && !c->replicated) mark("exchange positions");
         if (c->mp.constraint) {  // SHAKE, src/newmd.cpp:126
-            // rows plan: the face sums run over all faces on every rank (identical order, identical multiplier) and
-            // need VERTEX::neg_GradVi of every vertex; each rank computed its own slice in the last force evaluation
-            { int r = gather_records(c, c->ngv); if (r) return r; }
+            // rows plan: the face sums run over all faces on every rank (identical order, identical multiplier); they
+            // need VERTEX::neg_GradVi of every vertex, gathered at the end of the last force evaluation (below)
             k_constraint_sums<0><<<c->n_face_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv, c->face_v,
                                                                                   c->part_con, c->tickets + 2, c->scal, c->mp);
             k_shake_apply<<<(c->nv + kMeshThreads - 1) / kMeshThreads, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv,
@@ -765,6 +767,10 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair, bool 
     mark("k_pair (ordered) + k_lj");
     CU(cudaStreamWaitEvent(c->s_main, c->ev_join, 0));
     mark("join k_mesh");
+    if (c->mp.constraint) {  // rows plan: every rank needs every vertex's new neg_GradVi for RATTLE and the next SHAKE
+        int r = gather_records(c, c->ngv);
+        if (r) return r;
+    }
     if (c->mp.n_ions > 0) {  // before the kernel that advances the thermostat chains: it needs the ions' kinetic energy
         if (step) k_ion_finish<true><<<1, 256, 0, c->s_main>>>(c->ion_vel, c->ion_force, c->ion_e, c->scal, c->ip);
         else k_ion_finish<false><<<1, 256, 0, c->s_main>>>(c->ion_vel, c->ion_force, c->ion_e, c->scal, c->ip);
@@ -945,6 +951,16 @@ int upload_records(npsl_ctx *c, double4 *dev, const double *in, bool keep_w, int
     const int nb = (c->nv + 255) / 256;
     k_scatter3<<<nb, 256, 0, c->s_main>>>(dev, c->d_pack[slot], c->nv, keep_w ? 1 : 0);
     c->launches++;
+    return 0;
+}
+
+// Rows plan over peer memory: the ranks only meet inside a step, through the exchanges. A host-state call rewrites every
+// position of this rank's copy (and later reads them all back), while a rank that is a call ahead would already push
+// the next step's positions into that copy; one tiny NCCL collective after the rewrite and one after the read-back
+// keep the calls of the ranks in lock-step.
+int rows_barrier(npsl_ctx *c) {
+    if (c->world == 1 || c->replicated || !c->p2p) return 0;
+    NC(g_nccl.AllGather(c->scal, c->scal_all, SC_COUNT, ncclFloat64_, c->comm, c->s_main));
     return 0;
 }
 
@@ -1564,6 +1580,7 @@ int npsl_md_step_host(npsl_ctx *c, double *pos, double *vel, double *force, int 
         k_scatter3<<<nb, 256, 0, c->s_main>>>(dev[k], c->d_pack[k], c->nv, k == 0 ? 1 : 0);
     }
     c->launches += 3;
+    if ((r = rows_barrier(c))) return r;
     c->forces_valid = true;  // the caller's forvec is the force at the caller's posvec (src/newmd.cpp:114-117)
     c->local_valid = false;
     for (int k = 0; k < n_steps; k++) CU(cudaGraphLaunch(c->step_graph, c->s_main));
@@ -1577,6 +1594,7 @@ int npsl_md_step_host(npsl_ctx *c, double *pos, double *vel, double *force, int 
         CU(cudaMemcpyAsync(direct[k] ? in[k] : c->h_pin[k], c->d_pack[k], bytes, cudaMemcpyDeviceToHost, c->s_main));
     }
     c->launches += 3;
+    if ((r = rows_barrier(c))) return r;
     double ke = 0;
     CU(cudaMemcpyAsync(&ke, c->scal + SC_KE, sizeof(double), cudaMemcpyDeviceToHost, c->s_main));
     CU(cudaStreamSynchronize(c->s_main));
@@ -1620,10 +1638,12 @@ int npsl_md_step_packed(npsl_ctx *c, int n_steps) {
     const int nb = (c->nv + 255) / 256;
     CU(cudaMemcpyAsync(c->d_state_in, c->h_state, sizeof(double) * 3 * n3, cudaMemcpyHostToDevice, c->s_main));
     k_unpack_state<<<nb, 256, 0, c->s_main>>>(c->xyzq, c->vel, c->force, c->d_state_in, c->nv);
+    if ((r = rows_barrier(c))) return r;
     for (int k = 0; k < n_steps; k++) CU(cudaGraphLaunch(c->step_graph, c->s_main));
     if ((r = gather_records(c, c->vel))) return r;
     if ((r = gather_records(c, c->force))) return r;
     k_pack_state<<<nb, 256, 0, c->s_main>>>(c->xyzq, c->vel, c->force, c->scal, c->d_state_out, c->nv);
+    if ((r = rows_barrier(c))) return r;
     CU(cudaMemcpyAsync(c->h_state, c->d_state_out, sizeof(double) * (3 * n3 + 1), cudaMemcpyDeviceToHost, c->s_main));
     c->launches += 2 + (int64_t) c->launches_per_step * n_steps;
     CU(cudaStreamSynchronize(c->s_main));
@@ -1920,8 +1940,7 @@ int npsl_constraint_init(npsl_ctx *c) {
     if (!c->mp.constraint) return fail(c, NPSL_ERR_STATE, "npsl_constraint_init without npsl_set_volume_constraint");
     if (!c->forces_valid) return fail(c, NPSL_ERR_STATE, "npsl_constraint_init before npsl_force_init");
     int r;
-    if ((r = gather_records(c, c->ngv))) return r;  // rows plan, see issue()
-    if ((r = gather_records(c, c->vel))) return r;
+    if ((r = gather_records(c, c->vel))) return r;  // rows plan, see issue(); neg_GradVi was gathered by the force pass
     k_constraint_sums<0><<<c->n_face_blocks, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv, c->face_v, c->part_con,
                                                                           c->tickets + 2, c->scal, c->mp);
     k_shake_apply<<<(c->nv + kMeshThreads - 1) / kMeshThreads, kMeshThreads, 0, c->s_main>>>(c->xyzq, c->vel, c->ngv, c->scal,

@@ -17,8 +17,8 @@
 
 int main(int argc, char **argv) {
     double R = 10, q = 600, conc = 0.005, t = 1, v = 1, b = 40, s = 40, p = 0.5, dt = 0.001, T = 0.001, Qm = 0.01, Qi = 0.01;
-    int N = 1, steps = 25000, D = 4, C = 5, writedata = 500;
-    char B = 'n', Fflag = 'n', H = 'n', G = 'N';
+    int N = 1, steps = 25000, D = 4, C = 5, writedata = 500, anneal_freq = 50000, anneal_dura = 5000;  // src/main.cpp:148-168
+    char B = 'n', Fflag = 'n', H = 'n', G = 'N', annealFlag = 'y';
     std::string mesh_file, outdir = "outfiles", externalPattern = "None", ions_file;
     int dump_q = 0;
     for (int i = 1; i < argc; i++) {
@@ -27,6 +27,7 @@ int main(int argc, char **argv) {
             std::puts("np_shape_lab_b200 [-R r] [-q q] [-c conc] [-t st] [-v vt] [-b bend] [-s stretch] [-B y|n] [-N 1|2] [-p frac]\n"
                       "                  [-H n|y|c] [-F n|y] [-E pattern] [-G N|V]\n"
                       "                  [-S steps] [-D disc] [-d dt] [-T temp] [-Q Qmesh] [-C chain] [-W writedata]\n"
+                      "                  [-a y|n (anneal)] [-f anneal_freq] [-u anneal_dura]\n"
                       "                  [--mesh file.dat] [--out dir] [--ions counterions.xyz]\n"
                       "                  (needs a CUDA device; there is no CPU path)");
             return 0;
@@ -43,6 +44,7 @@ int main(int argc, char **argv) {
         else if (a == "--mesh") mesh_file = val; else if (a == "--out") outdir = val;
         else if (a == "-E") externalPattern = val; else if (a == "--dump-q") dump_q = atoi(val);
         else if (a == "--ions") ions_file = val;
+        else if (a == "-a") annealFlag = val[0]; else if (a == "-f") anneal_freq = atoi(val); else if (a == "-u") anneal_dura = atoi(val);
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     try {
@@ -58,6 +60,7 @@ int main(int argc, char **argv) {
         boundary.sconstant = s;
         const double scalefactor = epsilon_water * lB_water / R;
         mdremote.steps = steps; mdremote.timestep = dt; mdremote.writedata = writedata;
+        mdremote.anneal = annealFlag; mdremote.annealfreq = anneal_freq; mdremote.annealDuration = anneal_dura;
         mdremote.QAnnealFac = 1.00 + (mdremote.TAnnealFac / 10.0);
         boundary.ein = epsilon_water; boundary.eout = epsilon_water;
         boundary.set_up(R);
@@ -112,8 +115,17 @@ int main(int argc, char **argv) {
         boundary.compute_local_energies_by_component();
         const npsl_energies &e = boundary.parts;
         const double E = boundary.energy + e.mesh_bath_ke + e.mesh_bath_pe + e.ions_bath_ke + e.ions_bath_pe;
-        std::printf("{\"vertices\": %zu, \"steps\": %d, \"wall_s\": %.6f, \"A\": %.17g, \"U\": %.17g, \"E\": %.17g}\n",
-                    boundary.V.size(), steps, wall, boundary.total_area, boundary.penergy, E);
+        std::string baths = "[";  // THERMOSTAT Q, T, dof, xi, eta of every link of the mesh chain (annealing rescales Q and T)
+        for (size_t j = 0; j < mesh_bath.size(); j++) {
+            char buf[160];
+            std::snprintf(buf, sizeof buf, "%s[%.17g, %.17g, %.17g, %.17g, %.17g]", j ? ", " : "", mesh_bath[j].Q, mesh_bath[j].T,
+                          (double) mesh_bath[j].dof, mesh_bath[j].xi, mesh_bath[j].eta);
+            baths += buf;
+        }
+        baths += "]";
+        std::printf("{\"vertices\": %zu, \"steps\": %d, \"wall_s\": %.6f, \"A\": %.17g, \"U\": %.17g, \"E\": %.17g, "
+                    "\"KE_plus_PE\": %.17g, \"mesh_bath\": %s}\n",
+                    boundary.V.size(), steps, wall, boundary.total_area, boundary.penergy, E, boundary.energy, baths.c_str());
     } catch (const npsl_error &err) {
         std::fprintf(stderr, "np_shape_lab_b200: %s (status %d)\n", err.what(), err.status);
         return 1;

@@ -57,6 +57,9 @@ CONFIGS = {
     # explicit counterions: 64 monovalent ions placed by the driver (the reference's own placement
     # loop cannot terminate with its hard-wired box, see oracle/ref_driver.cpp:place_ions)
     "disc_D4_ions": ("ref:3_4", 4, DISC + ["--ions", "64"], [0, 1, 2], [100, 250, 500]),
+    # gradual annealing of the mesh thermostat (src/newmd.cpp:258-299) with CONTROL::annealfreq = 400 and annealDuration =
+    # 100 instead of 50 000 / 5 000: windows at steps 400..499 (T / 1.25) and 800..899 (T / 2) inside a 1000-step run
+    "disc_D4_anneal": ("ref:3_4", 4, DISC + ["--anneal-freq", "400", "--anneal-duration", "100"], [0], [399, 400, 450, 500, 799, 850, 900, 1000]),
 }
 
 FULL_KEYS = ["pos", "vel", "force", "bforce", "sforce", "tforce", "vforce", "pforce", "itsS", "face_area",

@@ -12,6 +12,8 @@ from np_shape_lab_b200 import capi, workloads as W
 name = sys.argv[1] if len(sys.argv) > 1 else "S64_disc"
 # math:unroll[:rows:threads(+1 = tighter register cap)]
 variants = [tuple(int(x) for x in v.split(":")) for v in (sys.argv[2] if len(sys.argv) > 2 else "0:1,2:1,0:2,2:2,1:1").split(",")]
+for kv in sys.argv[3:]:  # further NPSL_* knobs as NAME=value
+    os.environ[kv.split("=")[0]] = kv.split("=")[1]
 w = W.build(name)
 P = capi.make_params(w.params, w.mesh_bath, w.ions_bath)
 rng = np.random.default_rng(3)
