@@ -44,11 +44,10 @@ if ROOT not in sys.path:
 
 METRIC = "md_steps_per_s"
 UNIT = "steps/s"
-# FP64-pipe instructions the pair kernel executes per ORDERED pair, counted in the SASS of the inner loops
-# (tools/sass_count.py -> profiles/r01_pair_sass_count_v4.txt): k_pair_sym evaluates each unordered pair once
-# with 31.75 instructions (127 per 4 pairs, incl. the column accumulator update) = 15.875 per ordered pair;
-# the ordered k_pair needs 27 (force only).
-DFMA_PER_PAIR = {2: 15.875, 1: 27}
+# FP64-pipe instructions the pair kernel executes per pair come from the library (npsl_pair_kernel_info: SASS counts of
+# the inner loops, tools/sass_loops.py -> profiles/r02_pair_sass_loops.txt): k_pair_sym in its default form (reduced-
+# accuracy exact scheme, 6 rows per thread) needs 171 per 6 unordered pairs = 28.5, i.e. 14.25 per ORDERED pair as the
+# reference counts pairs; the ordered k_pair needs 27.
 ALGORITHMIC_FLOPS_PER_PAIR = 24  # force-only, exp and rsqrt counted as one flop each
 
 
@@ -324,10 +323,13 @@ def run_b200(args) -> None:
     dfma_peak = max_over_ranks(dfma_peak) if world > 1 else dfma_peak
     pairs_per_launch = (hi - lo) * (n - 1)
     mode = ctx.pair_mode()
+    kinfo = ctx.pair_kernel_info()
+    pair_math = ctx.pair_math()
+    dfma_per_ordered_pair = kinfo["fp64_instr_per_pair"] / (2.0 if mode == 2 else 1.0)
     ctx_pair_mode, ctx_xchg_mode, ctx_shard_plan = mode, ctx.exchange_mode(), ctx.shard_plan()
     # the symmetric kernel's launch covers this rank's share (1/world) of all unordered pairs
     pairs_per_launch = n * (n - 1) // world if mode == 2 else pairs_per_launch
-    achieved_dfma = pairs_per_launch * DFMA_PER_PAIR[mode] / (pair_ms * 1e-3) if pair_ms > 0 else 0.0
+    achieved_dfma = pairs_per_launch * dfma_per_ordered_pair / (pair_ms * 1e-3) if pair_ms > 0 else 0.0
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -434,11 +436,13 @@ def run_b200(args) -> None:
         "roofline": {
             "bound": "fp64", "achieved": 2e-12 * achieved_dfma, "peak": 2e-12 * dfma_peak, "unit": "TFLOP/s",
             "frac": achieved_dfma / dfma_peak if dfma_peak else None, "traffic": traffic,
-            "kernel": "k_pair_sym<4,128,3> (each unordered pair once, applied to both vertices)" if mode == 2
-                      else "k_pair<%d,false>" % geo["rows_per_thread"],
+            "kernel": "k_pair_sym<%d rows x %d threads, %s> (each unordered pair once, applied to both vertices)" % (
+                          kinfo["rows_per_thread"], kinfo["threads"],
+                          {0: "rsqrt / exp to 3e-16", 1: "piecewise-polynomial radial factor", 2: "reduced-accuracy rsqrt / exp, < 1e-12"}[pair_math])
+                      if mode == 2 else "k_pair<%d,false>" % geo["rows_per_thread"],
             "kernel_ms": pair_ms, "kernel_launches_timed": pair_count,
             "kernel_share_of_step": pair_ms / ms_per_step,
-            "fp64_instr_per_ordered_pair": DFMA_PER_PAIR[mode], "ordered_pairs_per_launch": pairs_per_launch,
+            "fp64_instr_per_ordered_pair": dfma_per_ordered_pair, "ordered_pairs_per_launch": pairs_per_launch,
             "algorithmic_tflops_%dflop_per_pair" % ALGORITHMIC_FLOPS_PER_PAIR:
                 1e-12 * pairs_per_launch * ALGORITHMIC_FLOPS_PER_PAIR / (pair_ms * 1e-3) if pair_ms > 0 else None,
             "peak_source": "pure-DFMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 entry); "

@@ -221,6 +221,10 @@ int npsl_constraint_multipliers(npsl_ctx *ctx, double *shake_lambda, double *rat
  * reduced-accuracy exact scheme (csrc/pair_sym_kernel.cuh; environment NPSL_SYM_MATH overrides the default). */
 int npsl_pair_poly_eval(double inv_kappa_out, const double *s, double *table_value, double *exact_value, int n);
 int npsl_pair_math(const npsl_ctx *ctx);
+/* Shape of the pair kernel in use (rows per thread, threads per CTA) and the FP64-pipe instructions it executes per
+ * pair evaluation, as counted in the SASS of its inner loop (tools/sass_loops.py): per UNORDERED pair for the symmetric
+ * kernel, per ordered pair for k_pair. bench.py derives the executed-instruction roofline from it. */
+int npsl_pair_kernel_info(const npsl_ctx *ctx, int32_t *rows_per_thread, int32_t *threads, double *fp64_instr_per_pair);
 
 /* ---- introspection (measurement only) --------------------------------------------------- */
 

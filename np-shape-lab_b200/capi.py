@@ -26,7 +26,7 @@ SYMBOLS = [
     "npsl_download_mesh_fields", "npsl_get_thermostat", "npsl_set_thermostat", "npsl_dressup", "npsl_force_init",
     "npsl_force", "npsl_step", "npsl_energy", "npsl_sync", "npsl_launch_count", "npsl_pair_timing",
     "npsl_pair_timing_read", "npsl_owned_rows", "npsl_pair_geometry", "npsl_fp64_peak", "npsl_md_run",
-    "npsl_step_timing", "npsl_step_timing_list", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_pair_poly_eval", "npsl_pair_math", "npsl_md_step_host", "npsl_host_state", "npsl_md_step_packed", "npsl_set_pair_mode",
+    "npsl_step_timing", "npsl_step_timing_list", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_pair_poly_eval", "npsl_pair_math", "npsl_pair_kernel_info", "npsl_md_step_host", "npsl_host_state", "npsl_md_step_packed", "npsl_set_pair_mode",
     "npsl_pair_mode", "npsl_exchange_mode", "npsl_shard_plan", "npsl_vertex_geometry", "npsl_local_energies", "npsl_step_profile", "npsl_set_volume_constraint", "npsl_constraint_init",
     "npsl_constraint_multipliers", "npsl_set_ions", "npsl_download_ions", "npsl_plan_pair_units",
 ]
@@ -116,6 +116,7 @@ def load() -> C.CDLL:
     L.npsl_host_state.argtypes = [vp] + [C.POINTER(dp)] * 4
     L.npsl_pair_poly_eval.argtypes = [C.c_double, dp, dp, dp, C.c_int]
     L.npsl_pair_math.argtypes = [vp]
+    L.npsl_pair_kernel_info.argtypes = [vp, ip, ip, dp]
     L.npsl_md_step_packed.argtypes = [vp, C.c_int]
     L.npsl_set_pair_plan.argtypes = [vp, C.c_int, C.c_int]
     L.npsl_set_pair_mode.argtypes = [vp, C.c_int]
@@ -388,6 +389,11 @@ class Context:
     def md_step_packed(self, n_steps: int = 1) -> None:
         """Loop body of md_interface over the page-locked state block (npsl_md_step_packed)."""
         self._ck(self.L.npsl_md_step_packed(self.h, int(n_steps)))
+
+    def pair_kernel_info(self) -> dict:
+        r, t, f = C.c_int32(), C.c_int32(), C.c_double()
+        self._ck(self.L.npsl_pair_kernel_info(self.h, C.byref(r), C.byref(t), C.byref(f)))
+        return {"rows_per_thread": r.value, "threads": t.value, "fp64_instr_per_pair": f.value}
 
     def pair_math(self) -> int:
         """0 exact, 1 polynomial table, 2 reduced-accuracy exact scheme (npsl_pair_math)."""

@@ -2043,6 +2043,23 @@ int npsl_pair_poly_eval(double inv_kappa_out, const double *s, double *table_val
     return NPSL_OK;
 }
 
+int npsl_pair_kernel_info(const npsl_ctx *c, int32_t *rows_per_thread, int32_t *threads, double *fp64_instr_per_pair) {
+    if (!c) return NPSL_ERR_ARG;
+    if (!c->use_sym) {  // ordered kernel: SASS count of k_pair's inner loop, per ordered pair (pair_kernel.cuh)
+        if (rows_per_thread) *rows_per_thread = c->pair_rows_per_thread;
+        if (threads) *threads = kPairThreads;
+        if (fp64_instr_per_pair) *fp64_instr_per_pair = 27.0;
+        return NPSL_OK;
+    }
+    if (rows_per_thread) *rows_per_thread = c->sym_rows;
+    if (threads) *threads = c->sym_threads;
+    // per UNORDERED pair, from the SASS of the inner loops (tools/sass_loops.py): 3 sub + 3 r^2 + the radial factor
+    // (17 exact / 14 reduced accuracy / 6 table) + 2 charge products + 6 accumulations, + 3 column-accumulator adds per step
+    const double radial = c->sym_math == SYM_EXACT ? 17.0 : (c->sym_math == SYM_FAST ? 14.0 : 6.0);
+    if (fp64_instr_per_pair) *fp64_instr_per_pair = 14.0 + radial + 3.0 / c->sym_rows;
+    return NPSL_OK;
+}
+
 int npsl_pair_math(const npsl_ctx *c) {
     if (!c) return NPSL_ERR_ARG;
     return c->use_sym ? c->sym_math : SYM_EXACT;
