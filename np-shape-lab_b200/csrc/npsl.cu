@@ -1324,6 +1324,26 @@ int npsl_upload_state(npsl_ctx *c, const double *pos, const double *vel, const d
     int r;
     if ((r = upload_records(c, c->xyzq, pos, true, 0))) return r;
     if (pos) c->forces_valid = c->local_valid = false;
+    if (pos && c->use_sym && c->sym_math == SYM_FAST) {
+        // The reduced-accuracy variant of k_pair_sym evaluates 2^(-r / (lambda ln 2)) without an underflow guard: fine
+        // up to r = 700 Debye lengths. The reference's meshes have radius 1 in reduced units and lambda ~ 0.3, i.e.
+        // r / lambda < 10; a state whose extent comes anywhere near the limit is handed to the exact variant instead.
+        double lo[3] = {pos[0], pos[1], pos[2]}, hi[3] = {pos[0], pos[1], pos[2]};
+        for (int i = 1; i < n; i++)
+            for (int k = 0; k < 3; k++) {
+                lo[k] = std::min(lo[k], pos[3 * i + k]);
+                hi[k] = std::max(hi[k], pos[3 * i + k]);
+            }
+        const double extent = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
+        if (!(extent < 100.0 * c->prm.inv_kappa_out)) {
+            CU(cudaStreamSynchronize(c->s_main));
+            c->sym_math = SYM_EXACT;
+            c->sym_shape_set = false;
+            if ((r = plan_sym(c))) return r;
+            if (c->world > 1 && (r = apply_shard_plan(c))) return r;
+            drop_graph(c);
+        }
+    }
     if ((r = upload_records(c, c->vel, vel, false, 1))) return r;
     if (q) {
         CU(cudaStreamSynchronize(c->s_main));

@@ -104,17 +104,18 @@ struct SymRow {
 // stream offers ROWS independent FP64 chains (the dependent-issue latency of the FP64 pipe is ~13 cycles).
 template <int ROWS, bool DIAG, int MATH, int UNROLL>
 __device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[ROWS], const int gj0,
-                                          const double *__restrict__ sx, const double *__restrict__ sy,
-                                          const double *__restrict__ sz, const double *__restrict__ sq,
-                                          double *__restrict__ sax, double *__restrict__ say, double *__restrict__ saz,
-                                          const int lane, const double c2s, const double inv_lambda,
+                                          const double2 *__restrict__ sxy, const double2 *__restrict__ szq,
+                                          double2 *__restrict__ saxy, double *__restrict__ saz, const int lane, const double c2s, const double inv_lambda,
                                           const double *__restrict__ tab, const double2 *__restrict__ ptab, int &min_r2_hi,
                                           int &max_r2_hi) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
 #pragma unroll UNROLL
     for (int s = 0; s < 32; s++) {
         const int col = (lane + s) & 31;
-        const double xj = sx[col], yj = sy[col], zj = sz[col], qj = sq[col];
+        // the tile is held as 16-byte pairs (x,y), (z,q), (ax,ay) + az: 4 addresses and 6 shared-memory instructions per
+        // step instead of 7 and 10 for seven separate arrays (the inner loop is sensitive to every instruction)
+        const double2 xy = sxy[col], zq = szq[col];
+        const double xj = xy.x, yj = xy.y, zj = zq.x, qj = zq.y;
         double dx[ROWS], dy[ROWS], dz[ROWS], qc[ROWS], qr[ROWS], a[ROWS];
 #pragma unroll
         for (int r = 0; r < ROWS; r++) {
@@ -178,7 +179,7 @@ __device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[R
                 f[r] = fma(a[r], c2s, -(tt[r] - MAGIC));
                 const int n = __double2loint(tt[r]);
                 const double Tj = tab[n & (kExpTabFast - 1)];
-                const int k = max(n >> NPSL_EXP2FAST_TB, -1000);
+                const int k = n >> NPSL_EXP2FAST_TB;  // no underflow guard: r < 700 lambda (npsl.cu checks the extent)
                 T[r] = __hiloint2double(__double2hiint(Tj) + (k << 20), __double2loint(Tj));
             }
 #pragma unroll
@@ -240,8 +241,10 @@ __device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[R
             ay = fma(si, dy[r], ay);
             az = fma(si, dz[r], az);
         }
-        sax[col] -= ax;
-        say[col] -= ay;
+        double2 a2 = saxy[col];
+        a2.x -= ax;
+        a2.y -= ay;
+        saxy[col] = a2;
         saz[col] -= az;
         __syncwarp();
     }
@@ -254,8 +257,8 @@ __device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[R
 template <int ROWS, int THREADS, int MATH, int UNROLL>
 __device__ __forceinline__ void sym_unit(SymRow (&row)[ROWS], const int (&gi)[ROWS], const double4 *__restrict__ xyzq,
                                          double *__restrict__ colpart, const int I, const int row0, const int col_begin,
-                                         const int col_end, double *sx, double *sy, double *sz, double *sq, double *sax,
-                                         double *say, double *saz, const double *__restrict__ tab,
+                                         const int col_end, double2 *sxy, double2 *szq, double2 *saxy, double *saz,
+                                         const double *__restrict__ tab,
                                          const double2 *__restrict__ ptab, const SymParams &P, int &min_r2_hi,
                                          int &max_r2_hi) {
     constexpr int RB = ROWS * THREADS;
@@ -275,11 +278,11 @@ __device__ __forceinline__ void sym_unit(SymRow (&row)[ROWS], const int (&gi)[RO
         __syncthreads();
         if (j < col_end) {
             const double4 v = xyzq[j];
-            sx[t] = v.x * cs; sy[t] = v.y * cs; sz[t] = v.z * cs; sq[t] = v.w;
-        } else {  // padding columns: far away, no charge
-            sx[t] = (1.0e3 + t) * cs; sy[t] = 0.0; sz[t] = 0.0; sq[t] = 0.0;
+            sxy[t] = make_double2(v.x * cs, v.y * cs); szq[t] = make_double2(v.z * cs, v.w);
+        } else {  // padding columns: no charge, away from every vertex (SYM_FAST: 64 + t Debye lengths, within exp's range)
+            sxy[t] = make_double2(MATH == SYM_FAST ? 64.0 + t : 1.0e3 + t, 0.0); szq[t] = make_double2(0.0, 0.0);
         }
-        sax[t] = 0.0; say[t] = 0.0; saz[t] = 0.0;
+        saxy[t] = make_double2(0.0, 0.0); saz[t] = 0.0;
         __syncthreads();
         const bool diag = j0 < row0 + RB;
 #pragma unroll 1
@@ -289,28 +292,24 @@ __device__ __forceinline__ void sym_unit(SymRow (&row)[ROWS], const int (&gi)[RO
                 int dummy = 0;
                 if (MATH == SYM_POLY && j0 + o + 32 <= col_end) {
                     if (!diag)
-                        sym_phase<ROWS, false, SYM_POLY, UNROLL>(row, gi, j0 + o, sx + o, sy + o, sz + o, sq + o, sax + o,
-                                                                 say + o, saz + o, lane, c2s, inv_lambda, tab, ptab,
+                        sym_phase<ROWS, false, SYM_POLY, UNROLL>(row, gi, j0 + o, sxy + o, szq + o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab,
                                                                  min_r2_hi, max_r2_hi);
                     else
-                        sym_phase<ROWS, true, SYM_POLY, UNROLL>(row, gi, j0 + o, sx + o, sy + o, sz + o, sq + o, sax + o,
-                                                                say + o, saz + o, lane, c2s, inv_lambda, tab, ptab,
+                        sym_phase<ROWS, true, SYM_POLY, UNROLL>(row, gi, j0 + o, sxy + o, szq + o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab,
                                                                 min_r2_hi, max_r2_hi);
                 } else {
                     if (!diag)
-                        sym_phase<ROWS, false, EXACT, UNROLL>(row, gi, j0 + o, sx + o, sy + o, sz + o, sq + o, sax + o, say + o,
-                                                              saz + o, lane, c2s, inv_lambda, tab, ptab, min_r2_hi, dummy);
+                        sym_phase<ROWS, false, EXACT, UNROLL>(row, gi, j0 + o, sxy + o, szq + o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab, min_r2_hi, dummy);
                     else
-                        sym_phase<ROWS, true, EXACT, UNROLL>(row, gi, j0 + o, sx + o, sy + o, sz + o, sq + o, sax + o, say + o,
-                                                             saz + o, lane, c2s, inv_lambda, tab, ptab, min_r2_hi, dummy);
+                        sym_phase<ROWS, true, EXACT, UNROLL>(row, gi, j0 + o, sxy + o, szq + o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab, min_r2_hi, dummy);
                 }
             }
             __syncthreads();
         }
         if (j < col_end) {
             double *cp = colpart + (size_t) I * 3 * P.npad + j;
-            cp[0] = sax[t] * out_scale;
-            cp[P.npad] = say[t] * out_scale;
+            cp[0] = saxy[t].x * out_scale;
+            cp[P.npad] = saxy[t].y * out_scale;
             cp[2 * (size_t) P.npad] = saz[t] * out_scale;
         }
     }
@@ -329,8 +328,8 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
            double *__restrict__ colpart, int *__restrict__ lj_hit, const SymParams P) {
     constexpr int RB = ROWS * THREADS;
     extern __shared__ double2 s_ptab[];
-    __shared__ double sx[THREADS], sy[THREADS], sz[THREADS], sq[THREADS];
-    __shared__ double sax[THREADS], say[THREADS], saz[THREADS];
+    __shared__ double2 sxy[THREADS], szq[THREADS], saxy[THREADS];
+    __shared__ double saz[THREADS];
     __shared__ double s_tab[MATH == SYM_POLY ? 1 : (MATH == SYM_FAST ? kExpTabFast : kExpTab)];
     const int t = threadIdx.x;
     unsigned long long t_begin = 0;
@@ -364,15 +363,12 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
     const int col_end = min(sym_chunk_tile0(P, c + 1) * kSymCT, P.n);
 
     if (MATH == SYM_POLY) {
-        sym_unit<ROWS, THREADS, SYM_POLY, UNROLL>(row, gi, xyzq, colpart, I, row0, col_begin, col_end, sx, sy, sz, sq, sax, say,
-                                                  saz, tab, s_ptab, P, min_r2_hi, max_r2_hi);
+        sym_unit<ROWS, THREADS, SYM_POLY, UNROLL>(row, gi, xyzq, colpart, I, row0, col_begin, col_end, sxy, szq, saxy, saz, tab, s_ptab, P, min_r2_hi, max_r2_hi);
         // a pair outside the table (or a non-finite distance): the whole unit is redone exactly
         if (__syncthreads_or(min_r2_hi < kPolyHiMin || max_r2_hi >= kPolyHiMax))
-            sym_unit<ROWS, THREADS, SYM_EXACT, UNROLL>(row, gi, xyzq, colpart, I, row0, col_begin, col_end, sx, sy, sz, sq, sax,
-                                                       say, saz, tab, s_ptab, P, min_r2_hi, max_r2_hi);
+            sym_unit<ROWS, THREADS, SYM_EXACT, UNROLL>(row, gi, xyzq, colpart, I, row0, col_begin, col_end, sxy, szq, saxy, saz, tab, s_ptab, P, min_r2_hi, max_r2_hi);
     } else {
-        sym_unit<ROWS, THREADS, MATH, UNROLL>(row, gi, xyzq, colpart, I, row0, col_begin, col_end, sx, sy, sz, sq, sax, say, saz,
-                                              tab, s_ptab, P, min_r2_hi, max_r2_hi);
+        sym_unit<ROWS, THREADS, MATH, UNROLL>(row, gi, xyzq, colpart, I, row0, col_begin, col_end, sxy, szq, saxy, saz, tab, s_ptab, P, min_r2_hi, max_r2_hi);
     }
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
