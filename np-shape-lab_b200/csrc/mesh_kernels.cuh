@@ -256,15 +256,19 @@ k_kick_drift(double4 *__restrict__ xyzq, double4 *__restrict__ vel, const double
              const double *__restrict__ scal, int *__restrict__ lj_hit, double4 *const *__restrict__ peer_xyzq,
              const Xchg X, const MeshParams P, const Packed K) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *lj_hit = 0;
+    if (K.in && xchg_has(X, XK_STATE)) {  // the packed image arrives in slices, one from every rank (k_state_share)
+        if (threadIdx.x < 32) xchg_wait_own_epoch(X, XK_STATE);
+        __syncthreads();
+    }
     const int i = P.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P.row_hi) {
         const double ef = __ldcg(scal + SC_EXPFAC), kick = __ldcg(scal + SC_KICK), dt = P.dt;
         double4 v, f, x;
         if (K.in) {  // (P.nv is the plane length of the packed block)
             const double *px = K.in + 3 * (size_t) i, *pv = px + 3 * (size_t) P.nv, *pf = pv + 3 * (size_t) P.nv;
-            x = make_double4(px[0], px[1], px[2], xyzq[i].w);
-            v = make_double4(pv[0], pv[1], pv[2], 0.0);
-            f = make_double4(pf[0], pf[1], pf[2], 0.0);
+            x = make_double4(__ldcg(px), __ldcg(px + 1), __ldcg(px + 2), xyzq[i].w);
+            v = make_double4(__ldcg(pv), __ldcg(pv + 1), __ldcg(pv + 2), 0.0);
+            f = make_double4(__ldcg(pf), __ldcg(pf + 1), __ldcg(pf + 2), 0.0);
         } else {
             v = vel[i];
             f = force[i];

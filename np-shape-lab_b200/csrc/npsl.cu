@@ -128,6 +128,7 @@ struct npsl_ctx {
     // graph of its own (copy in -> the step, reading / writing the packed images -> copies out)
     double *h_state = nullptr, *d_state_in = nullptr, *d_state_out = nullptr;
     cudaGraphExec_t packed_graph = nullptr;
+    int packed_launches = 0;
     cudaStream_t s_copy = nullptr;
     cudaEvent_t ev_copy_fork = nullptr, ev_copy_join = nullptr;
     ncclComm_t comm = nullptr;
@@ -186,7 +187,8 @@ struct npsl_ctx {
     unsigned int *xtickets = nullptr;
     int *x_timed_out = nullptr;                   // set by a wait that gave up (xchg.cuh)
     int *lj_all = nullptr;                        // NCCL exchanges: every rank's collision flag
-    void *peer_map[4][kMaxRanks] = {};            // host copies of the mapped peer pointers (xyzq, fv, ke, flags)
+    void *peer_map[5][kMaxRanks] = {};            // host copies of the mapped peer pointers (xyzq, fv, ke, flags, packed image)
+    double **d_peer_state = nullptr;
     double4 **d_peer_xyzq = nullptr;
     double **d_peer_fv = nullptr, **d_peer_ke = nullptr;
     unsigned long long **d_peer_flags = nullptr;
@@ -875,8 +877,24 @@ int ensure_packed_graph(npsl_ctx *c) {
     cudaGraph_t g = nullptr;
     const size_t n3 = (size_t) 3 * c->nv;
     CU(cudaStreamBeginCapture(c->s_main, cudaStreamCaptureModeThreadLocal));
-    cudaError_t e0 = cudaMemcpyAsync(c->d_state_in, c->h_state, sizeof(double) * 3 * n3, cudaMemcpyHostToDevice, c->s_main);
+    cudaError_t e0 = cudaSuccess;
+    int extra = 0;
+    if (c->xg.on & (1 << XK_STATE)) {
+        // replicated plan over peer memory: this rank's PCIe link carries its row slice only (the reference's own row
+        // decomposition, src/main.cpp:448-455); the slices travel on over NVLink
+        const int lo = std::min(c->rank * c->range, c->nv), hi = std::min((c->rank + 1) * c->range, c->nv);
+        for (int k = 0; k < 3 && e0 == cudaSuccess && hi > lo; k++)
+            e0 = cudaMemcpyAsync(c->d_state_in + k * n3 + (size_t) 3 * lo, c->h_state + k * n3 + (size_t) 3 * lo,
+                                 sizeof(double) * 3 * (hi - lo), cudaMemcpyHostToDevice, c->s_main);
+        const int total = 9 * std::max(hi - lo, 0);
+        k_state_share<<<std::max(1, (total + 255) / 256), 256, 0, c->s_main>>>(c->d_state_in, c->d_peer_state, c->nv, lo,
+                                                                              std::max(hi, lo), c->xg);
+        extra = 1;
+    } else {
+        e0 = cudaMemcpyAsync(c->d_state_in, c->h_state, sizeof(double) * 3 * n3, cudaMemcpyHostToDevice, c->s_main);
+    }
     int n = e0 == cudaSuccess ? issue(c, true, false, false, false, true) : -1;
+    if (n >= 0) n += extra;
     if (n >= 0) {
         cudaStreamWaitEvent(c->s_main, c->ev_copy_join, 0);
         e0 = cudaMemcpyAsync(c->h_state + n3, c->d_state_out + n3, sizeof(double) * (2 * n3 + 1), cudaMemcpyDeviceToHost, c->s_main);
@@ -890,6 +908,7 @@ int ensure_packed_graph(npsl_ctx *c) {
     e = cudaGraphInstantiateWithFlags(&c->packed_graph, g, cudaGraphInstantiateFlagUseNodePriority);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) return fail(c, NPSL_ERR_CUDA, "packed graph instantiate: %s", cudaGetErrorString(e));
+    c->packed_launches = n;
     return 0;
 }
 
@@ -990,12 +1009,16 @@ int setup_p2p(npsl_ctx *c) {
     CU(dalloc(&c->xstate, 2 * XK_KINDS));
     CU(dalloc(&c->xtickets, XK_KINDS));
     CU(dalloc(&c->x_timed_out, 1));
-    struct Handles { cudaIpcMemHandle_t h[4]; int ok; int pad[15]; };
+    {  // the packed image of npsl_md_step_packed is shared slice by slice (k_state_share): it has to exist before the mapping
+        int r = ensure_packed_buffers(c);
+        if (r) return r;
+    }
+    struct Handles { cudaIpcMemHandle_t h[5]; int ok; int pad[15]; };
     Handles mine;
     memset(&mine, 0, sizeof mine);
-    void *bufs[4] = {c->xyzq, c->sym_fv, c->ke_warp, c->xflags};
+    void *bufs[5] = {c->xyzq, c->sym_fv, c->ke_warp, c->xflags, c->d_state_in};
     mine.ok = 1;
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < 5; k++)
         if (cudaIpcGetMemHandle(&mine.h[k], bufs[k]) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
     Handles *d_all = nullptr;
     CU(dalloc(&d_all, c->world));
@@ -1008,7 +1031,7 @@ int setup_p2p(npsl_ctx *c) {
     bool ok = true;
     for (int r = 0; r < c->world; r++) ok = ok && all[r].ok;
     for (int r = 0; r < c->world && ok; r++)
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 5; k++) {
             if (r == c->rank) { c->peer_map[k][r] = bufs[k]; continue; }
             if (cudaIpcOpenMemHandle(&c->peer_map[k][r], all[r].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 ok = false;
@@ -1035,6 +1058,8 @@ int setup_p2p(npsl_ctx *c) {
     CU(cudaMemcpy(c->d_peer_fv, c->peer_map[1], sizeof(void *) * c->world, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_peer_ke, c->peer_map[2], sizeof(void *) * c->world, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_peer_flags, c->peer_map[3], sizeof(void *) * c->world, cudaMemcpyHostToDevice));
+    CU(dalloc(&c->d_peer_state, c->world));
+    CU(cudaMemcpy(c->d_peer_state, c->peer_map[4], sizeof(void *) * c->world, cudaMemcpyHostToDevice));
     c->xg.peer_flags = c->d_peer_flags; c->xg.state = c->xstate; c->xg.tickets = c->xtickets;
     c->xg.timed_out = c->x_timed_out;
     c->p2p = true;
@@ -1066,7 +1091,7 @@ int apply_shard_plan(npsl_ctx *c) {
     c->pp.row_lo = c->ljp.row_lo = c->mp.row_lo = c->row_lo;
     c->pp.row_hi = c->ljp.row_hi = c->mp.row_hi = c->row_hi;
     c->mp.n_ranks = c->replicated ? 1 : c->world;
-    c->xg.on = !c->p2p ? 0 : (c->replicated ? (1 << XK_FV) : (1 << XK_POS) | (1 << XK_FV) | (1 << XK_KE));
+    c->xg.on = !c->p2p ? 0 : (c->replicated ? (1 << XK_FV) | (1 << XK_STATE) : (1 << XK_POS) | (1 << XK_FV) | (1 << XK_KE));
     c->xg.fv_bcast = c->replicated ? 1 : 0;
     c->xg.cta_fence_sys = 0;
     if (const char *e = getenv("NPSL_CTA_FENCE_SYS")) c->xg.cta_fence_sys = atoi(e) ? 1 : 0;  // measurement knob
@@ -1287,7 +1312,7 @@ void npsl_destroy(npsl_ctx *c) {
     if (c->d_state_out) cudaFree(c->d_state_out);
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
     for (auto &e : c->pinned_user) cudaHostUnregister(e.first);
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < 5; k++)
         for (int r = 0; r < kMaxRanks; r++)
             if (c->peer_map[k][r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_map[k][r]);
     for (cudaEvent_t e : c->t_ev) cudaEventDestroy(e);
@@ -1303,7 +1328,7 @@ void npsl_destroy(npsl_ctx *c) {
                     c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_warp, c->th_cur, c->th_mid, c->part_mesh,
                     c->part_vert, c->tickets, c->ion_xyzq, c->ion_vel, c->ion_force, c->ion_mesh, c->ion_e, c->ion_mesh_lj, c->ion_part, c->edge_E, c->vertex_e, c->face_e, c->face_local, c->vertex_geo, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units, c->red_groups, c->pair_ptab,
                     c->sym_rowpart, c->sym_colpart, c->sym_fv, c->xflags, c->xstate, c->xtickets, c->x_timed_out, c->lj_all,
-                    c->d_peer_xyzq, c->d_peer_fv, c->d_peer_ke, c->d_peer_flags};
+                    c->d_peer_xyzq, c->d_peer_fv, c->d_peer_ke, c->d_peer_flags, c->d_peer_state};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -1648,7 +1673,7 @@ int npsl_md_step_packed(npsl_ctx *c, int n_steps) {
     if (n_steps == 1 && packed_fused_ok(c)) {
         if ((r = ensure_packed_graph(c))) return r;
         CU(cudaGraphLaunch(c->packed_graph, c->s_main));
-        c->launches += c->launches_per_step;
+        c->launches += c->packed_launches;
         CU(cudaStreamSynchronize(c->s_main));
         CU(cudaGetLastError());
         return NPSL_OK;

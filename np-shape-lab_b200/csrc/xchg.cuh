@@ -24,8 +24,9 @@
 namespace npsl {
 
 constexpr int kMaxRanks = 8;
-// XK_LJ0 / XK_LJ1: the two parities of the collision-flag exchange (k_lj_flag); never part of Xchg::on
-enum { XK_POS = 0, XK_FV = 1, XK_KE = 2, XK_LJ0 = 3, XK_LJ1 = 4, XK_KINDS = 5 };
+// XK_LJ0 / XK_LJ1: the two parities of the collision-flag exchange (k_lj_flag); never part of Xchg::on.
+// XK_STATE: the packed host state of npsl_md_step_packed, every rank uploads its own row slice and shares it.
+enum { XK_POS = 0, XK_FV = 1, XK_KE = 2, XK_LJ0 = 3, XK_LJ1 = 4, XK_STATE = 5, XK_KINDS = 6 };
 constexpr unsigned long long kXchgTimeoutNs = 30ull * 1000000000ull;  // a wait that long means a peer is gone
 
 struct Xchg {
@@ -150,6 +151,23 @@ __global__ void k_lj_flag(const Xchg X, int *__restrict__ lj_hit) {
         *lj_hit = hit ? 1 : 0;
         X.state[XK_LJ0] = e;
     }
+}
+
+// Packed host state (npsl_md_step_packed on a replicated-plan context): every rank has copied only ITS row slice
+// [lo, hi) of posvec / velvec / forvec from its host block into its packed device image; this kernel stores the slice
+// into every peer's image over NVLink, so that each PCIe link carries 1 / world of the state instead of all of it.
+// image = [pos | vel | force], n vertices each; one thread per double of the slice.
+__global__ void __launch_bounds__(256)
+k_state_share(const double *__restrict__ image, double *const *__restrict__ peer_image, int n, int lo, int hi, const Xchg X) {
+    const int len = 3 * (hi - lo);
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < 3 * len) {
+        const size_t off = (size_t) (k / len) * 3 * n + (size_t) 3 * lo + (k % len);
+        const double v = image[off];
+        for (int r = 0; r < X.world; r++)
+            if (r != X.rank) peer_image[r][off] = v;
+    }
+    xchg_signal(X, XK_STATE, gridDim.x);
 }
 
 // NCCL exchanges: the flags of all ranks were all-gathered into all[world]
