@@ -385,23 +385,32 @@ void sym_geometry(int nv, int rb, SymParams &sp) {
     sp.n = nv;
     sp.npad = (nv + kSymPad - 1) / kSymPad * kSymPad;
     sp.rb = rb;
-    // 256 columns per unit up to 32768 vertices, at most 256 chunks beyond: fine-grained enough to fill 8 GPUs
+    // 256 columns per unit up to 65536 vertices, at most 256 such chunks beyond: fine-grained enough to fill 8 GPUs
     sp.chunk_tiles = std::max(256 / kSymCT, (nv + 256 * kSymCT - 1) / (256 * kSymCT));
     if (const char *e = getenv("NPSL_SYM_CHUNK_TILES"))  // measurement knob; changes the grouping of the row sums
         if (atoi(e) > 0) sp.chunk_tiles = atoi(e);
     const int n_tiles = (nv + kSymCT - 1) / kSymCT;
-    // The last quarter of the column range is cut into half-width chunks. Units are launched heaviest first, so
-    // these run last and halve the raggedness at the end of the launch (each rank of an 8-GPU job has fewer than
-    // two waves of full units at S64). A function of the vertex count only, like everything else here.
-    int fine_pct = 25;
-    if (const char *e = getenv("NPSL_SYM_FINE_PCT")) fine_pct = std::max(0, std::min(100, atoi(e)));  // measurement knob
+    // The column range ends in narrower chunks: half width over its last quarter, of which the last part a quarter
+    // width (one 64-column tile at S64). Units are launched heaviest first, so these run last and even out the ragged
+    // end of the launch: a rank of an 8-GPU job at S64 has about seven tiles of work per resident CTA, a full-width unit is
+    // four. A function of the vertex count only, like everything else here.
+    int fine_pct = 25, finest_pct = 5;
+    if (const char *e = getenv("NPSL_SYM_FINE_PCT")) fine_pct = std::max(0, std::min(100, atoi(e)));      // measurement knobs
+    if (const char *e = getenv("NPSL_SYM_FINEST_PCT")) finest_pct = std::max(0, std::min(100, atoi(e)));
+    finest_pct = std::min(finest_pct, fine_pct);
     sp.fine_tiles = std::max(1, sp.chunk_tiles / 2);
-    if (const char *e = getenv("NPSL_SYM_FINE_TILES"))  // measurement knob
+    sp.finest_tiles = std::max(1, sp.chunk_tiles / 4);
+    if (const char *e = getenv("NPSL_SYM_FINE_TILES"))
         if (atoi(e) > 0) sp.fine_tiles = atoi(e);
+    if (const char *e = getenv("NPSL_SYM_FINEST_TILES"))
+        if (atoi(e) > 0) sp.finest_tiles = atoi(e);
     const int coarse_tiles = n_tiles - (int) ((long) n_tiles * fine_pct / 100);
     sp.n_coarse = fine_pct >= 100 ? 0 : (coarse_tiles + sp.chunk_tiles - 1) / sp.chunk_tiles;
     const int rest = std::max(0, n_tiles - sp.n_coarse * sp.chunk_tiles);
-    sp.n_chunks = sp.n_coarse + (rest + sp.fine_tiles - 1) / sp.fine_tiles;
+    const int finest_rest = std::min(rest, (int) ((long) n_tiles * finest_pct / 100));
+    sp.n_fine = finest_pct >= 100 ? 0 : (rest - finest_rest + sp.fine_tiles - 1) / sp.fine_tiles;
+    const int rest2 = std::max(0, rest - sp.n_fine * sp.fine_tiles);
+    sp.n_chunks = sp.n_coarse + sp.n_fine + (rest2 + sp.finest_tiles - 1) / sp.finest_tiles;
 }
 
 // Radial factor of the screened-Coulomb force, G(s) = e^{-r/lambda} (1/r^3 + 1/(lambda r^2)), r = sqrt(s), in

@@ -2,7 +2,7 @@
 // FP64, sm_100a. Force-only twin of k_pair (pair_kernel.cuh) for the per-step path; it replaces the
 // same reference loop (src/newforces.cpp:153-177), which walks all N(N-1) ordered pairs.
 //
-// Work unit = (row block I of ROWS x THREADS rows) x (column chunk c of chunk_tiles x 128 columns); a unit exists
+// Work unit = (row block I of ROWS x THREADS rows) x (column chunk c of chunk_tiles x 64 columns); a unit exists
 // when the chunk reaches past the start of the row block, and it covers the pairs (i,j), i in I, j in c,
 // j > i. Each thread keeps ROWS rows in registers (position, charge, force accumulator). A THREADS-column tile is
 // staged in shared memory (SoA) together with one force accumulator per column. Within a tile the
@@ -35,7 +35,6 @@ namespace npsl {
 enum { SYM_EXACT = 0, SYM_POLY = 1, SYM_FAST = 2 };
 constexpr int kExpTabFast = 1 << NPSL_EXP2FAST_TB;
 __device__ const double c_exp2_tab_fast[kExpTabFast] = {NPSL_EXP2FAST_TABLE};
-
 constexpr int kSymPad = 512;  // partial-buffer planes are padded to a multiple of this
 constexpr int kSymV = 8;      // virtual ranks (fixed grouping of the units)
 
@@ -44,9 +43,11 @@ struct SymParams {
     int n;            // vertices
     int npad;         // plane length of the partial buffers (>= n, multiple of kSymPad)
     int rb;           // rows per row block = threads per CTA x rows per thread
-    int chunk_tiles;  // 128-column tiles per column chunk (the first n_coarse chunks)
-    int n_coarse;     // chunks [n_coarse, n_chunks) at the high end of the column range are fine_tiles wide: smaller
-    int fine_tiles;   //   units that are scheduled last and even out the tail of the launch
+    int chunk_tiles;  // kSymCT-column tiles per column chunk (the first n_coarse chunks)
+    int n_coarse;     // chunks [n_coarse, n_coarse + n_fine) further up the column range are fine_tiles wide, the chunks
+    int fine_tiles;   //   [n_coarse + n_fine, n_chunks) at its high end finest_tiles wide: smaller units that are
+    int n_fine;       //   scheduled last and even out the tail of the launch
+    int finest_tiles;
     int n_chunks;
     int lj_cut_hi;
     const double2 *ptab;  // piecewise-polynomial table of the radial factor (kPoly* below), null: exact evaluation only
@@ -69,15 +70,19 @@ constexpr int kPolyShift = 20 - kPolyBits;          // interval index = (high wo
 constexpr int kPolyBase = (1023 + kPolyEmin) << kPolyBits;
 constexpr int kPolyHiMin = kPolyBase << kPolyShift; // high words of the covered range [min, max)
 constexpr int kPolyHiMax = (kPolyBase + kPolyCount) << kPolyShift;
-constexpr int kSymCT = 128;   // granularity of the column chunks (the kernels' column tile is THREADS wide)
+constexpr int kSymCT = 64;    // granularity of the column chunks (the kernels' column tile is THREADS wide)
 // first tile of chunk c (c == n_chunks: one past the last tile, before clamping to the vertex count)
 __host__ __device__ __forceinline__ int sym_chunk_tile0(const SymParams &P, const int c) {
-    return c <= P.n_coarse ? c * P.chunk_tiles : P.n_coarse * P.chunk_tiles + (c - P.n_coarse) * P.fine_tiles;
+    if (c <= P.n_coarse) return c * P.chunk_tiles;
+    const int t1 = P.n_coarse * P.chunk_tiles, c1 = c - P.n_coarse;
+    return c1 <= P.n_fine ? t1 + c1 * P.fine_tiles : t1 + P.n_fine * P.fine_tiles + (c1 - P.n_fine) * P.finest_tiles;
 }
 // chunk that holds tile t
 __host__ __device__ __forceinline__ int sym_chunk_of_tile(const SymParams &P, const int t) {
-    const int tc = P.n_coarse * P.chunk_tiles;
-    return t < tc ? t / P.chunk_tiles : P.n_coarse + (t - tc) / P.fine_tiles;
+    const int t1 = P.n_coarse * P.chunk_tiles;
+    if (t < t1) return t / P.chunk_tiles;
+    const int t2 = t1 + P.n_fine * P.fine_tiles;
+    return t < t2 ? P.n_coarse + (t - t1) / P.fine_tiles : P.n_coarse + P.n_fine + (t - t2) / P.finest_tiles;
 }
 
 // e^{-r/lambda} (1/r^3 + 1/(lambda r^2)) of one pair; d = x_i - x_j
@@ -179,8 +184,10 @@ __device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[R
                 f[r] = fma(a[r], c2s, -(tt[r] - MAGIC));
                 const int n = __double2loint(tt[r]);
                 const double Tj = tab[n & (kExpTabFast - 1)];
-                const int k = n >> NPSL_EXP2FAST_TB;  // no underflow guard: r < 700 lambda (npsl.cu checks the extent)
-                T[r] = __hiloint2double(__double2hiint(Tj) + (k << 20), __double2loint(Tj));
+                // exponent k = n >> TB added on the integer pipe in ONE multiply-add: the staged table holds the high word of
+                // 2^(j/2^TB) minus j << (20 - TB) (k_pair_sym), so  hi + (n << (20 - TB)) = hi(2^(j/2^TB)) + (k << 20).
+                // No underflow guard: r < 700 lambda (npsl.cu checks the extent)
+                T[r] = __hiloint2double(__double2hiint(Tj) + n * (1 << (20 - NPSL_EXP2FAST_TB)), __double2loint(Tj));
             }
 #pragma unroll
             for (int r = 0; r < ROWS; r++) b[r] = fma(f[r], NPSL_EXP2FAST_G2, NPSL_EXP2FAST_G1);
@@ -339,7 +346,10 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
         for (int k = t; k < 3 * kPolyCount; k += THREADS) s_ptab[k] = __ldg(P.ptab + k);
         tab = c_exp2_tab;
     } else if (MATH == SYM_FAST) {
-        for (int k = t; k < kExpTabFast; k += THREADS) s_tab[k] = c_exp2_tab_fast[k];
+        for (int k = t; k < kExpTabFast; k += THREADS) {  // see sym_phase: the high words are biased by the index
+            const double T = c_exp2_tab_fast[k];
+            s_tab[k] = __hiloint2double(__double2hiint(T) - (k << (20 - NPSL_EXP2FAST_TB)), __double2loint(T));
+        }
     } else {
         for (int k = t; k < kExpTab; k += THREADS) s_tab[k] = c_exp2_tab[k];
     }
