@@ -160,6 +160,7 @@ struct npsl_ctx {
     int sym_n_units = 0, sym_n_units_total = 0, sym_v_first = 0, sym_v_count = kSymV;
     int *red_groups = nullptr;  // k_pair_reduce: vertex groups of the CTAs (rows + columns first, then columns only)
     int red_n_a = 0, red_n_b_groups = 0, red_n_b_ctas = 0;
+    double *pair_etab = nullptr;   // SYM_FAST: index-biased table of the exponential (pair_sym_kernel.cuh), device copy
     double2 *pair_ptab = nullptr;  // piecewise-polynomial table of the radial factor (pair_sym_kernel.cuh), device copy
     int sym_math = SYM_FAST;       // how k_pair_sym evaluates the radial factor (pair_sym_kernel.cuh); NPSL_SYM_MATH
     bool sym_shape_set = false;    // rows / threads chosen through npsl_set_pair_plan
@@ -510,6 +511,20 @@ int plan_sym(npsl_ctx *c) {
         CU(cudaMemcpy(c->pair_ptab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     }
     sp.ptab = c->pair_ptab;
+    if (!c->pair_etab) {  // SYM_FAST: the exponential's table with the index folded into the high words (pair_sym_kernel.cuh)
+        static const double tab[kExpTabFast] = {NPSL_EXP2FAST_TABLE};
+        std::vector<double> biased(kExpTabFast);
+        for (int k = 0; k < kExpTabFast; k++) {
+            uint64_t bits;
+            memcpy(&bits, &tab[k], 8);
+            bits -= (uint64_t) k << (32 + 20 - NPSL_EXP2FAST_TB);  // high word - (k << (20 - TB)), no borrow into it from below
+            memcpy(&biased[k], &bits, 8);
+        }
+        CU(dalloc(&c->pair_etab, biased.size()));
+        CU(cudaMemcpy(c->pair_etab, biased.data(), sizeof(double) * biased.size(), cudaMemcpyHostToDevice));
+    }
+    sp.etab = c->pair_etab;
+    sp.fast_c2s = -1.4426950408889634074 * (double) kExpTabFast; sp.fast_g1 = NPSL_EXP2FAST_G1; sp.fast_g2 = NPSL_EXP2FAST_G2;
 
     const int n_rb = (nv + sp.rb - 1) / sp.rb;
     const bool want = c->pair_mode == 2 || (c->pair_mode == 0 && nv >= 4096);
@@ -718,7 +733,6 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair, bool 
                 case KEY(SYM_EXACT, 1, 2, 256, 0): SYM_LAUNCH(2, 256, 3, SYM_EXACT, 1, 0); break;
                 case KEY(SYM_EXACT, 1, 2, 128, 0): SYM_LAUNCH(2, 128, 6, SYM_EXACT, 1, 0); break;
                 case KEY(SYM_EXACT, 1, 2, 128, 1): SYM_LAUNCH(2, 128, 8, SYM_EXACT, 1, 0); break;
-                case KEY(SYM_EXACT, 1, 1, 512, 0): SYM_LAUNCH(1, 512, 2, SYM_EXACT, 1, 0); break;
                 case KEY(SYM_EXACT, 1, 1, 256, 0): SYM_LAUNCH(1, 256, 4, SYM_EXACT, 1, 0); break;
                 case KEY(SYM_EXACT, 1, 1, 128, 0): SYM_LAUNCH(1, 128, 8, SYM_EXACT, 1, 0); break;
                 default:
@@ -1335,7 +1349,7 @@ void npsl_destroy(npsl_ctx *c) {
     void *ptrs[] = {c->xyzq, c->vel, c->force, c->fmesh, c->ngv, c->part_con, c->comp[0], c->comp[1], c->comp[2], c->comp[3], c->comp[4], c->face_v,
                     c->edge_rec, c->l0, c->degree, c->ring, c->bslot_ref, c->ring_l0, c->bslot, c->pair_partial,
                     c->lj_out, c->lj_hit, c->scal, c->scal_all, c->ke_warp, c->th_cur, c->th_mid, c->part_mesh,
-                    c->part_vert, c->tickets, c->ion_xyzq, c->ion_vel, c->ion_force, c->ion_mesh, c->ion_e, c->ion_mesh_lj, c->ion_part, c->edge_E, c->vertex_e, c->face_e, c->face_local, c->vertex_geo, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units, c->red_groups, c->pair_ptab,
+                    c->part_vert, c->tickets, c->ion_xyzq, c->ion_vel, c->ion_force, c->ion_mesh, c->ion_e, c->ion_mesh_lj, c->ion_part, c->edge_E, c->vertex_e, c->face_e, c->face_local, c->vertex_geo, c->face_dir_area, c->face_vol, c->edge_S, c->peak_out, c->sym_units, c->red_groups, c->pair_ptab, c->pair_etab,
                     c->sym_rowpart, c->sym_colpart, c->sym_fv, c->xflags, c->xstate, c->xtickets, c->x_timed_out, c->lj_all,
                     c->d_peer_xyzq, c->d_peer_fv, c->d_peer_ke, c->d_peer_flags, c->d_peer_state};
     for (void *p : ptrs)
@@ -2108,9 +2122,10 @@ int npsl_pair_kernel_info(const npsl_ctx *c, int32_t *rows_per_thread, int32_t *
     if (rows_per_thread) *rows_per_thread = c->sym_rows;
     if (threads) *threads = c->sym_threads;
     // per UNORDERED pair, from the SASS of the inner loops (tools/sass_loops.py): 3 sub + 3 r^2 + the radial factor
-    // (17 exact / 14 reduced accuracy / 6 table) + 2 charge products + 6 accumulations, + 3 column-accumulator adds per step
+    // (17 exact / 14 reduced accuracy / 6 table) + 2 charge products + 6 accumulations (the column accumulators travel
+    // through registers, no separate adds)
     const double radial = c->sym_math == SYM_EXACT ? 17.0 : (c->sym_math == SYM_FAST ? 14.0 : 6.0);
-    if (fp64_instr_per_pair) *fp64_instr_per_pair = 14.0 + radial + 3.0 / c->sym_rows;
+    if (fp64_instr_per_pair) *fp64_instr_per_pair = 14.0 + radial;
     return NPSL_OK;
 }
 

@@ -34,7 +34,6 @@ namespace npsl {
 //              (3.2e-13): 28.75 per pair, relative error of the factor < 1e-12 against a contract of 1e-10.
 enum { SYM_EXACT = 0, SYM_POLY = 1, SYM_FAST = 2 };
 constexpr int kExpTabFast = 1 << NPSL_EXP2FAST_TB;
-__device__ const double c_exp2_tab_fast[kExpTabFast] = {NPSL_EXP2FAST_TABLE};
 constexpr int kSymPad = 512;  // partial-buffer planes are padded to a multiple of this
 constexpr int kSymV = 8;      // virtual ranks (fixed grouping of the units)
 
@@ -50,6 +49,9 @@ struct SymParams {
     int finest_tiles;
     int n_chunks;
     int lj_cut_hi;
+    double fast_c2s, fast_g1, fast_g2;  // SYM_FAST: -log2(e) 2^TB and the quadratic of exp2_table_fast.inc, as kernel
+                                        //   parameters so that they are constant-bank operands, not registers
+    const double *etab;   // SYM_FAST: 2^(j/2^TB) with the high words biased by the index (k_pair_sym), 16-byte aligned
     const double2 *ptab;  // piecewise-polynomial table of the radial factor (kPoly* below), null: exact evaluation only
     unsigned long long *trace;  // measurement only (NPSL_SYM_TRACE): per CTA {SM id, start ns, end ns}, else null
 };
@@ -112,14 +114,21 @@ __device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[R
                                           const double2 *__restrict__ sxy, const double2 *__restrict__ szq,
                                           double2 *__restrict__ saxy, double *__restrict__ saz, const int lane, const double c2s, const double inv_lambda,
                                           const double *__restrict__ tab, const double2 *__restrict__ ptab, int &min_r2_hi,
-                                          int &max_r2_hi) {
+                                          int &max_r2_hi, const double g1 = 0.0, const double g2 = 0.0) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+    const unsigned tab32 = (unsigned) __cvta_generic_to_shared(tab);
+    // The accumulator of the column a lane visits lives in registers and travels with the column: after its step the
+    // lane hands it to lane - 1, which visits that column next (3 x 2 shuffles per step instead of two loads, two stores,
+    // their addresses, three subtractions and a warp barrier). After the 32 steps lane l holds the sum of column l.
+    double cax = 0.0, cay = 0.0, caz = 0.0;
+    const int from = (lane + 1) & 31;
+    // the group's 32 columns are staged twice in a row (entries [0, 63)), so that column (lane + s) mod 32 is entry
+    // lane + s: one running address, no wrap-around arithmetic (every non-FP64 instruction of this loop costs a dispatch
+    // slot of the FP64-bound sub-partition)
+    const double2 *pxy = sxy + lane, *pzq = szq + lane;
 #pragma unroll UNROLL
     for (int s = 0; s < 32; s++) {
-        const int col = (lane + s) & 31;
-        // the tile is held as 16-byte pairs (x,y), (z,q), (ax,ay) + az: 4 addresses and 6 shared-memory instructions per
-        // step instead of 7 and 10 for seven separate arrays (the inner loop is sensitive to every instruction)
-        const double2 xy = sxy[col], zq = szq[col];
+        const double2 xy = pxy[s], zq = pzq[s];
         const double xj = xy.x, yj = xy.y, zj = zq.x, qj = zq.y;
         double dx[ROWS], dy[ROWS], dz[ROWS], qc[ROWS], qr[ROWS], a[ROWS];
 #pragma unroll
@@ -128,7 +137,7 @@ __device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[R
             qc[r] = qj;
             qr[r] = row[r].q;
             if (DIAG) {  // inside the row block: count (i,j) once, j > i; everything else contributes exactly zero
-                const bool on = (gj0 + col) > gi[r];
+                const bool on = (gj0 + ((lane + s) & 31)) > gi[r];
                 cx = on ? xj : row[r].x - 1.0;  // keeps r finite for the self pair
                 qc[r] = on ? qj : 0.0;
                 qr[r] = on ? qr[r] : 0.0;
@@ -183,14 +192,19 @@ __device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[R
             for (int r = 0; r < ROWS; r++) {
                 f[r] = fma(a[r], c2s, -(tt[r] - MAGIC));
                 const int n = __double2loint(tt[r]);
-                const double Tj = tab[n & (kExpTabFast - 1)];
+                // entry n mod 2^TB: one and, one multiply-add for the shared-memory address (left to itself the compiler
+                // shifts, masks and then adds the table's base: every integer instruction here costs a dispatch slot)
+                double Tj;
+                unsigned addr;
+                asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(n & (kExpTabFast - 1)), "r"(tab32));
+                asm("ld.shared.f64 %0, [%1];" : "=d"(Tj) : "r"(addr));
                 // exponent k = n >> TB added on the integer pipe in ONE multiply-add: the staged table holds the high word of
                 // 2^(j/2^TB) minus j << (20 - TB) (k_pair_sym), so  hi + (n << (20 - TB)) = hi(2^(j/2^TB)) + (k << 20).
                 // No underflow guard: r < 700 lambda (npsl.cu checks the extent)
                 T[r] = __hiloint2double(__double2hiint(Tj) + n * (1 << (20 - NPSL_EXP2FAST_TB)), __double2loint(Tj));
             }
 #pragma unroll
-            for (int r = 0; r < ROWS; r++) b[r] = fma(f[r], NPSL_EXP2FAST_G2, NPSL_EXP2FAST_G1);
+            for (int r = 0; r < ROWS; r++) b[r] = fma(f[r], g2, g1);
 #pragma unroll
             for (int r = 0; r < ROWS; r++) {
                 const double ex = fma(T[r], f[r] * b[r], T[r]);
@@ -237,24 +251,27 @@ __device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[R
                 a[r] = ex * w;  // e^{-r/lambda} (1/r^3 + 1/(lambda r^2))
             }
         }
-        double ax = 0.0, ay = 0.0, az = 0.0;
 #pragma unroll
         for (int r = 0; r < ROWS; r++) {
             const double sj = qc[r] * a[r], si = qr[r] * a[r];
             row[r].fx = fma(sj, dx[r], row[r].fx);
             row[r].fy = fma(sj, dy[r], row[r].fy);
             row[r].fz = fma(sj, dz[r], row[r].fz);
-            ax = fma(si, dx[r], ax);
-            ay = fma(si, dy[r], ay);
-            az = fma(si, dz[r], az);
+            cax = fma(si, dx[r], cax);
+            cay = fma(si, dy[r], cay);
+            caz = fma(si, dz[r], caz);
         }
-        double2 a2 = saxy[col];
-        a2.x -= ax;
-        a2.y -= ay;
-        saxy[col] = a2;
-        saz[col] -= az;
-        __syncwarp();
+        cax = __shfl_sync(0xffffffffu, cax, from);
+        cay = __shfl_sync(0xffffffffu, cay, from);
+        caz = __shfl_sync(0xffffffffu, caz, from);
     }
+    // the force on column j is minus the sum over the rows; the group's accumulators in shared memory collect the
+    // phases of the tile (one warp per group and phase, __syncthreads between the phases)
+    double2 a2 = saxy[lane];
+    a2.x -= cax;
+    a2.y -= cay;
+    saxy[lane] = a2;
+    saz[lane] -= caz;
 }
 
 // One pass over the column tiles of a unit. POLY: groups of 32 columns that are entirely real take the polynomial
@@ -276,18 +293,24 @@ __device__ __forceinline__ void sym_unit(SymRow (&row)[ROWS], const int (&gi)[RO
     const double inv_lambda = P.inv_lambda;
     // SYM_FAST works in units of lambda: the exponent scale no longer carries 1/lambda, the partial sums come out
     // lambda^2 too large (d and the radial factor scale by 1/lambda and lambda^3)
-    const double c2s = MATH == SYM_FAST ? -1.4426950408889634074 * (double) kExpTabFast : P.c2s;
+    const double c2s = MATH == SYM_FAST ? P.fast_c2s : P.c2s;
     const double cs = MATH == SYM_FAST ? inv_lambda : 1.0, out_scale = MATH == SYM_FAST ? inv_lambda * inv_lambda : 1.0;
 #pragma unroll
     for (int r = 0; r < ROWS; r++) row[r].fx = row[r].fy = row[r].fz = 0.0;
     for (int j0 = col_begin; j0 < col_end; j0 += THREADS) {
         const int j = j0 + t;
         __syncthreads();
-        if (j < col_end) {
-            const double4 v = xyzq[j];
-            sxy[t] = make_double2(v.x * cs, v.y * cs); szq[t] = make_double2(v.z * cs, v.w);
-        } else {  // padding columns: no charge, away from every vertex (SYM_FAST: 64 + t Debye lengths, within exp's range)
-            sxy[t] = make_double2(MATH == SYM_FAST ? 64.0 + t : 1.0e3 + t, 0.0); szq[t] = make_double2(0.0, 0.0);
+        {
+            double2 cxy, czq;
+            if (j < col_end) {
+                const double4 v = xyzq[j];
+                cxy = make_double2(v.x * cs, v.y * cs); czq = make_double2(v.z * cs, v.w);
+            } else {  // padding columns: no charge, away from every vertex (SYM_FAST: 64 + t Debye lengths, within exp's range)
+                cxy = make_double2(MATH == SYM_FAST ? 64.0 + t : 1.0e3 + t, 0.0); czq = make_double2(0.0, 0.0);
+            }
+            const int e = (t >> 5) * 64 + (t & 31);  // every group of 32 columns twice in a row (sym_phase)
+            sxy[e] = cxy; szq[e] = czq;
+            sxy[e + 32] = cxy; szq[e + 32] = czq;
         }
         saxy[t] = make_double2(0.0, 0.0); saz[t] = 0.0;
         __syncthreads();
@@ -299,16 +322,16 @@ __device__ __forceinline__ void sym_unit(SymRow (&row)[ROWS], const int (&gi)[RO
                 int dummy = 0;
                 if (MATH == SYM_POLY && j0 + o + 32 <= col_end) {
                     if (!diag)
-                        sym_phase<ROWS, false, SYM_POLY, UNROLL>(row, gi, j0 + o, sxy + o, szq + o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab,
+                        sym_phase<ROWS, false, SYM_POLY, UNROLL>(row, gi, j0 + o, sxy + 2 * o, szq + 2 * o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab,
                                                                  min_r2_hi, max_r2_hi);
                     else
-                        sym_phase<ROWS, true, SYM_POLY, UNROLL>(row, gi, j0 + o, sxy + o, szq + o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab,
+                        sym_phase<ROWS, true, SYM_POLY, UNROLL>(row, gi, j0 + o, sxy + 2 * o, szq + 2 * o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab,
                                                                 min_r2_hi, max_r2_hi);
                 } else {
                     if (!diag)
-                        sym_phase<ROWS, false, EXACT, UNROLL>(row, gi, j0 + o, sxy + o, szq + o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab, min_r2_hi, dummy);
+                        sym_phase<ROWS, false, EXACT, UNROLL>(row, gi, j0 + o, sxy + 2 * o, szq + 2 * o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab, min_r2_hi, dummy, P.fast_g1, P.fast_g2);
                     else
-                        sym_phase<ROWS, true, EXACT, UNROLL>(row, gi, j0 + o, sxy + o, szq + o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab, min_r2_hi, dummy);
+                        sym_phase<ROWS, true, EXACT, UNROLL>(row, gi, j0 + o, sxy + 2 * o, szq + 2 * o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab, min_r2_hi, dummy, P.fast_g1, P.fast_g2);
                 }
             }
             __syncthreads();
@@ -335,9 +358,17 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
            double *__restrict__ colpart, int *__restrict__ lj_hit, const SymParams P) {
     constexpr int RB = ROWS * THREADS;
     extern __shared__ double2 s_ptab[];
-    __shared__ double2 sxy[THREADS], szq[THREADS], saxy[THREADS];
-    __shared__ double saz[THREADS];
-    __shared__ double s_tab[MATH == SYM_POLY ? 1 : (MATH == SYM_FAST ? kExpTabFast : kExpTab)];
+    // one block of static shared memory with the exponential's table first: its entries sit at compile-time offsets
+    struct __align__(16) Smem {
+        double tab[MATH == SYM_POLY ? 2 : (MATH == SYM_FAST ? kExpTabFast : kExpTab)];
+        double2 xy[2 * THREADS], zq[2 * THREADS], axy[THREADS];
+        double az[THREADS];
+        unsigned long long mbar;  // arrival of the table (SYM_FAST: one bulk copy)
+    };
+    __shared__ Smem sm;
+    double *const s_tab = sm.tab;
+    double2 *const sxy = sm.xy, *const szq = sm.zq, *const saxy = sm.axy;
+    double *const saz = sm.az;
     const int t = threadIdx.x;
     unsigned long long t_begin = 0;
     if (P.trace && t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
@@ -346,9 +377,17 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
         for (int k = t; k < 3 * kPolyCount; k += THREADS) s_ptab[k] = __ldg(P.ptab + k);
         tab = c_exp2_tab;
     } else if (MATH == SYM_FAST) {
-        for (int k = t; k < kExpTabFast; k += THREADS) {  // see sym_phase: the high words are biased by the index
-            const double T = c_exp2_tab_fast[k];
-            s_tab[k] = __hiloint2double(__double2hiint(T) - (k << (20 - NPSL_EXP2FAST_TB)), __double2loint(T));
+        // the 16 KB table (high words biased by the index, see sym_phase; prepared once per context, P.etab) arrives by ONE
+        // bulk asynchronous copy issued by thread 0 while all threads load their rows; a short unit (one 64-column tile,
+        // ~30 us) otherwise spends several microseconds of its life in 32 dependent load / store rounds
+        if (t == 0) {
+            const unsigned mb = (unsigned) __cvta_generic_to_shared(&sm.mbar), dst = (unsigned) __cvta_generic_to_shared(sm.tab);
+            constexpr unsigned bytes = kExpTabFast * sizeof(double);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(P.etab), "r"(bytes), "r"(mb) : "memory");
         }
     } else {
         for (int k = t; k < kExpTab; k += THREADS) s_tab[k] = c_exp2_tab[k];
@@ -372,6 +411,12 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
     const int col_begin = max(sym_chunk_tile0(P, c) * kSymCT, row0);
     const int col_end = min(sym_chunk_tile0(P, c + 1) * kSymCT, P.n);
 
+    if (MATH == SYM_FAST) {  // the table has to be there (thread 0's mbarrier.init is ordered before by the barrier)
+        __syncthreads();
+        const unsigned mb = (unsigned) __cvta_generic_to_shared(&sm.mbar);
+        asm volatile("{\n.reg .pred p;\nNPSL_TAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra NPSL_TAB_DONE;\n"
+                     "bra NPSL_TAB_WAIT;\nNPSL_TAB_DONE:\n}" ::"r"(mb) : "memory");
+    }
     if (MATH == SYM_POLY) {
         sym_unit<ROWS, THREADS, SYM_POLY, UNROLL>(row, gi, xyzq, colpart, I, row0, col_begin, col_end, sxy, szq, saxy, saz, tab, s_ptab, P, min_r2_hi, max_r2_hi);
         // a pair outside the table (or a non-finite distance): the whole unit is redone exactly
