@@ -386,21 +386,24 @@ void sym_geometry(int nv, int rb, SymParams &sp) {
     sp.n = nv;
     sp.npad = (nv + kSymPad - 1) / kSymPad * kSymPad;
     sp.rb = rb;
-    // 256 columns per unit up to 65536 vertices, at most 256 such chunks beyond: fine-grained enough to fill 8 GPUs
-    sp.chunk_tiles = std::max(256 / kSymCT, (nv + 256 * kSymCT - 1) / (256 * kSymCT));
+    // 288 columns per unit up to 73728 vertices, at most 256 such chunks beyond: fine-grained enough to fill 8 GPUs.
+    // (Measured at S64, profiles/r02_unit_geometry.txt: 288 / 192 / 32-column chunks beat 256 / 128 / 32 by 2.3 % on one GPU
+    // -- fewer partial sums to write, fewer CTAs to start -- and tie on an eighth.)
+    sp.chunk_tiles = std::max(288 / kSymCT, (nv + 256 * kSymCT - 1) / (256 * kSymCT));
     if (const char *e = getenv("NPSL_SYM_CHUNK_TILES"))  // measurement knob; changes the grouping of the row sums
         if (atoi(e) > 0) sp.chunk_tiles = atoi(e);
     const int n_tiles = (nv + kSymCT - 1) / kSymCT;
-    // The column range ends in narrower chunks: half width over its last quarter, of which the last part a quarter
-    // width (one 64-column tile at S64). Units are launched heaviest first, so these run last and even out the ragged
-    // end of the launch: a rank of an 8-GPU job at S64 has about seven tiles of work per resident CTA, a full-width unit is
-    // four. A function of the vertex count only, like everything else here.
+    // The column range ends in narrower chunks: two thirds of the width over its last quarter, of which the last part a
+    // ninth (one 32-column group at S64, both warps of a CTA on it at once). Units are launched heaviest first, so these
+    // run last and even out the ragged end of the launch: a rank of an 8-GPU job at S64 has about seven 64-column tiles
+    // of work per resident CTA, so with whole tiles a third of the CTAs does eight -- the quantum decides the end of the
+    // launch. A function of the vertex count only, like everything else here.
     int fine_pct = 25, finest_pct = 5;
     if (const char *e = getenv("NPSL_SYM_FINE_PCT")) fine_pct = std::max(0, std::min(100, atoi(e)));      // measurement knobs
     if (const char *e = getenv("NPSL_SYM_FINEST_PCT")) finest_pct = std::max(0, std::min(100, atoi(e)));
     finest_pct = std::min(finest_pct, fine_pct);
-    sp.fine_tiles = std::max(1, sp.chunk_tiles / 2);
-    sp.finest_tiles = std::max(1, sp.chunk_tiles / 4);
+    sp.fine_tiles = std::max(1, 2 * sp.chunk_tiles / 3);
+    sp.finest_tiles = std::max(1, sp.chunk_tiles / 9);
     if (const char *e = getenv("NPSL_SYM_FINE_TILES"))
         if (atoi(e) > 0) sp.fine_tiles = atoi(e);
     if (const char *e = getenv("NPSL_SYM_FINEST_TILES"))
@@ -524,7 +527,7 @@ int plan_sym(npsl_ctx *c) {
         CU(cudaMemcpy(c->pair_etab, biased.data(), sizeof(double) * biased.size(), cudaMemcpyHostToDevice));
     }
     sp.etab = c->pair_etab;
-    sp.fast_c2s = -1.4426950408889634074 * (double) kExpTabFast; sp.fast_g1 = NPSL_EXP2FAST_G1; sp.fast_g2 = NPSL_EXP2FAST_G2;
+    sp.fast_c2s = 1.4426950408889634074 * (double) kExpTabFast; sp.fast_g1 = NPSL_EXP2FAST_G1; sp.fast_g2 = NPSL_EXP2FAST_G2;
 
     const int n_rb = (nv + sp.rb - 1) / sp.rb;
     const bool want = c->pair_mode == 2 || (c->pair_mode == 0 && nv >= 4096);
@@ -578,7 +581,7 @@ int plan_sym(npsl_ctx *c) {
     c->sym_trace = nullptr;
     sp.trace = nullptr;
     if (getenv("NPSL_SYM_TRACE")) {  // measurement only: per-CTA timeline of the last k_pair_sym launch
-        CU(dalloc(&c->sym_trace, 3 * units.size() + 3));
+        CU(dalloc(&c->sym_trace, 5 * units.size() + 5));
         sp.trace = c->sym_trace;
         c->sym_trace_units = units;
     }
@@ -1311,13 +1314,13 @@ int npsl_nccl_unique_id(void *out_id) {
 void npsl_destroy(npsl_ctx *c) {
     if (!c) return;
     if (c->s_main) cudaStreamSynchronize(c->s_main);
-    if (c->sym_trace && getenv("NPSL_SYM_TRACE")) {  // "block I chunk sm start_ns end_ns" of the last launch
-        std::vector<unsigned long long> tr(3 * c->sym_trace_units.size());
+    if (c->sym_trace && getenv("NPSL_SYM_TRACE")) {  // "block I chunk sm start_ns end_ns ready_ns pairs_done_ns" of the last launch
+        std::vector<unsigned long long> tr(5 * c->sym_trace_units.size());
         if (cudaMemcpy(tr.data(), c->sym_trace, tr.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
             if (FILE *f = fopen(getenv("NPSL_SYM_TRACE"), "w")) {
                 for (size_t k = 0; k < c->sym_trace_units.size(); k++)
-                    fprintf(f, "%zu %d %d %llu %llu %llu\n", k, c->sym_trace_units[k].x, c->sym_trace_units[k].y, tr[3 * k],
-                            tr[3 * k + 1], tr[3 * k + 2]);
+                    fprintf(f, "%zu %d %d %llu %llu %llu %llu %llu\n", k, c->sym_trace_units[k].x, c->sym_trace_units[k].y, tr[5 * k],
+                            tr[5 * k + 1], tr[5 * k + 2], tr[5 * k + 3], tr[5 * k + 4]);
                 fclose(f);
             }
         }

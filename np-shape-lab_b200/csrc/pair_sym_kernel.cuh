@@ -2,7 +2,7 @@
 // FP64, sm_100a. Force-only twin of k_pair (pair_kernel.cuh) for the per-step path; it replaces the
 // same reference loop (src/newforces.cpp:153-177), which walks all N(N-1) ordered pairs.
 //
-// Work unit = (row block I of ROWS x THREADS rows) x (column chunk c of chunk_tiles x 64 columns); a unit exists
+// Work unit = (row block I of ROWS x THREADS rows) x (column chunk c of chunk_tiles x 32 columns); a unit exists
 // when the chunk reaches past the start of the row block, and it covers the pairs (i,j), i in I, j in c,
 // j > i. Each thread keeps ROWS rows in registers (position, charge, force accumulator). A THREADS-column tile is
 // staged in shared memory (SoA) together with one force accumulator per column. Within a tile the
@@ -49,11 +49,11 @@ struct SymParams {
     int finest_tiles;
     int n_chunks;
     int lj_cut_hi;
-    double fast_c2s, fast_g1, fast_g2;  // SYM_FAST: -log2(e) 2^TB and the quadratic of exp2_table_fast.inc, as kernel
+    double fast_c2s, fast_g1, fast_g2;  // SYM_FAST: +log2(e) 2^TB (applied to -r) and the quadratic of exp2_table_fast.inc, as kernel
                                         //   parameters so that they are constant-bank operands, not registers
     const double *etab;   // SYM_FAST: 2^(j/2^TB) with the high words biased by the index (k_pair_sym), 16-byte aligned
     const double2 *ptab;  // piecewise-polynomial table of the radial factor (kPoly* below), null: exact evaluation only
-    unsigned long long *trace;  // measurement only (NPSL_SYM_TRACE): per CTA {SM id, start ns, end ns}, else null
+    unsigned long long *trace;  // measurement only (NPSL_SYM_TRACE): per CTA {SM id, start, rows and table there, pairs done, end} in ns, else null
 };
 
 // Piecewise polynomial of the whole radial factor  G(s) = e^{-sqrt(s)/lambda} (s^{-3/2} + s^{-1}/lambda),  s = r^2.
@@ -72,7 +72,7 @@ constexpr int kPolyShift = 20 - kPolyBits;          // interval index = (high wo
 constexpr int kPolyBase = (1023 + kPolyEmin) << kPolyBits;
 constexpr int kPolyHiMin = kPolyBase << kPolyShift; // high words of the covered range [min, max)
 constexpr int kPolyHiMax = (kPolyBase + kPolyCount) << kPolyShift;
-constexpr int kSymCT = 64;    // granularity of the column chunks (the kernels' column tile is THREADS wide)
+constexpr int kSymCT = 32;    // granularity of the column chunks (the kernels' column tile is THREADS wide)
 // first tile of chunk c (c == n_chunks: one past the last tile, before clamping to the vertex count)
 __host__ __device__ __forceinline__ int sym_chunk_tile0(const SymParams &P, const int c) {
     if (c <= P.n_coarse) return c * P.chunk_tiles;
@@ -184,8 +184,8 @@ __device__ __forceinline__ void sym_phase(SymRow (&row)[ROWS], const int (&gi)[R
 #pragma unroll
             for (int r = 0; r < ROWS; r++) y[r] = fma(y[r] * b[r], 0.5, y[r]);  // 1/r (1 - 3/8 e^2 ...)
 #pragma unroll
-            for (int r = 0; r < ROWS; r++) a[r] = a[r] * y[r];  // r
-            double tt[ROWS], f[ROWS], T[ROWS];
+            for (int r = 0; r < ROWS; r++) a[r] = -(a[r] * y[r]);  // -r: the scale c2p = log2(e) 2^TB then is a positive
+            double tt[ROWS], f[ROWS], T[ROWS];                     // constant (an un-negated uniform operand of both FMAs)
 #pragma unroll
             for (int r = 0; r < ROWS; r++) tt[r] = fma(a[r], c2s, MAGIC);
 #pragma unroll
@@ -315,32 +315,40 @@ __device__ __forceinline__ void sym_unit(SymRow (&row)[ROWS], const int (&gi)[RO
         saxy[t] = make_double2(0.0, 0.0); saz[t] = 0.0;
         __syncthreads();
         const bool diag = j0 < row0 + RB;
+        // A tile with a single group of real columns (the 32-column chunks at the end of the column range, the smallest
+        // units of the launch): both warps take that group in ONE phase instead of taking turns; warp 1's column sums go
+        // to the slots of the empty second group and are added below in a fixed order.
+        const bool single = GROUPS == 2 && col_end - j0 <= 32;
 #pragma unroll 1
-        for (int p = 0; p < GROUPS; p++) {
-            const int o = ((warp + p) % GROUPS) * 32;
+        for (int p = 0; p < (single ? 1 : GROUPS); p++) {
+            const int o = single ? 0 : ((warp + p) % GROUPS) * 32;
+            const int oa = single ? warp * 32 : o;
             if (j0 + o < col_end) {  // whole group of padding columns: nothing to do
                 int dummy = 0;
                 if (MATH == SYM_POLY && j0 + o + 32 <= col_end) {
                     if (!diag)
-                        sym_phase<ROWS, false, SYM_POLY, UNROLL>(row, gi, j0 + o, sxy + 2 * o, szq + 2 * o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab,
+                        sym_phase<ROWS, false, SYM_POLY, UNROLL>(row, gi, j0 + o, sxy + 2 * o, szq + 2 * o, saxy + oa, saz + oa, lane, c2s, inv_lambda, tab, ptab,
                                                                  min_r2_hi, max_r2_hi);
                     else
-                        sym_phase<ROWS, true, SYM_POLY, UNROLL>(row, gi, j0 + o, sxy + 2 * o, szq + 2 * o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab,
+                        sym_phase<ROWS, true, SYM_POLY, UNROLL>(row, gi, j0 + o, sxy + 2 * o, szq + 2 * o, saxy + oa, saz + oa, lane, c2s, inv_lambda, tab, ptab,
                                                                 min_r2_hi, max_r2_hi);
                 } else {
                     if (!diag)
-                        sym_phase<ROWS, false, EXACT, UNROLL>(row, gi, j0 + o, sxy + 2 * o, szq + 2 * o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab, min_r2_hi, dummy, P.fast_g1, P.fast_g2);
+                        sym_phase<ROWS, false, EXACT, UNROLL>(row, gi, j0 + o, sxy + 2 * o, szq + 2 * o, saxy + oa, saz + oa, lane, c2s, inv_lambda, tab, ptab, min_r2_hi, dummy, P.fast_g1, P.fast_g2);
                     else
-                        sym_phase<ROWS, true, EXACT, UNROLL>(row, gi, j0 + o, sxy + 2 * o, szq + 2 * o, saxy + o, saz + o, lane, c2s, inv_lambda, tab, ptab, min_r2_hi, dummy, P.fast_g1, P.fast_g2);
+                        sym_phase<ROWS, true, EXACT, UNROLL>(row, gi, j0 + o, sxy + 2 * o, szq + 2 * o, saxy + oa, saz + oa, lane, c2s, inv_lambda, tab, ptab, min_r2_hi, dummy, P.fast_g1, P.fast_g2);
                 }
             }
             __syncthreads();
         }
         if (j < col_end) {
+            double2 axy = saxy[t];
+            double az = saz[t];
+            if (single) { axy.x += saxy[t + 32].x; axy.y += saxy[t + 32].y; az += saz[t + 32]; }
             double *cp = colpart + (size_t) I * 3 * P.npad + j;
-            cp[0] = saxy[t].x * out_scale;
-            cp[P.npad] = saxy[t].y * out_scale;
-            cp[2 * (size_t) P.npad] = saz[t] * out_scale;
+            cp[0] = axy.x * out_scale;
+            cp[P.npad] = axy.y * out_scale;
+            cp[2 * (size_t) P.npad] = az * out_scale;
         }
     }
 #pragma unroll
@@ -411,12 +419,14 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
     const int col_begin = max(sym_chunk_tile0(P, c) * kSymCT, row0);
     const int col_end = min(sym_chunk_tile0(P, c + 1) * kSymCT, P.n);
 
+    unsigned long long t_ready = 0, t_done = 0;
     if (MATH == SYM_FAST) {  // the table has to be there (thread 0's mbarrier.init is ordered before by the barrier)
         __syncthreads();
         const unsigned mb = (unsigned) __cvta_generic_to_shared(&sm.mbar);
         asm volatile("{\n.reg .pred p;\nNPSL_TAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra NPSL_TAB_DONE;\n"
                      "bra NPSL_TAB_WAIT;\nNPSL_TAB_DONE:\n}" ::"r"(mb) : "memory");
     }
+    if (P.trace && t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ready));
     if (MATH == SYM_POLY) {
         sym_unit<ROWS, THREADS, SYM_POLY, UNROLL>(row, gi, xyzq, colpart, I, row0, col_begin, col_end, sxy, szq, saxy, saz, tab, s_ptab, P, min_r2_hi, max_r2_hi);
         // a pair outside the table (or a non-finite distance): the whole unit is redone exactly
@@ -425,6 +435,7 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
     } else {
         sym_unit<ROWS, THREADS, MATH, UNROLL>(row, gi, xyzq, colpart, I, row0, col_begin, col_end, sxy, szq, saxy, saz, tab, s_ptab, P, min_r2_hi, max_r2_hi);
     }
+    if (P.trace && t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_done));
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
         if (gi[r] < P.n) {
@@ -442,9 +453,11 @@ k_pair_sym(const double4 *__restrict__ xyzq, const int2 *__restrict__ units, dou
             unsigned int smid;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            P.trace[3 * blockIdx.x] = smid;
-            P.trace[3 * blockIdx.x + 1] = t_begin;
-            P.trace[3 * blockIdx.x + 2] = t_end;
+            P.trace[5 * blockIdx.x] = smid;
+            P.trace[5 * blockIdx.x + 1] = t_begin;
+            P.trace[5 * blockIdx.x + 2] = t_end;
+            P.trace[5 * blockIdx.x + 3] = t_ready;
+            P.trace[5 * blockIdx.x + 4] = t_done;
         }
     }
 }

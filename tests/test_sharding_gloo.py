@@ -156,7 +156,7 @@ def test_symmetric_units_cover_every_pair_exactly_once_on_any_rank_count(n):
     from np_shape_lab_b200 import capi
     all_units, geo1 = capi.plan_pair_units(n, 0, 1)
     rb = geo1["rows_per_block"]
-    assert rb == 6 * 64 and geo1["column_granularity"] == 64  # default shape of k_pair_sym: 6 rows x 64 threads
+    assert rb == 6 * 64 and geo1["column_granularity"] == 32  # default shape of k_pair_sym: 6 rows x 64 threads
     assert _pair_count(all_units.tolist(), n, rb) == n * (n - 1) // 2
     keys1 = sorted((int(u[0]), int(u[1])) for u in all_units)
     assert len(set(keys1)) == len(keys1)

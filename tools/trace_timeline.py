@@ -30,6 +30,8 @@ with capi.Context(w.mesh.edges, w.mesh.faces, w.params["l0"], P, n_vertices=w.n_
     ctx.sync()
 tr = np.loadtxt(path)
 os.unlink(path)
+if os.environ.get("NPSL_TRACE_KEEP"):  # raw rows + the units' widths for offline analysis
+    np.save(os.environ["NPSL_TRACE_KEEP"], np.concatenate([tr, (units[: len(tr), 3] - units[: len(tr), 2])[:, None]], axis=1))
 sm, t0, t1 = tr[:, 3].astype(int), tr[:, 4], tr[:, 5]
 begin, end = t0.min(), t1.max()
 t0, t1 = (t0 - begin) * 1e-3, (t1 - begin) * 1e-3  # us
@@ -38,10 +40,13 @@ cols = (units[:, 3] - units[:, 2])[: len(t0)]
 tiles = np.ceil(cols / geo["column_granularity"]).astype(int)
 print("%s, rank %d of %d: %d units, %d tiles, launch span %.1f us (first CTA start to last CTA end)" % (
     name, rank, world, len(t0), tiles.sum(), span))
+pro, epi = (tr[:, 6] - tr[:, 4]) * 1e-3, (tr[:, 5] - tr[:, 7]) * 1e-3  # start -> rows + table there; pairs done -> end
 for k in sorted(set(tiles)):
-    d = (t1 - t0)[tiles == k]
-    print("  units of %d tile(s): %5d, duration median %.1f us (min %.1f, max %.1f), %.2f us per tile" % (
-        k, len(d), np.median(d), d.min(), d.max(), np.median(d) / k))
+    m = tiles == k
+    d = (t1 - t0)[m]
+    print("  units of %d tile(s): %5d, duration median %.1f us (min %.1f, max %.1f), %.2f us per tile; prologue median %.2f us "
+          "(max %.2f), epilogue median %.2f us (max %.2f)" % (k, len(d), np.median(d), d.min(), d.max(), np.median(d) / k,
+                                                          np.median(pro[m]), pro[m].max(), np.median(epi[m]), epi[m].max()))
 # resident CTAs over time
 ev = np.concatenate([np.stack([t0, np.ones_like(t0)], 1), np.stack([t1, -np.ones_like(t1)], 1)])
 ev = ev[np.argsort(ev[:, 0], kind="stable")]
@@ -52,6 +57,20 @@ print("  peak resident CTAs %d; CTA-time used %.0f us = %.1f %% of peak x span" 
 for frac in (1.0, 0.75, 0.5, 0.25):
     k = np.where(act >= frac * peak)[0]
     print("  >= %3.0f %% of the peak resident from %.1f to %.1f us" % (100 * frac, ev[k[0], 0], ev[k[-1] + 1, 0] if k[-1] + 1 < len(ev) else span))
+# gap between a CTA's end and the start of the CTA that takes its place on the same SM (block scheduler + resource hand-over)
+gaps = []
+for sidx in np.unique(sm):
+    m = np.where(sm == sidx)[0]
+    starts = np.sort(t0[m])
+    ends = np.sort(t1[m])
+    later = starts[starts > 1.0]  # replacements (the first wave starts at 0)
+    for k, st in enumerate(later):
+        if k < len(ends) and ends[k] <= st:
+            gaps.append(st - ends[k])
+gaps = np.array(gaps)
+if len(gaps):
+    print("  hand-over on an SM (k-th CTA to end -> k-th replacement to start): median %.2f us, 90th percentile %.2f us, %d hand-overs"
+          % (np.median(gaps), np.percentile(gaps, 90), len(gaps)))
 per_sm_end = np.array([t1[sm == s].max() for s in np.unique(sm)])
 per_sm_busy = np.array([np.sum((t1 - t0)[sm == s]) for s in np.unique(sm)])
 print("  per SM: last CTA ends at %.1f .. %.1f us (median %.1f); CTA-time per SM %.0f .. %.0f us" % (
