@@ -718,6 +718,7 @@ int issue(npsl_ctx *c, bool step, bool energy, bool store, bool time_pair, bool 
 #define KEY(M, U, R, T, TIGHT) ((((M) * 10 + (U)) * 10 + (R)) * 10000 + (T) * 10 + (TIGHT))
             switch (key) {
                 case KEY(SYM_FAST, 1, 6, 64, 0): SYM_LAUNCH(6, 64, 4, SYM_FAST, 1, 0); break;
+                case KEY(SYM_FAST, 1, 6, 32, 0): SYM_LAUNCH(6, 32, 8, SYM_FAST, 1, 0); break;
                 case KEY(SYM_FAST, 1, 6, 128, 0): SYM_LAUNCH(6, 128, 2, SYM_FAST, 1, 0); break;
                 case KEY(SYM_FAST, 1, 6, 256, 0): SYM_LAUNCH(6, 256, 1, SYM_FAST, 1, 0); break;
                 case KEY(SYM_FAST, 1, 4, 128, 0): SYM_LAUNCH(4, 128, 3, SYM_FAST, 1, 0); break;
@@ -1981,7 +1982,7 @@ int npsl_set_pair_plan(npsl_ctx *c, int rows_per_thread, int col_splits) {
     if (c->use_sym) {  // measurement knob for the symmetric kernel: (rows per thread, threads per CTA [+1: tighter register cap])
         if (rows_per_thread) c->sym_rows = rows_per_thread;
         c->sym_shape_set = true;
-        if (col_splits >= 64) { c->sym_threads = col_splits & ~1; c->sym_minb = (col_splits & 1) ? 8 : 0; }
+        if (col_splits >= 32) { c->sym_threads = col_splits & ~1; c->sym_minb = (col_splits & 1) ? 8 : 0; }
         c->plan_rows = c->plan_splits = 0;
         plan_pair(c, c->n_sm);
         int r = plan_sym(c);
