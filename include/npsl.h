@@ -220,6 +220,12 @@ int npsl_constraint_multipliers(npsl_ctx *ctx, double *shake_lambda, double *rat
  * npsl_pair_math: how the context's symmetric pair kernel evaluates G -- 0 rsqrt / exp to 3e-16, 1 the table, 2 the
  * reduced-accuracy exact scheme (csrc/pair_sym_kernel.cuh; environment NPSL_SYM_MATH overrides the default). */
 int npsl_pair_poly_eval(double inv_kappa_out, const double *s, double *table_value, double *exact_value, int n);
+/* The default evaluation (npsl_pair_math == 2) restated on the host, operation for operation: s[i] = r^2 in units of
+ * lambda^2 (the kernel pre-scales the coordinates); value = e^{-r} (1/r^3 + 1/r^2) as the device computes it from a
+ * reciprocal-square-root seed cut to seed_bits mantissa bits (the device's MUFU.RSQ64H seed is better than 20 bits),
+ * exact_value = the extended-precision value. Pins the scheme's error budget (< 2e-12 against the path's 1e-10), the
+ * index-biased exponent table and the polynomial constants without a GPU. Either output may be NULL. */
+int npsl_pair_fast_eval(const double *s, double *value, double *exact_value, int n, int seed_bits);
 int npsl_pair_math(const npsl_ctx *ctx);
 /* Shape of the pair kernel in use (rows per thread, threads per CTA) and the FP64-pipe instructions it executes per
  * pair evaluation, as counted in the SASS of its inner loop (tools/sass_loops.py): per UNORDERED pair for the symmetric

@@ -26,7 +26,7 @@ SYMBOLS = [
     "npsl_download_mesh_fields", "npsl_get_thermostat", "npsl_set_thermostat", "npsl_dressup", "npsl_force_init",
     "npsl_force", "npsl_step", "npsl_energy", "npsl_sync", "npsl_launch_count", "npsl_pair_timing",
     "npsl_pair_timing_read", "npsl_owned_rows", "npsl_pair_geometry", "npsl_fp64_peak", "npsl_md_run",
-    "npsl_step_timing", "npsl_step_timing_list", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_pair_poly_eval", "npsl_pair_math", "npsl_pair_kernel_info", "npsl_md_step_host", "npsl_host_state", "npsl_md_step_packed", "npsl_set_pair_mode",
+    "npsl_step_timing", "npsl_step_timing_list", "npsl_set_pair_plan", "npsl_force_calculation", "npsl_pair_poly_eval", "npsl_pair_fast_eval", "npsl_pair_math", "npsl_pair_kernel_info", "npsl_md_step_host", "npsl_host_state", "npsl_md_step_packed", "npsl_set_pair_mode",
     "npsl_pair_mode", "npsl_exchange_mode", "npsl_shard_plan", "npsl_vertex_geometry", "npsl_local_energies", "npsl_step_profile", "npsl_set_volume_constraint", "npsl_constraint_init",
     "npsl_constraint_multipliers", "npsl_set_ions", "npsl_download_ions", "npsl_plan_pair_units",
 ]
@@ -115,6 +115,7 @@ def load() -> C.CDLL:
     L.npsl_md_step_host.argtypes = [vp, dp, dp, dp, C.c_int, dp]
     L.npsl_host_state.argtypes = [vp] + [C.POINTER(dp)] * 4
     L.npsl_pair_poly_eval.argtypes = [C.c_double, dp, dp, dp, C.c_int]
+    L.npsl_pair_fast_eval.argtypes = [dp, dp, dp, C.c_int, C.c_int]
     L.npsl_pair_math.argtypes = [vp]
     L.npsl_pair_kernel_info.argtypes = [vp, ip, ip, dp]
     L.npsl_md_step_packed.argtypes = [vp, C.c_int]
@@ -186,6 +187,18 @@ def plan_pair_units(n_vertices: int, rank: int = 0, world: int = 1):
     L.npsl_plan_pair_units(n_vertices, rank, world, units.ctypes.data_as(C.POINTER(C.c_int32)), n, None)
     return units, dict(zip(["rows_per_block", "column_granularity", "chunks", "full_chunks", "tiles_full", "tiles_half"],
                            [int(x) for x in geo]))
+
+
+def pair_fast_eval(s: np.ndarray, seed_bits: int = 20):
+    """(device-order value, extended-precision value) of e^{-r}(1/r^3 + 1/r^2) at s = r^2 (lambda units) for the default
+    reduced-accuracy scheme of k_pair_sym with a seed of seed_bits bits (npsl_pair_fast_eval; host only)."""
+    L = load()
+    s = np.ascontiguousarray(s, dtype=np.float64)
+    v, ev = np.zeros_like(s), np.zeros_like(s)
+    st = L.npsl_pair_fast_eval(_dp(s), _dp(v), _dp(ev), int(s.size), int(seed_bits))
+    if st != 0:
+        raise NpslError(st, "npsl_pair_fast_eval")
+    return v, ev
 
 
 def nccl_unique_id() -> bytes:

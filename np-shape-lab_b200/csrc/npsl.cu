@@ -2115,6 +2115,52 @@ int npsl_pair_poly_eval(double inv_kappa_out, const double *s, double *table_val
     return NPSL_OK;
 }
 
+// The default radial-factor evaluation of k_pair_sym (SYM_FAST, pair_sym_kernel.cuh), operation for operation on the host:
+// s = r^2 in units of lambda^2. The device's rsqrt seed comes from MUFU.RSQ64H (not available here): it is modelled as
+// 1/sqrt(s) cut to seed_bits mantissa bits, so the test can bound the scheme's error for any seed at least that good.
+int npsl_pair_fast_eval(const double *s, double *value, double *exact_value, int n, int seed_bits) {
+    npsl_ctx *c = nullptr;
+    if (!s || n < 0 || seed_bits < 8 || seed_bits > 52) return fail(c, NPSL_ERR_ARG, "bad argument");
+    static const double tab[kExpTabFast] = {NPSL_EXP2FAST_TABLE};
+    const double MAGIC = 6755399441055744.0, c2p = 1.4426950408889634074 * (double) kExpTabFast;
+    for (int i = 0; i < n; i++) {
+        const double a = s[i];
+        if (value) {
+            double y0 = (double) (1.0L / sqrtl((long double) a));
+            uint64_t yb;
+            memcpy(&yb, &y0, 8);
+            yb &= ~((uint64_t(1) << (52 - seed_bits)) - 1);
+            memcpy(&y0, &yb, 8);
+            const double b = a * y0;
+            const double e = fma(-b, y0, 1.0);
+            const double y = fma(y0 * e, 0.5, y0);
+            const double rn = -(a * y);
+            const double tt = fma(rn, c2p, MAGIC);
+            const double f = fma(rn, c2p, -(tt - MAGIC));
+            uint64_t tb;
+            memcpy(&tb, &tt, 8);
+            const int32_t nn = (int32_t) (uint32_t) tb;  // low word: round(-r log2(e) 2^TB)
+            const int j = nn & (kExpTabFast - 1);
+            uint64_t Tb;
+            memcpy(&Tb, &tab[j], 8);
+            Tb -= (uint64_t) j << (32 + 20 - NPSL_EXP2FAST_TB);            // the staged table (plan_sym)
+            const uint32_t hi = (uint32_t) (Tb >> 32) + (uint32_t) (nn * (1 << (20 - NPSL_EXP2FAST_TB)));  // one multiply-add
+            Tb = ((uint64_t) hi << 32) | (Tb & 0xffffffffu);
+            double T;
+            memcpy(&T, &Tb, 8);
+            const double g = fma(f, NPSL_EXP2FAST_G2, NPSL_EXP2FAST_G1);
+            const double ex = fma(T, f * g, T);
+            const double y2 = y * y;
+            value[i] = ex * fma(y2, y, y2);
+        }
+        if (exact_value) {
+            const long double r = sqrtl((long double) a);
+            exact_value[i] = (double) (expl(-r) * (1.0L / (r * r * r) + 1.0L / (r * r)));
+        }
+    }
+    return NPSL_OK;
+}
+
 int npsl_pair_kernel_info(const npsl_ctx *c, int32_t *rows_per_thread, int32_t *threads, double *fp64_instr_per_pair) {
     if (!c) return NPSL_ERR_ARG;
     if (!c->use_sym) {  // ordered kernel: SASS count of k_pair's inner loop, per ordered pair (pair_kernel.cuh)

@@ -51,3 +51,24 @@ def test_table_is_continuous_across_interval_edges():
     u = np.sqrt(edge) / lam
     jump = np.abs(tv_hi - tv_lo) / tv_hi
     assert jump[u <= 4].max() < 2e-11 and jump.max() < 3e-10
+
+
+def test_reduced_accuracy_scheme_error_budget():
+    """The DEFAULT evaluation of k_pair_sym (second-order rsqrt correction, 2048-entry index-biased 2^(j/2048) table,
+    quadratic, exponent added by one integer multiply-add), restated operation for operation on the host
+    (npsl_pair_fast_eval): relative error of e^{-r}(1/r^3 + 1/r^2) against extended precision, for a seed no better than
+    20 bits (the device's MUFU.RSQ64H seed is better). The error of e^{-r} grows like r x (error of r), so the bound is
+    stated as rel / (1 + r); what matters for a force is the error weighted with the size of the term, far below 1e-12
+    of the largest term everywhere. The contract of the path is 1e-10."""
+    rng = np.random.default_rng(0)
+    r = np.concatenate([10.0 ** rng.uniform(-2, 1, 200000), np.linspace(0.01, 700.0, 200000)])
+    for bits, bound in ((20, 5e-12), (22, 8e-13)):
+        v, e = capi.pair_fast_eval(r * r, bits)
+        assert np.isfinite(v).all() and (v > 0).all()
+        rel = np.abs(v - e) / e
+        assert (rel / (1.0 + r)).max() < bound, (bits, (rel / (1.0 + r)).max())
+        far = r >= 1.0
+        assert np.abs(v - e)[far].max() < 1e-12 * 2.0 * np.exp(-1.0)  # weighted with the term's size, against G(1)
+    # the exponent path: k = n >> 11 down to about -1000 (r = 700 lambda) through the biased table, still a normal number
+    v, e = capi.pair_fast_eval(np.array([690.0 ** 2, 700.0 ** 2]), 24)
+    assert np.all(np.abs(v - e) / e < 1e-9) and np.all(v > 0)
