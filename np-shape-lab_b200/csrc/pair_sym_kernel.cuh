@@ -5,19 +5,22 @@
 // Work unit = (row block I of ROWS x THREADS rows) x (column chunk c of chunk_tiles x 32 columns); a unit exists
 // when the chunk reaches past the start of the row block, and it covers the pairs (i,j), i in I, j in c,
 // j > i. Each thread keeps ROWS rows in registers (position, charge, force accumulator). A THREADS-column tile is
-// staged in shared memory (SoA) together with one force accumulator per column. Within a tile the
-// warps work on the 32-column groups, rotating groups between phases; inside a phase lane l
-// visits column (l + s) mod 32 at step s, so at any time every column is touched by exactly one thread:
-// the column accumulators need no atomics and receive their contributions in a fixed order.
+// staged in shared memory as 16-byte pairs (x,y), (z,q), every group of 32 columns twice in a row. Within a tile the
+// warps work on the 32-column groups, rotating groups between phases; inside a phase lane l visits column
+// (l + s) mod 32 at step s, and the column's force accumulator travels with the column through registers (lane l hands
+// it to lane l - 1 after its step): at any time every column is touched by exactly one thread, so the column sums
+// need no atomics and receive their contributions in a fixed order.
 //   row partials    rowpart[c][k][i]   sum over the columns of chunk c        (k = x,y,z)
 //   column partials colpart[I][k][j]   minus the sum over the rows of block I
 // k_pair_reduce then adds, per vertex, the partials of each of 8 "virtual ranks" (a fixed function of the
 // row block) in a fixed order, and k_vertex adds the 8 results: the value does not depend on which GPU computed which
 // unit, so trajectories are bit-identical on 1, 2, 4 and 8 GPUs.
 //
-// FP64-pipe work per unordered pair: 31.75 instructions (19 for r, 1/r, exp; 4 for the geometry factor;
-// 2 charge products; 6 FMA into the two accumulators; 3 adds per 4 pairs for the column update)
-// = 15.9 per ordered pair, against 27 in k_pair (tools/sass_count.py).
+// FP64-pipe work per unordered pair in the default form (SYM_FAST, 6 rows x 64 threads): 28 instructions (3 sub, 3 r^2,
+// 14 for 1/r, r, exp and the radial factor, 2 charge products, 6 FMA into the two accumulators) = 14 per ordered pair,
+// against 27 in k_pair; the loop is 221 instructions per 6 pairs (tools/sass_loops.py). What bounds it is the dispatch
+// port of an SM sub-partition: every instruction of the loop that is not FP64 costs FP64 throughput,
+// and the loop is sensitive to every register (243 of 255 in use).
 #pragma once
 #include "pair_kernel.cuh"
 #include "xchg.cuh"
@@ -31,7 +34,7 @@ namespace npsl {
 //   SYM_FAST   the exact scheme with the accuracy the contract of the path does not need taken out: coordinates
 //              pre-scaled by 1/lambda (the factor becomes e^{-r}(1/r^3 + 1/r^2), one FMA less), second-order instead of
 //              third-order correction of the rsqrt seed (3/8 e^2 <= 4e-13), 2048-entry 2^(j/2048) table with a quadratic
-//              (3.2e-13): 28.75 per pair, relative error of the factor < 1e-12 against a contract of 1e-10.
+//              (3.2e-13): 28 per pair, relative error of the factor < 1e-12 against a contract of 1e-10.
 enum { SYM_EXACT = 0, SYM_POLY = 1, SYM_FAST = 2 };
 constexpr int kExpTabFast = 1 << NPSL_EXP2FAST_TB;
 constexpr int kSymPad = 512;  // partial-buffer planes are padded to a multiple of this
