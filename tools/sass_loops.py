@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "np-shape-lab_b200", "libnpsl.so")
+LIB = os.environ.get("NPSL_LIB") or os.path.join(ROOT, "np-shape-lab_b200", "libnpsl.so")
 want = sys.argv[1]
 min_fp = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 txt = subprocess.run(["cuobjdump", "-sass", LIB], stdout=subprocess.PIPE, text=True).stdout
