@@ -466,6 +466,9 @@ def run_b200(args) -> None:
             "fp64_instr_per_ordered_pair": dfma_per_ordered_pair, "ordered_pairs_per_launch": pairs_per_launch,
             "algorithmic_tflops_%dflop_per_pair" % ALGORITHMIC_FLOPS_PER_PAIR:
                 1e-12 * pairs_per_launch * ALGORITHMIC_FLOPS_PER_PAIR / (pair_ms * 1e-3) if pair_ms > 0 else None,
+            # the same against the peak: the fraction on SURVEY 8d's algorithmic count (exp and rsqrt as one flop each)
+            "algorithmic_frac": (pairs_per_launch * ALGORITHMIC_FLOPS_PER_PAIR / (pair_ms * 1e-3)) / (2.0 * dfma_peak)
+                                if pair_ms > 0 and dfma_peak else None,
             "peak_source": "pure-DFMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 entry); "
                            "nominal 148 SM x 64 DFMA/clk x %.0f MHz = %.2f TFLOP/s" %
                            (nominal_mhz, 148 * 64 * 2 * nominal_mhz * 1e-6),
