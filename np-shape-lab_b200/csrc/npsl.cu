@@ -386,24 +386,24 @@ void sym_geometry(int nv, int rb, SymParams &sp) {
     sp.n = nv;
     sp.npad = (nv + kSymPad - 1) / kSymPad * kSymPad;
     sp.rb = rb;
-    // 288 columns per unit up to 73728 vertices, at most 256 such chunks beyond: fine-grained enough to fill 8 GPUs.
-    // (Measured at S64, profiles/r02_unit_geometry.txt: 288 / 192 / 32-column chunks beat 256 / 128 / 32 by 2.3 % on one GPU
-    // -- fewer partial sums to write, fewer CTAs to start -- and tie on an eighth.)
-    sp.chunk_tiles = std::max(288 / kSymCT, (nv + 256 * kSymCT - 1) / (256 * kSymCT));
+    // 256 columns per unit up to 65536 vertices, at most 256 such chunks beyond: fine-grained enough to fill 8 GPUs.
+    sp.chunk_tiles = std::max(256 / kSymCT, (nv + 256 * kSymCT - 1) / (256 * kSymCT));
     if (const char *e = getenv("NPSL_SYM_CHUNK_TILES"))  // measurement knob; changes the grouping of the row sums
         if (atoi(e) > 0) sp.chunk_tiles = atoi(e);
     const int n_tiles = (nv + kSymCT - 1) / kSymCT;
-    // The column range ends in narrower chunks: two thirds of the width over its last quarter, of which the last part a
-    // ninth (one 32-column group at S64, both warps of a CTA on it at once). Units are launched heaviest first, so these
+    // The column range ends in narrower chunks: half width over its last 12 %, of which the last quarter an eighth of the
+    // width (one 32-column group at S64, both warps of a CTA on it at once). Units are launched heaviest first, so these
     // run last and even out the ragged end of the launch: a rank of an 8-GPU job at S64 has about seven 64-column tiles
-    // of work per resident CTA, so with whole tiles a third of the CTAs does eight -- the quantum decides the end of the
-    // launch. A function of the vertex count only, like everything else here.
-    int fine_pct = 25, finest_pct = 5;
+    // of work per resident CTA. The mix was chosen by measurement on one GPU playing one rank of 8 and on the full
+    // launch (profiles/r02_unit_geometry.txt): a CTA that arrives beside an older CTA on its SM sub-partitions runs at
+    // half speed until the older one leaves (21 against 9.8 us per 32 columns), so a mid-sized unit dispatched late is what
+    // ends a rank's launch -- few mid-sized units, many small ones. A function of the vertex count only, like everything here.
+    int fine_pct = 12, finest_pct = 3;
     if (const char *e = getenv("NPSL_SYM_FINE_PCT")) fine_pct = std::max(0, std::min(100, atoi(e)));      // measurement knobs
     if (const char *e = getenv("NPSL_SYM_FINEST_PCT")) finest_pct = std::max(0, std::min(100, atoi(e)));
     finest_pct = std::min(finest_pct, fine_pct);
-    sp.fine_tiles = std::max(1, 2 * sp.chunk_tiles / 3);
-    sp.finest_tiles = std::max(1, sp.chunk_tiles / 9);
+    sp.fine_tiles = std::max(1, sp.chunk_tiles / 2);
+    sp.finest_tiles = std::max(1, sp.chunk_tiles / 8);
     if (const char *e = getenv("NPSL_SYM_FINE_TILES"))
         if (atoi(e) > 0) sp.fine_tiles = atoi(e);
     if (const char *e = getenv("NPSL_SYM_FINEST_TILES"))
